@@ -1,0 +1,258 @@
+"""ctypes binding of libaos_gpu.so (include/aos_gpu.h).
+
+This is plumbing for the tests and bench.py; the product is the C-ABI library.  There is NO CPU
+fallback: if the library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libaos_gpu.so")
+
+AOS_MEM_HOST, AOS_MEM_DEVICE = 0, 1
+GRID_RAW, GRID_INFLATED, GRID_OCCUPANCY, GRID_OPENED, GRID_SKELETON, GRID_SKELETON_FRAMED = range(6)
+FMT_INT8, FMT_BITS = 0, 1
+
+EXPORTED_SYMBOLS = [
+    "aos_create", "aos_destroy", "aos_last_error", "aos_version", "aos_set_stream", "aos_synchronize",
+    "aos_bits_pitch_words", "aos_grid_geometry", "aos_seed_stage", "aos_seed_summary_get", "aos_get_grid",
+    "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
+    "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
+]
+
+
+class AosError(RuntimeError):
+    pass
+
+
+class CSeedParams(C.Structure):
+    _fields_ = [
+        ("clipping_minz", C.c_float), ("clipping_maxz", C.c_float),
+        ("clipping_minx", C.c_float), ("clipping_maxx", C.c_float),
+        ("clipping_miny", C.c_float), ("clipping_maxy", C.c_float),
+        ("grid_resolution", C.c_float), ("inflation_radius", C.c_float),
+        ("cluster_min_length", C.c_double),
+        ("n_polygon", C.c_int32), ("polygon", C.POINTER(C.c_double)),
+        ("n_exclusion", C.c_int32), ("exclusion", C.POINTER(C.c_float)),
+    ]
+
+
+class CGridInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("resolution", C.c_float),
+                ("origin_x", C.c_double), ("origin_y", C.c_double)]
+
+
+class CCluster(C.Structure):
+    _fields_ = [("label", C.c_int32), ("size", C.c_int32), ("center_x", C.c_float), ("center_y", C.c_float),
+                ("length", C.c_float), ("reserved", C.c_int32), ("sum_x", C.c_int64), ("sum_y", C.c_int64),
+                ("max_d2", C.c_int64)]
+
+
+class CTreeRow(C.Structure):
+    _fields_ = [("center_x", C.c_double), ("center_y", C.c_double), ("start_x", C.c_double), ("start_y", C.c_double),
+                ("end_x", C.c_double), ("end_y", C.c_double), ("length", C.c_double), ("cluster", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class CSeedSummary(C.Structure):
+    _fields_ = [("info", CGridInfo), ("n_clusters", C.c_int32), ("n_rows", C.c_int32),
+                ("thinning_launches", C.c_int32), ("thinning_subiters", C.c_int32), ("n_points_in", C.c_int64)]
+
+
+CLUSTER_DTYPE = np.dtype([("label", "<i4"), ("size", "<i4"), ("center_x", "<f4"), ("center_y", "<f4"),
+                          ("length", "<f4"), ("reserved", "<i4"), ("sum_x", "<i8"), ("sum_y", "<i8"),
+                          ("max_d2", "<i8")])
+ROW_DTYPE = np.dtype([("center_x", "<f8"), ("center_y", "<f8"), ("start_x", "<f8"), ("start_y", "<f8"),
+                      ("end_x", "<f8"), ("end_y", "<f8"), ("length", "<f8"), ("cluster", "<i4"), ("reserved", "<i4")])
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libaos_gpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AosError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz = C.c_void_p, C.c_int32, C.c_size_t
+    L.aos_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.aos_destroy.argtypes = [vp]
+    L.aos_destroy.restype = None
+    L.aos_last_error.argtypes = [vp]
+    L.aos_last_error.restype = C.c_char_p
+    L.aos_version.restype = C.c_char_p
+    L.aos_set_stream.argtypes = [vp, vp]
+    L.aos_synchronize.argtypes = [vp]
+    L.aos_bits_pitch_words.argtypes = [i32]
+    L.aos_grid_geometry.argtypes = [C.POINTER(CSeedParams), C.POINTER(CGridInfo)]
+    L.aos_seed_stage.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    L.aos_seed_summary_get.argtypes = [vp, C.POINTER(CSeedSummary)]
+    L.aos_get_grid.argtypes = [vp, C.c_int, C.c_int, vp, sz, C.c_int]
+    L.aos_grid_device_bits.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i32)]
+    L.aos_get_labels.argtypes = [vp, vp, sz, C.c_int]
+    L.aos_get_clusters.argtypes = [vp, vp, i32, C.POINTER(i32)]
+    L.aos_get_tree_rows.argtypes = [vp, vp, i32, C.POINTER(i32)]
+    L.aos_inflate_bits.argtypes = [vp, vp, vp, vp, i32, i32, i32]
+    L.aos_open_bits.argtypes = [vp, vp, vp, i32, i32]
+    L.aos_thin_bits.argtypes = [vp, vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.aos_pack_int8.argtypes = [vp, vp, C.c_int, vp, i32, i32]
+    L.aos_unpack_int8.argtypes = [vp, vp, vp, C.c_int, i32, i32]
+    _lib = L
+    return L
+
+
+@dataclass
+class SeedParams:
+    """aos_seed_gen_node parameters (config/aos_planner_params.yaml names and defaults)."""
+    clipping_minz: float = -0.4
+    clipping_maxz: float = 0.5
+    clipping_minx: float = -5.0
+    clipping_maxx: float = 72.0
+    clipping_miny: float = -10.0
+    clipping_maxy: float = 20.0
+    grid_resolution: float = 0.05
+    inflation_radius: float = 0.8
+    cluster_min_length: float = 2.0
+    polygon: np.ndarray = field(default_factory=lambda: np.zeros((0, 2)))
+    exclusion: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+
+    def to_c(self) -> CSeedParams:
+        poly = np.ascontiguousarray(self.polygon, dtype=np.float64).reshape(-1, 2)
+        excl = np.ascontiguousarray(self.exclusion, dtype=np.float32).reshape(-1, 3)
+        p = CSeedParams(self.clipping_minz, self.clipping_maxz, self.clipping_minx, self.clipping_maxx,
+                        self.clipping_miny, self.clipping_maxy, self.grid_resolution, self.inflation_radius,
+                        self.cluster_min_length, len(poly), poly.ctypes.data_as(C.POINTER(C.c_double)), len(excl),
+                        excl.ctypes.data_as(C.POINTER(C.c_float)))
+        p._keep = (poly, excl)
+        return p
+
+
+def grid_geometry(params: SeedParams) -> CGridInfo:
+    gi = CGridInfo()
+    rc = load().aos_grid_geometry(C.byref(params.to_c()), C.byref(gi))
+    if rc != 0:
+        raise AosError(f"aos_grid_geometry -> {rc}")
+    return gi
+
+
+class Context:
+    """One libaos_gpu context (device buffers are reused call after call)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.aos_create(device, C.byref(h))
+        if rc != 0:
+            raise AosError(f"aos_create(device={device}) -> {rc} (no CUDA device? this library has no CPU path)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.aos_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise AosError(f"{what} -> {rc}: {self.L.aos_last_error(self.h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self.L.aos_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "aos_set_stream")
+
+    def synchronize(self):
+        self._check(self.L.aos_synchronize(self.h), "aos_synchronize")
+
+    # ---- seed stage -------------------------------------------------------------------------
+    def seed_stage(self, params: SeedParams, points, n_points=None, point_step=None, offsets=(0, 4, 8)):
+        """points: numpy float32 [N, k] (host) or an object with data_ptr() (torch CUDA tensor, [N, k] float32)."""
+        cp = params.to_c()
+        if hasattr(points, "data_ptr"):
+            ptr, mem = points.data_ptr(), AOS_MEM_DEVICE
+            n = points.shape[0] if n_points is None else n_points
+            step = points.stride(0) * points.element_size() if point_step is None else point_step
+            self._keep_points = points
+        else:
+            pts = np.ascontiguousarray(points)
+            ptr, mem = pts.ctypes.data, AOS_MEM_HOST
+            n = pts.shape[0] if n_points is None else n_points
+            step = pts.strides[0] if point_step is None else point_step
+            self._keep_points = pts
+        rc = self.L.aos_seed_stage(self.h, C.byref(cp), C.c_void_p(ptr), n, step, offsets[0], offsets[1], offsets[2], mem)
+        self._check(rc, "aos_seed_stage")
+        return self.seed_summary()
+
+    def seed_summary(self) -> CSeedSummary:
+        s = CSeedSummary()
+        self._check(self.L.aos_seed_summary_get(self.h, C.byref(s)), "aos_seed_summary_get")
+        return s
+
+    def grid_int8(self, which: int) -> np.ndarray:
+        s = self.seed_summary()
+        out = np.empty((s.info.height, s.info.width), np.int8)
+        self._check(self.L.aos_get_grid(self.h, which, FMT_INT8, out.ctypes.data_as(C.c_void_p), out.nbytes, AOS_MEM_HOST),
+                    "aos_get_grid")
+        return out
+
+    def grid_bits(self, which: int) -> np.ndarray:
+        s = self.seed_summary()
+        pitch = self.L.aos_bits_pitch_words(s.info.width)
+        out = np.empty((s.info.height, pitch), np.uint32)
+        self._check(self.L.aos_get_grid(self.h, which, FMT_BITS, out.ctypes.data_as(C.c_void_p), out.nbytes, AOS_MEM_HOST),
+                    "aos_get_grid")
+        return out
+
+    def grid_device_bits(self, which: int):
+        p = C.c_void_p()
+        pitch = C.c_int32()
+        self._check(self.L.aos_grid_device_bits(self.h, which, C.byref(p), C.byref(pitch)), "aos_grid_device_bits")
+        return p.value, pitch.value
+
+    def labels(self) -> np.ndarray:
+        s = self.seed_summary()
+        out = np.empty((s.info.height, s.info.width), np.int32)
+        self._check(self.L.aos_get_labels(self.h, out.ctypes.data_as(C.c_void_p), out.size, AOS_MEM_HOST), "aos_get_labels")
+        return out
+
+    def clusters(self) -> np.ndarray:
+        n = C.c_int32()
+        self._check(self.L.aos_get_clusters(self.h, None, 0, C.byref(n)), "aos_get_clusters")
+        out = np.zeros(n.value, CLUSTER_DTYPE)
+        if n.value:
+            self._check(self.L.aos_get_clusters(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_clusters")
+        return out
+
+    def tree_rows(self) -> np.ndarray:
+        n = C.c_int32()
+        self._check(self.L.aos_get_tree_rows(self.h, None, 0, C.byref(n)), "aos_get_tree_rows")
+        out = np.zeros(n.value, ROW_DTYPE)
+        if n.value:
+            self._check(self.L.aos_get_tree_rows(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_tree_rows")
+        return out
+
+
+def unpack_bits(bits: np.ndarray, width: int) -> np.ndarray:
+    """Host-side view of an AOS_FMT_BITS grid as bool [H, W] (test helper)."""
+    b = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")
+    return b[:, :width].astype(bool)
+
+
+def pack_bits(img: np.ndarray) -> np.ndarray:
+    """bool/0-1 [H, W] -> uint32 [H, pitch] in the library's bit layout (test helper)."""
+    h, w = img.shape
+    pitch = (((w + 31) >> 5) + 3) & ~3
+    pad = np.zeros((h, pitch * 32), np.uint8)
+    pad[:, :w] = img != 0
+    return np.packbits(pad, axis=1, bitorder="little").view(np.uint32).reshape(h, pitch)

@@ -1,0 +1,399 @@
+// aos_api.cu -- the C-ABI of libaos_gpu (include/aos_gpu.h): context, the seed-gen stage pipeline
+// (processPointCloud, src/aos_seed_gen_node.cpp:452-579) and the getters.
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+
+#include "aos_common.cuh"
+
+using namespace aos;
+
+struct aos_ctx : public aos::Ctx {};
+
+namespace {
+
+// getActiveBounds, seed_gen:874-890
+void active_bounds(const aos_seed_params *p, float *minx, float *maxx, float *miny, float *maxy) {
+  if (p->n_polygon > 0) {
+    double bx0 = p->polygon[0], bx1 = p->polygon[0], by0 = p->polygon[1], by1 = p->polygon[1];
+    for (int i = 0; i < p->n_polygon; ++i) {
+      bx0 = std::min(bx0, p->polygon[2 * i]);
+      bx1 = std::max(bx1, p->polygon[2 * i]);
+      by0 = std::min(by0, p->polygon[2 * i + 1]);
+      by1 = std::max(by1, p->polygon[2 * i + 1]);
+    }
+    const double margin = 2.5;
+    *minx = static_cast<float>(bx0 - margin);
+    *maxx = static_cast<float>(bx1 + margin);
+    *miny = static_cast<float>(by0 - margin);
+    *maxy = static_cast<float>(by1 + margin);
+  } else {
+    *minx = p->clipping_minx;
+    *maxx = p->clipping_maxx;
+    *miny = p->clipping_miny;
+    *maxy = p->clipping_maxy;
+  }
+}
+
+// worldToGrid, seed_gen:760-769 (float result of a double expression, floor, clamp)
+void world_to_grid(double ox, double oy, float res, int w, int h, float wx, float wy, int *gx, int *gy) {
+  float rel_x = static_cast<float>((wx - ox) / res);
+  float rel_y = static_cast<float>((wy - oy) / res);
+  *gx = static_cast<int>(floorf(rel_x));
+  *gy = static_cast<int>(floorf(rel_y));
+  *gx = std::max(0, std::min(w - 1, *gx));
+  *gy = std::max(0, std::min(h - 1, *gy));
+}
+
+aos_status check_params(aos_ctx *ctx, const aos_seed_params *p) {
+  AOS_REQUIRE(ctx, p != nullptr, "params is null");
+  AOS_REQUIRE(ctx, p->grid_resolution > 0.f && std::isfinite(p->grid_resolution), "grid_resolution must be > 0");
+  AOS_REQUIRE(ctx, p->n_polygon >= 0 && p->n_polygon <= kMaxPoly, "polygon has more than 64 vertices");
+  AOS_REQUIRE(ctx, p->n_exclusion >= 0 && p->n_exclusion <= kMaxExcl, "more than 64 exclusion discs");
+  AOS_REQUIRE(ctx, p->n_polygon == 0 || p->polygon != nullptr, "polygon pointer is null");
+  AOS_REQUIRE(ctx, p->n_exclusion == 0 || p->exclusion != nullptr, "exclusion pointer is null");
+  return AOS_OK;
+}
+
+DevBuf *grid_buf(aos_ctx *c, aos_grid_id which) {
+  switch (which) {
+    case AOS_GRID_RAW: return &c->g_raw;
+    case AOS_GRID_INFLATED: return &c->g_infl;
+    case AOS_GRID_OCCUPANCY: return &c->g_occ;
+    case AOS_GRID_OPENED: return &c->g_open;
+    case AOS_GRID_SKELETON: return &c->g_skel;
+    case AOS_GRID_SKELETON_FRAMED: return &c->g_framed;
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *aos_version(void) { return "libaos_gpu 0.1 (sm_100a)"; }
+
+int32_t aos_bits_pitch_words(int32_t width) { return pitch_words_for(width); }
+
+aos_status aos_create(int device, aos_ctx **out) {
+  if (!out) return AOS_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return AOS_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return AOS_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return AOS_ERR_CUDA;
+  aos_ctx *c = new (std::nothrow) aos_ctx();
+  if (!c) return AOS_ERR_CUDA;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void **>(&c->h_flag), 64 * sizeof(int)) != cudaSuccess) {
+    delete c;
+    return AOS_ERR_CUDA;
+  }
+  c->own_stream = true;
+  *out = c;
+  return AOS_OK;
+}
+
+void aos_destroy(aos_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch,
+                    &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
+                    &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf};
+  for (DevBuf *b : bufs) b->release();
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *aos_last_error(const aos_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+aos_status aos_set_stream(aos_ctx *c, void *cuda_stream) {
+  if (!c) return AOS_ERR_INVALID;
+  if (c->own_stream && c->stream) {
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->stream);
+  }
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  c->own_stream = false;
+  return AOS_OK;
+}
+
+aos_status aos_synchronize(aos_ctx *c) {
+  if (!c) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_grid_geometry(const aos_seed_params *p, aos_grid_info *info) {
+  if (!p || !info || !(p->grid_resolution > 0.f)) return AOS_ERR_INVALID;
+  float minx, maxx, miny, maxy;
+  active_bounds(p, &minx, &maxx, &miny, &maxy);
+  // generateOccupancyGrid, seed_gen:587-600: float arithmetic
+  float width = std::max(0.0f, maxx - minx);
+  float height = std::max(0.0f, maxy - miny);
+  unsigned int w = static_cast<unsigned int>(std::ceil(width / p->grid_resolution));
+  unsigned int h = static_cast<unsigned int>(std::ceil(height / p->grid_resolution));
+  if (w == 0) w = 1;
+  if (h == 0) h = 1;
+  info->width = static_cast<int32_t>(w);
+  info->height = static_cast<int32_t>(h);
+  info->resolution = p->grid_resolution;
+  info->origin_x = minx;
+  info->origin_y = miny;
+  return AOS_OK;
+}
+
+aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points,
+                          uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  if (!c) return AOS_ERR_INVALID;
+  aos_status s = check_params(c, p);
+  if (s != AOS_OK) return s;
+  AOS_REQUIRE(c, n_points == 0 || points != nullptr, "points is null");
+  AOS_REQUIRE(c, n_points == 0 || (point_step >= 12 && off_x + 4 <= point_step && off_y + 4 <= point_step &&
+                                   off_z + 4 <= point_step),
+              "point_step / field offsets do not describe float32 x,y,z inside a record");
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->have_seed = false;
+
+  aos_grid_info gi;
+  aos_grid_geometry(p, &gi);
+  AOS_REQUIRE(c, (double)gi.width * (double)gi.height < 2.0e9, "grid has more than 2^31 cells");
+  SeedDeviceParams &P = c->P;
+  memset(&P, 0, sizeof(P));
+  active_bounds(p, &P.minx, &P.maxx, &P.miny, &P.maxy);
+  P.minz = p->clipping_minz;
+  P.maxz = p->clipping_maxz;
+  P.res = p->grid_resolution;
+  P.ox = gi.origin_x;
+  P.oy = gi.origin_y;
+  P.w = gi.width;
+  P.h = gi.height;
+  P.pitch = pitch_words_for(gi.width);
+  P.n_excl = p->n_exclusion;
+  for (int i = 0; i < 3 * p->n_exclusion; ++i) P.excl[i] = p->exclusion[i];
+  P.n_poly = p->n_polygon;
+  for (int i = 0; i < 2 * p->n_polygon; ++i) P.poly[i] = p->polygon[i];
+
+  const size_t gbytes = (size_t)P.pitch * P.h * 4;
+  DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch};
+  for (DevBuf *g : grids) AOS_CUDA_OK(c, g->reserve(gbytes));
+  AOS_CUDA_OK(c, c->misc.reserve(4096));
+  cudaStream_t st = c->stream;
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->g_raw.p, 0, gbytes, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->g_scratch.p, 0, gbytes, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->misc.p, 0, 4096, st));
+
+  const void *dpoints = points;
+  if (points_mem == AOS_MEM_HOST && n_points) {
+    AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, st));
+    dpoints = c->points_stage.p;
+  }
+  unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->misc.as<char>() + 1024);
+  s = launch_bin(c, P, dpoints, n_points, point_step, off_x, off_y, off_z, c->g_raw.as<uint32_t>(), d_kept);
+  if (s != AOS_OK) return s;
+
+  // applyInflation: int(inflation_radius / grid_resolution) in float (seed_gen:936)
+  const int R = static_cast<int>(p->inflation_radius / p->grid_resolution);
+  AOS_REQUIRE(c, R >= 0, "negative inflation radius");
+  s = launch_inflate(c, c->g_raw.as<uint32_t>(), c->g_infl.as<uint32_t>(), c->g_occ.as<uint32_t>(), P.w, P.h, R);
+  if (s != AOS_OK) return s;
+  // skeletonizeOccupancyGrid runs on the inflated grid WITHOUT the frame (seed_gen:560)
+  s = launch_open(c, c->g_infl.as<uint32_t>(), c->g_open.as<uint32_t>(), P.w, P.h);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_open.p, gbytes, cudaMemcpyDeviceToDevice, st));
+  int launches = 0, subiters = 0;
+  s = launch_thin(c, c->g_skel.as<uint32_t>(), c->g_scratch.as<uint32_t>(), P.w, P.h, &launches, &subiters);
+  if (s != AOS_OK) return s;
+
+  // markPolygonBoundaryAsOccupied (seed_gen:772-825)
+  if (p->n_polygon > 0) {
+    double bx0 = p->polygon[0], bx1 = bx0, by0 = p->polygon[1], by1 = by0;
+    for (int i = 0; i < p->n_polygon; ++i) {
+      bx0 = std::min(bx0, p->polygon[2 * i]);
+      bx1 = std::max(bx1, p->polygon[2 * i]);
+      by0 = std::min(by0, p->polygon[2 * i + 1]);
+      by1 = std::max(by1, p->polygon[2 * i + 1]);
+    }
+    const double margin = 2.5;
+    int gx0, gy0, gx1, gy1;
+    world_to_grid(P.ox, P.oy, P.res, P.w, P.h, static_cast<float>(bx0 - margin), static_cast<float>(by0 - margin), &gx0, &gy0);
+    world_to_grid(P.ox, P.oy, P.res, P.w, P.h, static_cast<float>(bx1 + margin), static_cast<float>(by1 + margin), &gx1, &gy1);
+    s = launch_frame(c, c->g_skel.as<uint32_t>(), c->g_framed.as<uint32_t>(), P.w, P.h, std::min(gx0, gx1),
+                     std::min(gy0, gy1), std::max(gx0, gx1), std::max(gy0, gy1), 1);
+  } else {
+    s = launch_frame(c, c->g_skel.as<uint32_t>(), c->g_framed.as<uint32_t>(), P.w, P.h, 0, 0, P.w - 1, P.h - 1, 5);
+  }
+  if (s != AOS_OK) return s;
+
+  s = run_clusters(c, P, c->g_skel.as<uint32_t>(), static_cast<float>(p->cluster_min_length));
+  if (s != AOS_OK) return s;
+
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag + 32, d_kept, 8, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  c->summary.info = gi;
+  c->summary.n_clusters = c->n_clusters;
+  c->summary.n_rows = static_cast<int32_t>(c->h_rows.size());
+  c->summary.thinning_launches = launches;
+  c->summary.thinning_subiters = subiters;
+  memcpy(&c->summary.n_points_in, c->h_flag + 32, 8);
+  c->have_seed = true;
+  return AOS_OK;
+}
+
+aos_status aos_seed_summary_get(aos_ctx *c, aos_seed_summary *out) {
+  if (!c || !out) return AOS_ERR_INVALID;
+  if (!c->have_seed) {
+    set_error(c, "aos_seed_stage has not completed");
+    return AOS_ERR_STATE;
+  }
+  *out = c->summary;
+  return AOS_OK;
+}
+
+aos_status aos_get_grid(aos_ctx *c, aos_grid_id which, aos_grid_fmt fmt, void *dst, size_t dst_bytes, aos_mem dst_mem) {
+  if (!c || !dst) return AOS_ERR_INVALID;
+  if (!c->have_seed) {
+    set_error(c, "aos_seed_stage has not completed");
+    return AOS_ERR_STATE;
+  }
+  DevBuf *g = grid_buf(c, which);
+  AOS_REQUIRE(c, g != nullptr, "unknown grid id");
+  const SeedDeviceParams &P = c->P;
+  cudaStream_t st = c->stream;
+  if (fmt == AOS_FMT_BITS) {
+    size_t need = (size_t)P.pitch * P.h * 4;
+    if (dst_bytes < need) return AOS_ERR_CAPACITY;
+    AOS_CUDA_OK(c, cudaMemcpyAsync(dst, g->p, need, dst_mem == AOS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  } else {
+    size_t need = (size_t)P.w * P.h;
+    if (dst_bytes < need) return AOS_ERR_CAPACITY;
+    if (dst_mem == AOS_MEM_DEVICE) {
+      aos_status s = launch_unpack(c, g->as<uint32_t>(), static_cast<int8_t *>(dst), P.w, P.h);
+      if (s != AOS_OK) return s;
+    } else {
+      AOS_CUDA_OK(c, c->points_stage.reserve(need));  // reuse the staging buffer for the byte image
+      aos_status s = launch_unpack(c, g->as<uint32_t>(), c->points_stage.as<int8_t>(), P.w, P.h);
+      if (s != AOS_OK) return s;
+      AOS_CUDA_OK(c, cudaMemcpyAsync(dst, c->points_stage.p, need, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  return AOS_OK;
+}
+
+aos_status aos_grid_device_bits(aos_ctx *c, aos_grid_id which, const uint32_t **bits, int32_t *pitch_words) {
+  if (!c || !bits) return AOS_ERR_INVALID;
+  if (!c->have_seed) return AOS_ERR_STATE;
+  DevBuf *g = grid_buf(c, which);
+  AOS_REQUIRE(c, g != nullptr, "unknown grid id");
+  *bits = g->as<uint32_t>();
+  if (pitch_words) *pitch_words = c->P.pitch;
+  return AOS_OK;
+}
+
+aos_status aos_get_labels(aos_ctx *c, int32_t *dst, size_t dst_count, aos_mem dst_mem) {
+  if (!c || !dst) return AOS_ERR_INVALID;
+  if (!c->have_seed) return AOS_ERR_STATE;
+  size_t cells = (size_t)c->P.w * c->P.h;
+  if (dst_count < cells) return AOS_ERR_CAPACITY;
+  if (dst_mem == AOS_MEM_DEVICE) {
+    aos_status s = launch_labels(c, dst);
+    if (s != AOS_OK) return s;
+  } else {
+    AOS_CUDA_OK(c, c->points_stage.reserve(cells * 4));
+    aos_status s = launch_labels(c, c->points_stage.as<int32_t>());
+    if (s != AOS_OK) return s;
+    AOS_CUDA_OK(c, cudaMemcpyAsync(dst, c->points_stage.p, cells * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_get_clusters(aos_ctx *c, aos_cluster *dst, int32_t capacity, int32_t *n_out) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_seed) return AOS_ERR_STATE;
+  int n = static_cast<int>(c->h_clusters.size());
+  if (n_out) *n_out = n;
+  if (!dst) return AOS_OK;
+  if (capacity < n) return AOS_ERR_CAPACITY;
+  if (n) memcpy(dst, c->h_clusters.data(), sizeof(aos_cluster) * (size_t)n);
+  return AOS_OK;
+}
+
+aos_status aos_get_tree_rows(aos_ctx *c, aos_tree_row *dst, int32_t capacity, int32_t *n_out) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_seed) return AOS_ERR_STATE;
+  int n = static_cast<int>(c->h_rows.size());
+  if (n_out) *n_out = n;
+  if (!dst) return AOS_OK;
+  if (capacity < n) return AOS_ERR_CAPACITY;
+  if (n) memcpy(dst, c->h_rows.data(), sizeof(aos_tree_row) * (size_t)n);
+  return AOS_OK;
+}
+
+// ---- stand-alone steps ---------------------------------------------------------------------------
+aos_status aos_inflate_bits(aos_ctx *c, const uint32_t *in, uint32_t *out, uint32_t *out_border, int32_t w, int32_t h,
+                            int32_t radius_cells) {
+  if (!c || !in || !out) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  return launch_inflate(c, in, out, out_border, w, h, radius_cells);
+}
+
+aos_status aos_open_bits(aos_ctx *c, const uint32_t *in, uint32_t *out, int32_t w, int32_t h) {
+  if (!c || !in || !out) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  return launch_open(c, in, out, w, h);
+}
+
+aos_status aos_thin_bits(aos_ctx *c, uint32_t *inout, int32_t w, int32_t h, int32_t *launches, int32_t *subiters) {
+  if (!c || !inout) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  size_t gbytes = (size_t)pitch_words_for(w) * h * 4;
+  AOS_CUDA_OK(c, c->g_scratch.reserve(gbytes));
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->g_scratch.p, 0, gbytes, c->stream));
+  int l = 0, s = 0;
+  aos_status r = launch_thin(c, inout, c->g_scratch.as<uint32_t>(), w, h, &l, &s);
+  if (launches) *launches = l;
+  if (subiters) *subiters = s;
+  if (r != AOS_OK) return r;
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_pack_int8(aos_ctx *c, const int8_t *src, aos_mem src_mem, uint32_t *dst_bits, int32_t w, int32_t h) {
+  if (!c || !src || !dst_bits) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  const int8_t *d = src;
+  if (src_mem == AOS_MEM_HOST) {
+    AOS_CUDA_OK(c, c->points_stage.reserve((size_t)w * h));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, src, (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+    d = c->points_stage.as<int8_t>();
+  }
+  aos_status r = launch_pack(c, d, dst_bits, w, h);
+  if (r != AOS_OK) return r;
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_unpack_int8(aos_ctx *c, const uint32_t *src_bits, int8_t *dst, aos_mem dst_mem, int32_t w, int32_t h) {
+  if (!c || !src_bits || !dst) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  if (dst_mem == AOS_MEM_DEVICE) {
+    aos_status r = launch_unpack(c, src_bits, dst, w, h);
+    if (r != AOS_OK) return r;
+  } else {
+    AOS_CUDA_OK(c, c->points_stage.reserve((size_t)w * h));
+    aos_status r = launch_unpack(c, src_bits, c->points_stage.as<int8_t>(), w, h);
+    if (r != AOS_OK) return r;
+    AOS_CUDA_OK(c, cudaMemcpyAsync(dst, c->points_stage.p, (size_t)w * h, cudaMemcpyDeviceToHost, c->stream));
+  }
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+}  // extern "C"

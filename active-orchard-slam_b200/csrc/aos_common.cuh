@@ -1,0 +1,207 @@
+// aos_common.cuh -- shared declarations of libaos_gpu (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "aos_gpu.h"
+
+#ifndef __CUDA_ARCH_LIST__
+#endif
+
+namespace aos {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// Tile geometry shared by the stencil kernels.  TMA needs the innermost start coordinate and box width
+// to be multiples of 16 bytes (4 words), so a CTA that owns kTileOwnW words per row stages the aligned
+// superset [own_start-4, own_start+32).  Lane l of a warp works on column own_start - 2 + l, i.e. box word
+// l + kTileLane0; lanes kTileLane0 .. kTileLane0+kTileOwnW-1 own output, two halo lanes on each side.
+constexpr int kTileBoxW = 36;
+constexpr int kTileOwnW = 28;
+constexpr int kTileLane0 = 2;
+
+// ---- error plumbing: nothing throws across the C boundary -------------------------------------
+struct Ctx;
+void set_error(Ctx *c, const char *fmt, ...);
+
+#define AOS_CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      aos::set_error((ctx), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return AOS_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define AOS_REQUIRE(ctx, cond, msg)                                  \
+  do {                                                               \
+    if (!(cond)) {                                                   \
+      aos::set_error((ctx), "%s:%d %s", __FILE__, __LINE__, (msg));  \
+      return AOS_ERR_INVALID;                                        \
+    }                                                                \
+  } while (0)
+
+// ---- bit-packed grid: 32 cells per word, LSB = lowest x ----------------------------------------
+// Row pitch is a multiple of 4 words (16 B) so TMA tensor maps and uint4 accesses are legal.
+__host__ __device__ inline int pitch_words_for(int width) { return (((width + 31) >> 5) + 3) & ~3; }
+
+struct BitGrid {
+  uint32_t *bits = nullptr;
+  int w = 0, h = 0, pitch = 0;  // pitch in words
+  size_t words() const { return (size_t)pitch * (size_t)h; }
+  size_t bytes() const { return words() * 4; }
+};
+
+// A device buffer that only ever grows (contexts are reused map after map).
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---- TMA (cp.async.bulk.tensor) helpers --------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+// 2-D map over a bit grid (uint32 elements): dim0 = pitch words, dim1 = rows; OOB reads give 0.
+bool make_bitgrid_tmap(CUtensorMap *map, const uint32_t *base, int pitch_words, int rows, int box_w, int box_h);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared tile; coordinates may be negative / past the end: TMA zero-fills.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// streaming 16-byte load that does not pollute L1
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+#endif
+
+// ---- host-visible parameter block copied to the kernels -----------------------------------------
+constexpr int kMaxPoly = 64;
+constexpr int kMaxExcl = 64;
+
+struct SeedDeviceParams {
+  float minz, maxz, minx, maxx, miny, maxy;  // active bounds (float, inclusive)
+  float res;
+  double ox, oy;  // origin = (double)minx, (double)miny
+  int w, h, pitch;
+  int n_excl;
+  float excl[kMaxExcl * 3];
+  int n_poly;
+  double poly[kMaxPoly * 2];
+};
+
+// ---- launchers (one per kernel file) -------------------------------------------------------------
+struct Ctx;
+aos_status launch_bin(Ctx *c, const SeedDeviceParams &P, const void *points, size_t n, uint32_t step, uint32_t ox,
+                      uint32_t oy, uint32_t oz, uint32_t *bits, unsigned long long *n_kept);
+aos_status launch_inflate(Ctx *c, const uint32_t *in, uint32_t *out, uint32_t *out_border, int w, int h, int R);
+aos_status launch_open(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h);
+aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters);
+aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h, int gx0, int gy0, int gx1, int gy1,
+                        int thickness);
+aos_status launch_pack(Ctx *c, const int8_t *src, uint32_t *dst, int w, int h);
+aos_status launch_unpack(Ctx *c, const uint32_t *src, int8_t *dst, int w, int h);
+aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel, float min_length);
+aos_status launch_labels(Ctx *c, int32_t *dst);
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // seed stage state
+  bool have_seed = false;
+  SeedDeviceParams P{};
+  aos_seed_summary summary{};
+  DevBuf g_raw, g_infl, g_occ, g_open, g_skel, g_framed, g_scratch;
+  DevBuf points_stage;  // device copy of host point clouds
+  DevBuf misc;          // small counters / flags
+  int *h_flag = nullptr;  // pinned host word(s) for convergence flags and counters
+
+  // clustering state (k_cluster.cu)
+  DevBuf cc_mask, cc_prefix, cc_blocksum, cc_parent, cc_cellpos, cc_rootrank;
+  DevBuf cl_stats;   // per-root accumulators
+  DevBuf cl_table;   // aos_cluster[n_clusters]
+  DevBuf cl_aux;     // per-cluster extreme points, candidate lists ...
+  DevBuf cand_buf;
+  int n_skel_cells = 0;
+  int *d_cell_cluster = nullptr;  // compact cell -> cluster ordinal (inside cand_buf)
+  int *d_root_cellpos = nullptr;  // cluster ordinal -> canonical label (inside cl_aux)
+  int n_clusters = 0;
+  std::vector<aos_cluster> h_clusters;
+  std::vector<aos_tree_row> h_rows;
+  std::vector<int32_t> h_cluster_root;  // compact index of each cluster's root
+};
+
+}  // namespace aos

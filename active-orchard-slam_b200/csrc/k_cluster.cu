@@ -1,0 +1,866 @@
+// k_cluster.cu -- clusterOccupiedCells + the row extraction of convertClustersToTreeRows
+// (src/aos_seed_gen_node.cpp:970-1083, 1231-1255, 1258-1306, 1309-1406) on the GPU.
+//
+//  1. mask   : skeleton bits AND "cell centre inside the exploration polygon" (even-odd ray cast in
+//              double, the reference's literal formula), popcount per word.
+//  2. scan   : exclusive prefix over the word popcounts -> every skeleton cell gets a compact index
+//              in raster order (the reference's discovery order).
+//  3. link   : lock-free union-find over compact indices (CAS hooking, larger root under smaller, so a
+//              component's root is its raster-first cell == the reference's BFS start == the canonical
+//              label "min linear index").  Only the 4 raster-earlier neighbours are hooked.
+//  4. rank   : roots numbered in raster order -> cluster ordinal; sizes, exact int64 coordinate sums and
+//              8 directional extreme cells by atomics; cells grouped per cluster.
+//  5. per-cluster CTA: exact max pairwise d^2 (extreme-point lower bound + bounding-box pruning, then
+//              brute force over the survivors), float32 centre, length, cluster_min_length and polygon
+//              filters, farthest / opposite-farthest cells (row start / end).
+// Order-dependent details of the reference (float32 running sums once they pass 2^24, first-in-BFS-order
+// tie breaks) are resolved by an exact BFS-order replay of the flagged clusters (bfs_replay_kernel).
+#include "aos_common.cuh"
+
+namespace aos {
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (three kernels; n up to 2^31)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 8;
+constexpr int kScanBlock = kScanThreads * kScanPer;  // 2048 elements per block
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total) {
+  __shared__ uint32_t wsum[kScanThreads / 32];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan(v, lane);
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < kScanThreads / 32 ? wsum[lane] : 0;
+    uint32_t wi = warp_incl_scan(w, lane);
+    if (lane < kScanThreads / 32) wsum[lane] = wi - w;  // exclusive warp offsets
+    if (lane == kScanThreads / 32 - 1) *total = wi;
+  }
+  __syncthreads();
+  uint32_t r = inc - v + wsum[warp];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t *__restrict__ in, size_t n,
+                                                                   uint32_t *__restrict__ blocksum) {
+  __shared__ uint32_t tot;
+  size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPer;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k)
+    if (base + k < n) s += in[base + k];
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_blocksums_kernel(uint32_t *blocksum, int nb, uint32_t *total_out) {
+  __shared__ uint32_t tot;
+  uint32_t carry = 0;
+  for (int base = 0; base < nb; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nb ? blocksum[i] : 0;
+    uint32_t ex = block_excl_scan(v, &tot);
+    if (i < nb) blocksum[i] = ex + carry;
+    carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ data, size_t n,
+                                                                  const uint32_t *__restrict__ blocksum) {
+  __shared__ uint32_t tot;
+  size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPer;
+  uint32_t v[kScanPer], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    v[k] = base + k < n ? data[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t ex = block_excl_scan(s, &tot) + blocksum[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    if (base + k < n) data[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+// in-place exclusive scan; total written to d_total (device)
+static aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum_buf, uint32_t *d_total) {
+  int nb = (int)((n + kScanBlock - 1) / kScanBlock);
+  if (nb < 1) nb = 1;
+  AOS_CUDA_OK(c, blocksum_buf.reserve(sizeof(uint32_t) * (size_t)nb));
+  uint32_t *bs = blocksum_buf.as<uint32_t>();
+  scan_reduce_kernel<<<nb, kScanThreads, 0, c->stream>>>(data, n, bs);
+  scan_blocksums_kernel<<<1, kScanThreads, 0, c->stream>>>(bs, nb, d_total);
+  scan_apply_kernel<<<nb, kScanThreads, 0, c->stream>>>(data, n, bs);
+  AOS_CUDA_OK(c, cudaGetLastError());
+  return AOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 1. polygon mask + popcount
+// ---------------------------------------------------------------------------------------------------
+// isPointInPolygon, seed_gen:1231-1255 (double, |dy| > 1e-9 guard); compiled with -fmad=false
+__device__ __forceinline__ bool point_in_polygon(const SeedDeviceParams &P, double px, double py) {
+  if (P.n_poly < 3) return false;
+  bool inside = false;
+  int j = P.n_poly - 1;
+  for (int i = 0; i < P.n_poly; ++i) {
+    double pix = P.poly[2 * i], piy = P.poly[2 * i + 1];
+    double pjx = P.poly[2 * j], pjy = P.poly[2 * j + 1];
+    double dy = pjy - piy;
+    if (fabs(dy) > 1e-9) {
+      if (((piy > py) != (pjy > py)) && (px < (pjx - pix) * (py - piy) / dy + pix)) inside = !inside;
+    }
+    j = i;
+  }
+  return inside;
+}
+
+// world coordinate of a cell as the reference computes it (seed_gen:998-999, 1349-1350):
+// float(double(origin) + double(float(idx) * res_f32))
+__device__ __forceinline__ float cell_world(double origin, int idx, float res) {
+  return (float)(origin + (double)__fmul_rn((float)idx, res));
+}
+
+__global__ void mask_count_kernel(const __grid_constant__ SeedDeviceParams P, const uint32_t *__restrict__ skel,
+                                  uint32_t *__restrict__ mask, uint32_t *__restrict__ counts) {
+  size_t total = (size_t)P.pitch * P.h;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    uint32_t v = skel[i];
+    if (v && P.n_poly > 0) {  // use_polygon_filter (seed_gen:979-982)
+      int y = (int)(i / (size_t)P.pitch), cw = (int)(i - (size_t)y * P.pitch);
+      float wy = cell_world(P.oy, y, P.res);
+      uint32_t keep = 0, rem = v;
+      while (rem) {
+        int b = __ffs(rem) - 1;
+        rem &= rem - 1;
+        float wx = cell_world(P.ox, (cw << 5) + b, P.res);
+        if (point_in_polygon(P, (double)wx, (double)wy)) keep |= 1u << b;
+      }
+      v = keep;
+    }
+    mask[i] = v;
+    counts[i] = __popc(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3. union-find
+// ---------------------------------------------------------------------------------------------------
+__global__ void cc_init_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix, int pitch, int h,
+                               int w, int *__restrict__ parent, int *__restrict__ cellpos) {
+  size_t total = (size_t)pitch * h;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    uint32_t v = mask[i];
+    if (!v) continue;
+    int y = (int)(i / (size_t)pitch), cw = (int)(i - (size_t)y * pitch);
+    int idx = (int)prefix[i];
+    while (v) {
+      int b = __ffs(v) - 1;
+      v &= v - 1;
+      parent[idx] = idx;
+      cellpos[idx] = y * w + (cw << 5) + b;
+      ++idx;
+    }
+  }
+}
+
+__device__ __forceinline__ int uf_find(int *parent, int i) {
+  int cur = parent[i];
+  if (cur != i) {
+    int prev = i, next;
+    while (cur > (next = parent[cur])) {
+      parent[prev] = next;  // pointer jumping; parents only ever decrease, so this is benign
+      prev = cur;
+      cur = next;
+    }
+  }
+  return cur;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+  int ra = uf_find(parent, a), rb = uf_find(parent, b);
+  bool repeat;
+  do {
+    repeat = false;
+    if (ra != rb) {
+      int ret;
+      if (ra < rb) {
+        if ((ret = atomicCAS(&parent[rb], rb, ra)) != rb) {
+          rb = ret;
+          repeat = true;
+        }
+      } else {
+        if ((ret = atomicCAS(&parent[ra], ra, rb)) != ra) {
+          ra = ret;
+          repeat = true;
+        }
+      }
+    }
+  } while (repeat);
+}
+
+__device__ __forceinline__ int compact_index(const uint32_t *mask, const uint32_t *prefix, int pitch, int x, int y) {
+  size_t wi = (size_t)y * pitch + (x >> 5);
+  uint32_t m = mask[wi];
+  uint32_t bit = 1u << (x & 31);
+  if (!(m & bit)) return -1;
+  return (int)prefix[wi] + __popc(m & (bit - 1u));
+}
+
+__global__ void cc_link_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix, int pitch, int h,
+                               int w, int *parent) {
+  size_t total = (size_t)pitch * h;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    uint32_t v = mask[i];
+    if (!v) continue;
+    int y = (int)(i / (size_t)pitch), cw = (int)(i - (size_t)y * pitch);
+    int idx = (int)prefix[i];
+    while (v) {
+      int b = __ffs(v) - 1;
+      v &= v - 1;
+      int x = (cw << 5) + b;
+      // raster-earlier half of the 8-neighbourhood: W, NW, N, NE  (N = row y-1)
+      if (x > 0) {
+        int n = compact_index(mask, prefix, pitch, x - 1, y);
+        if (n >= 0) uf_union(parent, idx, n);
+      }
+      if (y > 0) {
+        if (x > 0) {
+          int n = compact_index(mask, prefix, pitch, x - 1, y - 1);
+          if (n >= 0) uf_union(parent, idx, n);
+        }
+        int n = compact_index(mask, prefix, pitch, x, y - 1);
+        if (n >= 0) uf_union(parent, idx, n);
+        if (x + 1 < w) {
+          n = compact_index(mask, prefix, pitch, x + 1, y - 1);
+          if (n >= 0) uf_union(parent, idx, n);
+        }
+      }
+      ++idx;
+    }
+  }
+}
+
+__global__ void cc_flatten_kernel(int *parent, uint32_t *__restrict__ is_root, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = i, p;
+    while ((p = parent[r]) != r) r = p;
+    parent[i] = r;  // racing writers all store a value on the path to the same root
+    is_root[i] = (r == i) ? 1u : 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4. per-cluster accumulators
+// ---------------------------------------------------------------------------------------------------
+struct ClusterAcc {          // one per cluster, zero/identity-initialised
+  unsigned int size;
+  unsigned int cursor;       // fill cursor for grouping
+  unsigned long long sumx, sumy;
+  // directional extremes: key = (value + bias) << 32 | compact cell pos ; [0..3] max of x, y, x+y, x-y ; [4..7] min
+  unsigned long long ext[8];
+};
+constexpr long long kExtBias = 1ll << 30;
+
+__global__ void acc_init_kernel(ClusterAcc *acc, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ClusterAcc a;
+  a.size = 0;
+  a.cursor = 0;
+  a.sumx = a.sumy = 0;
+  for (int k = 0; k < 4; ++k) a.ext[k] = 0ull;
+  for (int k = 4; k < 8; ++k) a.ext[k] = ~0ull;
+  acc[i] = a;
+}
+
+__global__ void cc_accumulate_kernel(const int *__restrict__ parent, const uint32_t *__restrict__ rootrank,
+                                     const int *__restrict__ cellpos, int n, int w, int *__restrict__ cell_cluster,
+                                     ClusterAcc *acc) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = (int)rootrank[parent[i]];
+    cell_cluster[i] = c;
+    int pos = cellpos[i];
+    int y = pos / w, x = pos - y * w;
+    ClusterAcc *a = acc + c;
+    atomicAdd(&a->size, 1u);
+    atomicAdd(&a->sumx, (unsigned long long)x);
+    atomicAdd(&a->sumy, (unsigned long long)y);
+    long long vals[4] = {x, y, (long long)x + y, (long long)x - y};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned long long key = ((unsigned long long)(vals[k] + kExtBias) << 32) | (unsigned int)pos;
+      atomicMax(&a->ext[k], key);
+      atomicMin(&a->ext[4 + k], key);
+    }
+  }
+}
+
+__global__ void acc_sizes_kernel(const ClusterAcc *acc, int n, uint32_t *sizes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sizes[i] = acc[i].size;
+}
+
+__global__ void cc_group_kernel(const int *__restrict__ cell_cluster, const int *__restrict__ cellpos, int n,
+                                const uint32_t *__restrict__ offsets, ClusterAcc *acc, int *__restrict__ grouped) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = cell_cluster[i];
+    unsigned int k = atomicAdd(&acc[c].cursor, 1u);
+    grouped[offsets[c] + k] = cellpos[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 5. one CTA per cluster
+// ---------------------------------------------------------------------------------------------------
+constexpr int kClThreads = 128;
+enum : int { kFlagNeedsOrder = 1, kFlagRow = 2, kFlagTie = 4 };
+
+struct RowOut {  // device-side mirror of aos_tree_row + book-keeping
+  aos_tree_row row;
+  int valid;
+  int flags;
+};
+
+template <typename T>
+__device__ __forceinline__ T block_reduce_max(T v, T *scratch) {
+  for (int o = 16; o > 0; o >>= 1) {
+    T t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = scratch[0];
+  for (int k = 1; k < kClThreads / 32; ++k) r = scratch[k] > r ? scratch[k] : r;
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ T block_reduce_min(T v, T *scratch) {
+  for (int o = 16; o > 0; o >>= 1) {
+    T t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = scratch[0];
+  for (int k = 1; k < kClThreads / 32; ++k) r = scratch[k] < r ? scratch[k] : r;
+  return r;
+}
+__device__ __forceinline__ int block_reduce_sum(int v, int *scratch) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0;
+  for (int k = 0; k < kClThreads / 32; ++k) r += scratch[k];
+  return r;
+}
+
+__device__ __forceinline__ long long d2ll(int ax, int ay, int bx, int by) {
+  long long dx = ax - bx, dy = ay - by;
+  return dx * dx + dy * dy;
+}
+
+// Exact diameter^2, centre, length, filters, row endpoints.  `cells` = this cluster's cell positions
+// (any order).  order_rank (may be null) = BFS rank of each grouped cell when a replay was needed.
+__global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
+    const __grid_constant__ SeedDeviceParams P, const ClusterAcc *__restrict__ acc, const uint32_t *__restrict__ offsets,
+    const int *__restrict__ grouped, const int *__restrict__ root_cellpos, float min_length,
+    const float *__restrict__ replay_centre /* 2 per cluster or null */, const int *__restrict__ order_rank,
+    aos_cluster *__restrict__ out_clusters, RowOut *__restrict__ out_rows) {
+  __shared__ unsigned long long s_u64[kClThreads / 32];
+  __shared__ long long s_i64[kClThreads / 32];
+  __shared__ int s_int[kClThreads / 32];
+  const int c = blockIdx.x;
+  const ClusterAcc a = acc[c];
+  const int n = (int)a.size;
+  const int *cells = grouped + offsets[c];
+  const int *ranks = order_rank ? order_rank + offsets[c] : nullptr;
+  const int w = P.w;
+
+  // ---- exact max pairwise squared distance -------------------------------------------------------
+  int ex[8], ey[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int pos = (int)(a.ext[k] & 0xffffffffull);
+    ey[k] = pos / w;
+    ex[k] = pos - ey[k] * w;
+  }
+  long long lb = 0;  // lower bound from the 8 directional extreme cells
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = i + 1; j < 8; ++j) {
+      long long d = d2ll(ex[i], ey[i], ex[j], ey[j]);
+      lb = d > lb ? d : lb;
+    }
+  const int bx0 = ex[4], bx1 = ex[0], by0 = ey[5], by1 = ey[1];  // min x, max x, min y, max y
+  // a cell can end a longer pair only if its farthest bounding-box corner is at least lb away
+  auto is_cand = [&](int x, int y) -> bool {
+    long long dx = max(x - bx0, bx1 - x), dy = max(y - by0, by1 - y);
+    return dx * dx + dy * dy >= lb;
+  };
+  long long best = lb;
+  for (int i = threadIdx.x; i < n; i += kClThreads) {
+    int pi = cells[i];
+    int yi = pi / w, xi = pi - yi * w;
+    if (!is_cand(xi, yi)) continue;
+    for (int j = 0; j < n; ++j) {
+      int pj = cells[j];
+      int yj = pj / w, xj = pj - yj * w;
+      if (!is_cand(xj, yj)) continue;
+      long long d = d2ll(xi, yi, xj, yj);
+      best = d > best ? d : best;
+    }
+  }
+  const long long maxd2 = block_reduce_max<long long>(best, s_i64);
+
+  // ---- centre (seed_gen:1053-1059) ---------------------------------------------------------------
+  // float32 running sums are exact (order-independent) while every partial sum is below 2^24
+  int flags = 0;
+  float cx, cy;
+  const bool exact_sum = a.sumx < (1ull << 24) && a.sumy < (1ull << 24);
+  if (exact_sum || replay_centre == nullptr) {
+    cx = __fdiv_rn((float)a.sumx, (float)(unsigned long long)n);
+    cy = __fdiv_rn((float)a.sumy, (float)(unsigned long long)n);
+    if (!exact_sum) flags |= kFlagNeedsOrder;
+  } else {
+    cx = replay_centre[2 * c];
+    cy = replay_centre[2 * c + 1];
+  }
+  // length (seed_gen:1068,1074): float( sqrt(int d2) [double] * res [float->double] )
+  float length = maxd2 > 0 ? (float)(sqrt((double)maxd2) * (double)P.res) : 0.0f;
+
+  // ---- filters (seed_gen:1262-1270, 1333-1341) ------------------------------------------------------
+  const float centre_wx = (float)(P.ox + (double)__fmul_rn(cx, P.res));
+  const float centre_wy = (float)(P.oy + (double)__fmul_rn(cy, P.res));
+  bool is_row = length >= min_length;
+  if (is_row && P.n_poly > 0) is_row = point_in_polygon(P, (double)centre_wx, (double)centre_wy);
+
+  RowOut ro;
+  memset(&ro, 0, sizeof(ro));
+  if (is_row) {
+    flags |= kFlagRow;
+    const double rcx = (double)centre_wx, rcy = (double)centre_wy;
+    // -- farthest cell from the centre (strict >, first in BFS order wins ties) --
+    unsigned long long bestk = 0;
+    for (int i = threadIdx.x; i < n; i += kClThreads) {
+      int p = cells[i];
+      int y = p / w, x = p - y * w;
+      double dx = (double)cell_world(P.ox, x, P.res) - rcx, dy = (double)cell_world(P.oy, y, P.res) - rcy;
+      double d2 = dx * dx + dy * dy;
+      unsigned long long k = (unsigned long long)__double_as_longlong(d2);
+      bestk = k > bestk ? k : bestk;
+    }
+    const unsigned long long max1 = block_reduce_max<unsigned long long>(bestk, s_u64);
+    // winner among ties: lowest BFS rank if known, else lowest raster position (+ tie flag)
+    long long pick = 0x7fffffffffffffffll;
+    int ties = 0;
+    for (int i = threadIdx.x; i < n; i += kClThreads) {
+      int p = cells[i];
+      int y = p / w, x = p - y * w;
+      double dx = (double)cell_world(P.ox, x, P.res) - rcx, dy = (double)cell_world(P.oy, y, P.res) - rcy;
+      double d2 = dx * dx + dy * dy;
+      if ((unsigned long long)__double_as_longlong(d2) == max1 && max1 != 0ull) {
+        ++ties;
+        long long key = ((long long)(ranks ? ranks[i] : 0) << 32) | (unsigned int)p;
+        pick = key < pick ? key : pick;
+      }
+    }
+    const int nties1 = block_reduce_sum(ties, s_int);
+    const long long pick1 = block_reduce_min<long long>(pick, s_i64);
+    int first_pos;
+    double fdx = 0.0, fdy = 0.0;
+    if (max1 == 0ull) {
+      // no cell differs from the centre: first_idx stays 0 == the BFS start == the root cell
+      first_pos = root_cellpos[c];
+    } else {
+      first_pos = (int)(pick1 & 0xffffffffll);
+      if (nties1 > 1 && !ranks) flags |= kFlagTie;
+      int y = first_pos / w, x = first_pos - y * w;
+      double dx = (double)cell_world(P.ox, x, P.res) - rcx, dy = (double)cell_world(P.oy, y, P.res) - rcy;
+      double s = sqrt(dx * dx + dy * dy);
+      fdx = dx / s;
+      fdy = dy / s;
+    }
+    // -- farthest cell with negative dot to the first direction --
+    bestk = 0;
+    for (int i = threadIdx.x; i < n; i += kClThreads) {
+      int p = cells[i];
+      if (p == first_pos) continue;
+      int y = p / w, x = p - y * w;
+      double dx = (double)cell_world(P.ox, x, P.res) - rcx, dy = (double)cell_world(P.oy, y, P.res) - rcy;
+      double d2 = dx * dx + dy * dy;
+      double nx = dx, ny = dy;
+      if (d2 > 0.0) {
+        double s = sqrt(d2);
+        nx = dx / s;
+        ny = dy / s;
+      }
+      double dot = nx * fdx + ny * fdy;
+      if (dot < 0.0) {
+        unsigned long long k = (unsigned long long)__double_as_longlong(d2);
+        bestk = k > bestk ? k : bestk;
+      }
+    }
+    const unsigned long long max2 = block_reduce_max<unsigned long long>(bestk, s_u64);
+    int second_pos;
+    if (max2 != 0ull) {
+      pick = 0x7fffffffffffffffll;
+      ties = 0;
+      for (int i = threadIdx.x; i < n; i += kClThreads) {
+        int p = cells[i];
+        if (p == first_pos) continue;
+        int y = p / w, x = p - y * w;
+        double dx = (double)cell_world(P.ox, x, P.res) - rcx, dy = (double)cell_world(P.oy, y, P.res) - rcy;
+        double d2 = dx * dx + dy * dy;
+        if ((unsigned long long)__double_as_longlong(d2) != max2) continue;
+        double s = sqrt(d2);
+        double dot = (dx / s) * fdx + (dy / s) * fdy;
+        if (dot < 0.0) {
+          ++ties;
+          long long key = ((long long)(ranks ? ranks[i] : 0) << 32) | (unsigned int)p;
+          pick = key < pick ? key : pick;
+        }
+      }
+      const int nties2 = block_reduce_sum(ties, s_int);
+      const long long pick2 = block_reduce_min<long long>(pick, s_i64);
+      second_pos = (int)(pick2 & 0xffffffffll);
+      if (nties2 > 1 && !ranks) flags |= kFlagTie;
+    } else {
+      // seed_gen:1388-1399: no opposite cell -> farthest from the first cell (second_idx starts at 0)
+      const int fy = first_pos / w, fx = first_pos - fy * w;
+      const double fwx = (double)cell_world(P.ox, fx, P.res), fwy = (double)cell_world(P.oy, fy, P.res);
+      bestk = 0;
+      for (int i = threadIdx.x; i < n; i += kClThreads) {
+        int p = cells[i];
+        if (p == first_pos) continue;
+        int y = p / w, x = p - y * w;
+        double dx = (double)cell_world(P.ox, x, P.res) - fwx, dy = (double)cell_world(P.oy, y, P.res) - fwy;
+        unsigned long long k = (unsigned long long)__double_as_longlong(dx * dx + dy * dy);
+        bestk = k > bestk ? k : bestk;
+      }
+      const unsigned long long max3 = block_reduce_max<unsigned long long>(bestk, s_u64);
+      pick = 0x7fffffffffffffffll;
+      ties = 0;
+      for (int i = threadIdx.x; i < n; i += kClThreads) {
+        int p = cells[i];
+        if (p == first_pos) continue;
+        int y = p / w, x = p - y * w;
+        double dx = (double)cell_world(P.ox, x, P.res) - fwx, dy = (double)cell_world(P.oy, y, P.res) - fwy;
+        if ((unsigned long long)__double_as_longlong(dx * dx + dy * dy) == max3 && max3 != 0ull) {
+          ++ties;
+          long long key = ((long long)(ranks ? ranks[i] : 0) << 32) | (unsigned int)p;
+          pick = key < pick ? key : pick;
+        }
+      }
+      const int nties3 = block_reduce_sum(ties, s_int);
+      const long long pick3 = block_reduce_min<long long>(pick, s_i64);
+      if (max3 == 0ull) second_pos = root_cellpos[c];  // second_idx stays 0
+      else {
+        second_pos = (int)(pick3 & 0xffffffffll);
+        if (nties3 > 1 && !ranks) flags |= kFlagTie;
+      }
+    }
+    if (threadIdx.x == 0) {
+      int y1 = first_pos / w, x1 = first_pos - y1 * w, y2 = second_pos / w, x2 = second_pos - y2 * w;
+      ro.row.center_x = rcx;
+      ro.row.center_y = rcy;
+      ro.row.start_x = (double)cell_world(P.ox, x1, P.res);
+      ro.row.start_y = (double)cell_world(P.oy, y1, P.res);
+      ro.row.end_x = (double)cell_world(P.ox, x2, P.res);
+      ro.row.end_y = (double)cell_world(P.oy, y2, P.res);
+      ro.row.length = (double)length;
+      ro.row.cluster = c;
+      ro.valid = 1;
+    }
+  }
+  if (threadIdx.x == 0) {
+    aos_cluster oc;
+    oc.label = root_cellpos[c];
+    oc.size = n;
+    oc.center_x = cx;
+    oc.center_y = cy;
+    oc.length = length;
+    oc.reserved = flags;
+    oc.sum_x = (int64_t)a.sumx;
+    oc.sum_y = (int64_t)a.sumy;
+    oc.max_d2 = maxd2;
+    out_clusters[c] = oc;
+    ro.flags = flags;
+    out_rows[c] = ro;
+  }
+}
+
+__global__ void root_cellpos_kernel(const uint32_t *__restrict__ is_root_rank, const int *__restrict__ parent,
+                                    const int *__restrict__ cellpos, int n, int *__restrict__ root_cellpos) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (parent[i] == i) root_cellpos[is_root_rank[i]] = cellpos[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BFS-order replay (seed_gen:1008-1049): one warp per flagged cluster walks the component exactly as
+// the reference's queue does (neighbour order dx,dy = (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1))
+// and accumulates the float32 sums in that order.  `visited` is a scratch copy of the masked grid whose
+// bits are cleared on first visit.  Emits the BFS rank of every grouped cell.
+// ---------------------------------------------------------------------------------------------------
+__global__ void bfs_replay_kernel(const __grid_constant__ SeedDeviceParams P, const int *__restrict__ flagged, int n_flagged,
+                                  const ClusterAcc *__restrict__ acc, const uint32_t *__restrict__ offsets,
+                                  const int *__restrict__ root_cellpos, uint32_t *visited, int *__restrict__ queue,
+                                  float *__restrict__ centre_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_flagged) return;
+  const int c = flagged[warp];
+  const int n = (int)acc[c].size;
+  int *q = queue + offsets[c];  // BFS order of cell positions
+  const int w = P.w, h = P.h, pitch = P.pitch;
+  const int ddx[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  const int ddy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  int head = 0, tail = 0;
+  float sum_x = 0.f, sum_y = 0.f;
+  {
+    int start = root_cellpos[c];
+    if (lane == 0) {
+      q[0] = start;
+      int y = start / w, x = start - y * w;
+      atomicAnd(&visited[(size_t)y * pitch + (x >> 5)], ~(1u << (x & 31)));
+    }
+    tail = 1;
+    __syncwarp();
+  }
+  while (head < tail) {
+    int cur = q[head];
+    ++head;
+    int cy = cur / w, cx = cur - cy * w;
+    sum_x = __fadd_rn(sum_x, (float)cx);
+    sum_y = __fadd_rn(sum_y, (float)cy);
+    bool take = false;
+    int nx = 0, ny = 0;
+    if (lane < 8) {
+      nx = cx + ddx[lane];
+      ny = cy + ddy[lane];
+      if (nx >= 0 && nx < w && ny >= 0 && ny < h) {
+        uint32_t word = __ldcg(&visited[(size_t)ny * pitch + (nx >> 5)]);  // atomics live in L2: bypass L1
+        take = (word >> (nx & 31)) & 1u;
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, take);
+    if (take) {
+      int k = __popc(m & ((1u << lane) - 1u));
+      q[tail + k] = ny * w + nx;
+      atomicAnd(&visited[(size_t)ny * pitch + (nx >> 5)], ~(1u << (nx & 31)));
+    }
+    tail += __popc(m);
+    __syncwarp();
+    __threadfence_block();
+  }
+  if (lane == 0) {
+    centre_out[2 * c] = __fdiv_rn(sum_x, (float)(unsigned long long)n);
+    centre_out[2 * c + 1] = __fdiv_rn(sum_y, (float)(unsigned long long)n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------------
+static inline int grid_for(size_t n, int threads, int cap_mult = 16) {
+  size_t b = (n + threads - 1) / threads;
+  size_t cap = (size_t)kNumSMs * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel, float min_length) {
+  const size_t words = (size_t)P.pitch * P.h;
+  cudaStream_t st = c->stream;
+  c->n_clusters = 0;
+  c->n_skel_cells = 0;
+  c->h_clusters.clear();
+  c->h_rows.clear();
+  AOS_CUDA_OK(c, c->cc_mask.reserve(words * 4));
+  AOS_CUDA_OK(c, c->cc_prefix.reserve(words * 4));
+  AOS_CUDA_OK(c, c->misc.reserve(4096));
+  uint32_t *mask = c->cc_mask.as<uint32_t>();
+  uint32_t *prefix = c->cc_prefix.as<uint32_t>();
+  uint32_t *d_tot = c->misc.as<uint32_t>();  // [0] skeleton cells, [1] clusters
+
+  mask_count_kernel<<<grid_for(words, 256), 256, 0, st>>>(P, skel, mask, prefix);
+  AOS_CUDA_OK(c, cudaGetLastError());
+  aos_status s = exclusive_scan_u32(c, prefix, words, c->cc_blocksum, d_tot);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  const int n = c->h_flag[0];
+  c->n_skel_cells = n;
+  if (n == 0) return AOS_OK;
+
+  AOS_CUDA_OK(c, c->cc_parent.reserve(sizeof(int) * (size_t)n));
+  AOS_CUDA_OK(c, c->cc_cellpos.reserve(sizeof(int) * (size_t)n));
+  AOS_CUDA_OK(c, c->cc_rootrank.reserve(sizeof(uint32_t) * (size_t)n));
+  int *parent = c->cc_parent.as<int>();
+  int *cellpos = c->cc_cellpos.as<int>();
+  uint32_t *rootrank = c->cc_rootrank.as<uint32_t>();
+  cc_init_kernel<<<grid_for(words, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, parent, cellpos);
+  cc_link_kernel<<<grid_for(words, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, parent);
+  cc_flatten_kernel<<<grid_for(n, 256), 256, 0, st>>>(parent, rootrank, n);
+  AOS_CUDA_OK(c, cudaGetLastError());
+  s = exclusive_scan_u32(c, rootrank, (size_t)n, c->cc_blocksum, d_tot + 1);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  const int nc = c->h_flag[0];
+  c->n_clusters = nc;
+
+  // layout of cl_aux: ClusterAcc[nc] | sizes/offsets u32[nc+1] | root_cellpos int[nc] | centre f32[2nc] | flagged int[nc]
+  size_t off_acc = 0;
+  size_t off_offsets = off_acc + sizeof(ClusterAcc) * (size_t)nc;
+  size_t off_rootpos = off_offsets + sizeof(uint32_t) * (size_t)(nc + 4);
+  size_t off_centre = off_rootpos + sizeof(int) * (size_t)(nc + 4);
+  size_t off_flagged = off_centre + sizeof(float) * 2 * (size_t)(nc + 4);
+  size_t aux_bytes = off_flagged + sizeof(int) * (size_t)(nc + 4);
+  AOS_CUDA_OK(c, c->cl_aux.reserve(aux_bytes));
+  char *aux = c->cl_aux.as<char>();
+  ClusterAcc *acc = reinterpret_cast<ClusterAcc *>(aux + off_acc);
+  uint32_t *offsets = reinterpret_cast<uint32_t *>(aux + off_offsets);
+  int *root_cellpos = reinterpret_cast<int *>(aux + off_rootpos);
+  float *centre = reinterpret_cast<float *>(aux + off_centre);
+  int *flagged = reinterpret_cast<int *>(aux + off_flagged);
+
+  // cell_cluster int[n] | grouped int[n] | order queue int[n] | rank int[n]
+  AOS_CUDA_OK(c, c->cand_buf.reserve(sizeof(int) * 4 * (size_t)n));
+  int *cell_cluster = c->cand_buf.as<int>();
+  int *grouped = cell_cluster + n;
+  int *queue = grouped + n;
+  int *rank = queue + n;
+  c->d_cell_cluster = cell_cluster;
+  c->d_root_cellpos = root_cellpos;
+
+  acc_init_kernel<<<(nc + 127) / 128, 128, 0, st>>>(acc, nc);
+  root_cellpos_kernel<<<grid_for(n, 256), 256, 0, st>>>(rootrank, parent, cellpos, n, root_cellpos);
+  cc_accumulate_kernel<<<grid_for(n, 256), 256, 0, st>>>(parent, rootrank, cellpos, n, P.w, cell_cluster, acc);
+  acc_sizes_kernel<<<(nc + 127) / 128, 128, 0, st>>>(acc, nc, offsets);
+  AOS_CUDA_OK(c, cudaGetLastError());
+  s = exclusive_scan_u32(c, offsets, (size_t)nc, c->cc_blocksum, d_tot + 2);
+  if (s != AOS_OK) return s;
+  cc_group_kernel<<<grid_for(n, 256), 256, 0, st>>>(cell_cluster, cellpos, n, offsets, acc, grouped);
+
+  AOS_CUDA_OK(c, c->cl_table.reserve(sizeof(aos_cluster) * (size_t)nc + sizeof(RowOut) * (size_t)nc));
+  aos_cluster *d_clusters = c->cl_table.as<aos_cluster>();
+  RowOut *d_rows = reinterpret_cast<RowOut *>(d_clusters + nc);
+  cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, nullptr,
+                                                     nullptr, d_clusters, d_rows);
+  AOS_CUDA_OK(c, cudaGetLastError());
+
+  c->h_clusters.resize(nc);
+  std::vector<RowOut> h_rows(nc);
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_clusters.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc,
+                                 cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+
+  // ---- order-dependent clusters: replay the reference's BFS and finalise again --------------------
+  // needed when a float32 partial sum can round (sum >= 2^24) or an arg-max tie must be broken by BFS order
+  std::vector<int> need;
+  for (int i = 0; i < nc; ++i)
+    if (h_rows[i].flags & (kFlagNeedsOrder | kFlagTie)) need.push_back(i);
+  if (!need.empty()) {
+    // visited = scratch copy of the mask (cc_prefix is free now: compact indices are no longer needed)
+    uint32_t *visited = prefix;
+    AOS_CUDA_OK(c, cudaMemcpyAsync(visited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(flagged, need.data(), sizeof(int) * need.size(), cudaMemcpyHostToDevice, st));
+    int nf = (int)need.size();
+    bfs_replay_kernel<<<(nf * 32 + 127) / 128, 128, 0, st>>>(P, flagged, nf, acc, offsets, root_cellpos, visited, queue,
+                                                             centre);
+    AOS_CUDA_OK(c, cudaGetLastError());
+    // the replayed queue becomes the cluster's cell list; its index is the BFS rank
+    // (grouped[] of flagged clusters is overwritten by the queue; rank = position)
+    // simple: copy queue segment over grouped segment and build identity ranks on the host side sizes
+    std::vector<uint32_t> h_off(nc + 1);
+    AOS_CUDA_OK(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint32_t) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    h_off[nc] = (uint32_t)n;
+    for (int i : need) {
+      size_t b = h_off[i], e = (i + 1 < nc) ? h_off[i + 1] : (size_t)n;
+      AOS_CUDA_OK(c, cudaMemcpyAsync(grouped + b, queue + b, sizeof(int) * (e - b), cudaMemcpyDeviceToDevice, st));
+    }
+    // rank[i] = i - offset  for every grouped slot (only meaningful for replayed clusters)
+    {
+      std::vector<int> h_rank(n);
+      for (int i = 0; i < nc; ++i) {
+        size_t b = h_off[i], e = (i + 1 < nc) ? h_off[i + 1] : (size_t)n;
+        for (size_t k = b; k < e; ++k) h_rank[k] = (int)(k - b);
+      }
+      AOS_CUDA_OK(c, cudaMemcpyAsync(rank, h_rank.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+      AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    }
+    // re-run the finaliser for everything (cheap) with replayed centres where available:
+    // centre[] is only valid for flagged clusters, so un-flagged ones must keep the exact-sum path.
+    // Mark by writing NaN-free data: fill centre for un-flagged clusters from the first pass.
+    {
+      std::vector<float> h_c(2 * (size_t)nc);
+      AOS_CUDA_OK(c, cudaMemcpyAsync(h_c.data(), centre, sizeof(float) * 2 * (size_t)nc, cudaMemcpyDeviceToHost, st));
+      AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+      std::vector<char> isf(nc, 0);
+      for (int i : need) isf[i] = 1;
+      for (int i = 0; i < nc; ++i)
+        if (!isf[i]) {
+          h_c[2 * i] = c->h_clusters[i].center_x;
+          h_c[2 * i + 1] = c->h_clusters[i].center_y;
+        }
+      AOS_CUDA_OK(c, cudaMemcpyAsync(centre, h_c.data(), sizeof(float) * 2 * (size_t)nc, cudaMemcpyHostToDevice, st));
+      AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    }
+    cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, centre, rank,
+                                                       d_clusters, d_rows);
+    AOS_CUDA_OK(c, cudaGetLastError());
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_clusters.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc,
+                                   cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  }
+  for (int i = 0; i < nc; ++i)
+    if (h_rows[i].valid) c->h_rows.push_back(h_rows[i].row);
+  return AOS_OK;
+}
+
+// per-cell canonical label map: -1 everywhere, min linear index of the component at clustered cells
+__global__ void labels_kernel(const int *__restrict__ cell_cluster, const int *__restrict__ cellpos,
+                              const int *__restrict__ root_cellpos, int n, int32_t *__restrict__ labels) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    labels[cellpos[i]] = root_cellpos[cell_cluster[i]];
+}
+
+aos_status launch_labels(Ctx *c, int32_t *dst) {
+  size_t cells = (size_t)c->P.w * c->P.h;
+  AOS_CUDA_OK(c, cudaMemsetAsync(dst, 0xff, cells * 4, c->stream));
+  if (c->n_skel_cells > 0) {
+    labels_kernel<<<grid_for((size_t)c->n_skel_cells, 256), 256, 0, c->stream>>>(
+        c->d_cell_cluster, c->cc_cellpos.as<int>(), c->d_root_cellpos, c->n_skel_cells, dst);
+    AOS_CUDA_OK(c, cudaGetLastError());
+  }
+  return AOS_OK;
+}
+
+}  // namespace aos

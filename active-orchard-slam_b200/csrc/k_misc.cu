@@ -1,0 +1,145 @@
+// k_misc.cu -- ABI-edge conversions (occupancyGridToMat / matToOccupancyGrid, src/aos_seed_gen_node.cpp:
+// 626-669: 100 <-> set bit, anything else is free), the 1-px rectangle of markPolygonBoundaryAsOccupied
+// (:772-825; its four Bresenham lines are axis-aligned), TMA descriptor creation and error plumbing.
+#include <stdarg.h>
+
+#include "aos_common.cuh"
+
+namespace aos {
+
+void set_error(Ctx *c, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+bool make_bitgrid_tmap(CUtensorMap *map, const uint32_t *base, int pitch_words, int rows, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)pitch_words, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch_words * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// ---- int8 {0,100} -> bits: one warp packs 32 words from 1024 bytes with coalesced 4-byte loads -----
+__global__ void pack_kernel(const int8_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int pitch) {
+  int wordcol = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y;
+  if (wordcol >= pitch) return;
+  uint32_t v = 0;
+  int x0 = wordcol << 5;
+  const int8_t *row = src + (size_t)y * w;
+  for (int b = 0; b < 32; ++b) {
+    int x = x0 + b;
+    if (x < w && row[x] == 100) v |= 1u << b;
+  }
+  dst[(size_t)y * pitch + wordcol] = v;
+}
+
+// ---- bits -> int8 {0,100}: thread per 4 cells, 4-byte stores when the row is 4-aligned -------------
+__global__ void unpack_kernel(const uint32_t *__restrict__ src, int8_t *__restrict__ dst, int w, int h, int pitch) {
+  size_t total = (size_t)w * h;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int y = (int)(i / (size_t)w), x = (int)(i - (size_t)y * w);
+    uint32_t word = __ldg(src + (size_t)y * pitch + (x >> 5));
+    dst[i] = ((word >> (x & 31)) & 1u) ? 100 : 0;
+  }
+}
+
+__global__ void unpack4_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst4, int w4, int h, int pitch) {
+  // w is a multiple of 4 and dst is 4-byte aligned: every thread emits 4 cells as one 32-bit store
+  size_t total = (size_t)w4 * h;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int y = (int)(i / (size_t)w4), q = (int)(i - (size_t)y * w4);
+    int x = q << 2;
+    uint32_t nib = (__ldg(src + (size_t)y * pitch + (x >> 5)) >> (x & 31)) & 0xfu;
+    uint32_t v = ((nib & 1u) ? 100u : 0u) | ((nib & 2u) ? 100u << 8 : 0u) | ((nib & 4u) ? 100u << 16 : 0u) |
+                 ((nib & 8u) ? 100u << 24 : 0u);
+    dst4[i] = v;
+  }
+}
+
+// bits of the word starting at cell x0 that fall in the cell range [lo, hi]
+__device__ __forceinline__ uint32_t range_mask(int lo, int hi, int x0) {
+  lo = max(lo - x0, 0);
+  hi = min(hi - x0, 31);
+  if (lo > hi) return 0u;
+  return (hi - lo == 31) ? 0xffffffffu : (((1u << (hi - lo + 1)) - 1u) << lo);
+}
+
+// ring of thickness t along the rectangle [gx0,gx1] x [gy0,gy1] OR-ed into the grid
+__global__ void frame_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int w, int h, int pitch,
+                             int gx0, int gy0, int gx1, int gy1, int t) {
+  size_t total = (size_t)pitch * h;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int y = (int)(i / (size_t)pitch), cw = (int)(i - (size_t)y * pitch);
+    uint32_t v = in[i];
+    int x0 = cw << 5;
+    if (y >= gy0 && y <= gy1) {
+      if (y < gy0 + t || y > gy1 - t) v |= range_mask(gx0, gx1, x0);
+      else v |= range_mask(gx0, min(gx0 + t - 1, gx1), x0) | range_mask(max(gx1 - t + 1, gx0), gx1, x0);
+    }
+    out[i] = v;
+  }
+}
+
+aos_status launch_pack(Ctx *c, const int8_t *src, uint32_t *dst, int w, int h) {
+  int pitch = pitch_words_for(w);
+  dim3 grid((pitch + 127) / 128, h);
+  pack_kernel<<<grid, 128, 0, c->stream>>>(src, dst, w, h, pitch);
+  AOS_CUDA_OK(c, cudaGetLastError());
+  return AOS_OK;
+}
+
+aos_status launch_unpack(Ctx *c, const uint32_t *src, int8_t *dst, int w, int h) {
+  int pitch = pitch_words_for(w);
+  size_t total = (size_t)w * h;
+  if ((w & 3) == 0 && (((uintptr_t)dst) & 3u) == 0) {
+    size_t t4 = total / 4;
+    int grid = (int)((t4 + 255) / 256 < (size_t)kNumSMs * 32 ? (t4 + 255) / 256 : (size_t)kNumSMs * 32);
+    if (grid < 1) grid = 1;
+    unpack4_kernel<<<grid, 256, 0, c->stream>>>(src, reinterpret_cast<uint32_t *>(dst), w / 4, h, pitch);
+  } else {
+    int grid = (int)((total + 255) / 256 < (size_t)kNumSMs * 32 ? (total + 255) / 256 : (size_t)kNumSMs * 32);
+    if (grid < 1) grid = 1;
+    unpack_kernel<<<grid, 256, 0, c->stream>>>(src, dst, w, h, pitch);
+  }
+  AOS_CUDA_OK(c, cudaGetLastError());
+  return AOS_OK;
+}
+
+aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h, int gx0, int gy0, int gx1, int gy1,
+                        int t) {
+  int pitch = pitch_words_for(w);
+  size_t total = (size_t)pitch * h;
+  int grid = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+  if (grid < 1) grid = 1;
+  frame_kernel<<<grid, 256, 0, c->stream>>>(in, out, w, h, pitch, gx0, gy0, gx1, gy1, t);
+  AOS_CUDA_OK(c, cudaGetLastError());
+  return AOS_OK;
+}
+
+}  // namespace aos

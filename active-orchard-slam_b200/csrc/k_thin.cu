@@ -1,0 +1,190 @@
+// k_thin.cu -- Zhang-Suen thinning (cv::ximgproc::thinning(THINNING_ZHANGSUEN), call site
+// src/aos_seed_gen_node.cpp:684) on the bit-packed grid.
+//
+// One launch runs kSub sub-iterations (0,1,0,1,...) on a tile held in shared memory (temporal
+// blocking): the tile is loaded by TMA with a halo of kSub rows above/below and one 32-cell word left/
+// right, every sub-iteration invalidates one more ring of the halo, and after kSub of them the owned
+// interior is exact.  A sub-iteration is the parallel update of the published algorithm -- deletions are
+// computed from the pre-sub-iteration image (ping-pong between two shared-memory tiles) -- evaluated
+// 32 pixels at a time with bit-sliced logic: the neighbour count B through a carry-save adder tree, the
+// transition count A==1 through a one/two accumulator, 32 lanes of a warp = 32 consecutive words of a row,
+// left/right words by shuffle.  Image-border pixels (row 0, H-1, column 0, W-1) are never deleted, as in
+// opencv_contrib's loops (1..rows-2, 1..cols-2).
+//
+// Convergence: the reference stops when a full (0,1) pair changes nothing; extra sub-iterations at the
+// fixed point are no-ops, so running whole launches until one deletes nothing in its owned region gives
+// the same image.  Launches are queued in batches; each launch first reads its predecessor's deletion
+// counter and exits at once if that was zero, so the host synchronises once per batch, not per launch.
+#include "aos_common.cuh"
+
+namespace aos {
+
+constexpr int kSub = 8;                       // sub-iterations per launch (even)
+constexpr int kThinOwn = 112;                 // owned rows per CTA
+constexpr int kThinBox = kThinOwn + 2 * kSub; // 128 tile rows
+constexpr int kThinThreads = 256;
+constexpr int kThinBatch = 8;                 // launches queued per host synchronisation
+
+__device__ __forceinline__ uint32_t zs_delete_mask(uint32_t C, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t p5,
+                                                   uint32_t p6, uint32_t p7, uint32_t p8, uint32_t p9, int iter) {
+  // B = p2+...+p9 by carry-save addition
+  uint32_t s1 = p2 ^ p3 ^ p4, c1 = (p2 & p3) | (p4 & (p2 ^ p3));
+  uint32_t s2 = p5 ^ p6 ^ p7, c2 = (p5 & p6) | (p7 & (p5 ^ p6));
+  uint32_t s3 = p8 ^ p9, c3 = p8 & p9;
+  uint32_t b0 = s1 ^ s2 ^ s3, c4 = (s1 & s2) | (s3 & (s1 ^ s2));
+  uint32_t s5 = c1 ^ c2 ^ c3, c5 = (c1 & c2) | (c3 & (c1 ^ c2));
+  uint32_t b1 = s5 ^ c4, c6 = s5 & c4;
+  uint32_t b2 = c5 ^ c6, b3 = c5 & c6;
+  uint32_t condB = (b1 | b2) & ~b3 & ~(b0 & b1 & b2);  // 2 <= B <= 6
+  // A = number of 0->1 transitions in p2,p3,...,p9,p2 ; need exactly one
+  uint32_t one = ~p2 & p3, two = 0, t;
+  t = ~p3 & p4; two |= one & t; one |= t;
+  t = ~p4 & p5; two |= one & t; one |= t;
+  t = ~p5 & p6; two |= one & t; one |= t;
+  t = ~p6 & p7; two |= one & t; one |= t;
+  t = ~p7 & p8; two |= one & t; one |= t;
+  t = ~p8 & p9; two |= one & t; one |= t;
+  t = ~p9 & p2; two |= one & t; one |= t;
+  uint32_t condA = one & ~two;
+  uint32_t condM = iter == 0 ? ~(p4 & p6 & (p2 | p8)) : ~(p2 & p8 & (p4 | p6));
+  return C & condB & condA & condM;
+}
+
+struct ThinParams {
+  int w, h, pitch;
+};
+
+__global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                            const __grid_constant__ ThinParams P,
+                                                            uint32_t *__restrict__ dst, const int *prev_count,
+                                                            int *my_count) {
+  __shared__ __align__(128) uint32_t buf[2][kThinBox * kTileBoxW];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_deleted;
+  if (prev_count && *prev_count == 0) return;  // predecessor already at the fixed point
+
+  const int own0 = blockIdx.x * kTileOwnW;
+  const int y0 = blockIdx.y * kThinOwn - kSub;  // image row of tile row 0
+  if (threadIdx.x == 0) {
+    s_deleted = 0;
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(kThinBox * kTileBoxW * 4));
+    tma_load_2d(buf[0], &tmap, &bar, own0 - 4, y0);
+  }
+  mbar_wait(&bar, 0);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cw = own0 - kTileLane0 + lane;
+  const int sl = lane + kTileLane0;  // this lane's word inside a staged row
+  // pixels that may never be deleted: x == 0, x == w-1 (and rows 0, h-1 below)
+  uint32_t xmask = 0xffffffffu;
+  if (cw == 0) xmask &= ~1u;
+  if (cw == ((P.w - 1) >> 5)) xmask &= ~(1u << ((P.w - 1) & 31));
+  const bool lane_owned = lane >= kTileLane0 && lane < kTileLane0 + kTileOwnW && cw >= 0;
+  constexpr int kRowsPerWarp = kThinBox / (kThinThreads / 32);  // 16
+  const int r_begin = warp * kRowsPerWarp, r_end = r_begin + kRowsPerWarp;
+  int deleted_owned = 0;
+
+  int cur = 0;
+#pragma unroll 1
+  for (int s = 0; s < kSub; ++s) {
+    const uint32_t *src = buf[cur];
+    uint32_t *out = buf[cur ^ 1];
+    const int iter = s & 1;
+    // sliding window over rows: (centre, west-neighbour plane, east-neighbour plane) of rows r-1, r, r+1
+    auto planes = [&](int r, uint32_t &c, uint32_t &wv, uint32_t &ev) {
+      c = (r >= 0 && r < kThinBox) ? src[r * kTileBoxW + sl] : 0u;
+      uint32_t l = __shfl_up_sync(0xffffffffu, c, 1), rr = __shfl_down_sync(0xffffffffu, c, 1);
+      wv = __funnelshift_l(l, c, 1);   // bit i = pixel x-1
+      ev = __funnelshift_r(c, rr, 1);  // bit i = pixel x+1
+    };
+    uint32_t nC, nW, nE, cC, cW, cE, sC, sW, sE;
+    planes(r_begin - 1, nC, nW, nE);
+    planes(r_begin, cC, cW, cE);
+    for (int r = r_begin; r < r_end; ++r) {
+      planes(r + 1, sC, sW, sE);
+      uint32_t res = cC;
+      if (r > 0 && r < kThinBox - 1) {
+        // a pixel with all 8 neighbours set (or a zero pixel) cannot go: skip solid / empty stretches
+        uint32_t boundary = cC & ~(nC & nW & nE & cW & cE & sC & sW & sE);
+        if (__any_sync(0xffffffffu, boundary != 0)) {
+          const int y = y0 + r;
+          uint32_t del = zs_delete_mask(cC, nC, nE, cE, sE, sC, sW, cW, nW, iter);
+          del &= xmask;
+          if (y <= 0 || y >= P.h - 1) del = 0;
+          res = cC & ~del;
+          if (lane_owned && r >= kSub && r < kSub + kThinOwn) deleted_owned |= (del != 0);
+        }
+      }
+      out[r * kTileBoxW + sl] = res;
+      nC = cC; nW = cW; nE = cE;
+      cC = sC; cW = sW; cE = sE;
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  // write back the owned interior (rows kSub .. kSub+kThinOwn-1, lanes 1..30)
+  const uint32_t *fin = buf[cur];
+  for (int r = kSub + warp; r < kSub + kThinOwn; r += kThinThreads / 32) {
+    int y = y0 + r;
+    if (y >= P.h) break;
+    if (lane_owned && cw < P.pitch) dst[(size_t)y * P.pitch + cw] = fin[r * kTileBoxW + sl];
+  }
+  if (__any_sync(0xffffffffu, deleted_owned) && lane == 0) atomicOr(&s_deleted, 1);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_deleted) atomicAdd(my_count, 1);
+}
+
+// img holds the input; on return *result_in_scratch says which of (img, scratch) holds the skeleton.
+aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters) {
+  ThinParams P{w, h, pitch_words_for(w)};
+  CUtensorMap map_img, map_scr;
+  if (!make_bitgrid_tmap(&map_img, img, P.pitch, h, kTileBoxW, kThinBox) ||
+      !make_bitgrid_tmap(&map_scr, scratch, P.pitch, h, kTileBoxW, kThinBox)) {
+    set_error(c, "cuTensorMapEncodeTiled failed (thin)");
+    return AOS_ERR_CUDA;
+  }
+  int words_used = (w + 31) >> 5;
+  dim3 grid((words_used + kTileOwnW - 1) / kTileOwnW, (h + kThinOwn - 1) / kThinOwn);
+  AOS_CUDA_OK(c, c->misc.reserve(4096));
+  int *d_counts = c->misc.as<int>() + 64;  // [kThinBatch] deletion counters
+  int total = 0;
+  bool src_is_img = true;
+  for (int batch = 0; batch < 4096; ++batch) {
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_counts, 0, sizeof(int) * kThinBatch, c->stream));
+    for (int j = 0; j < kThinBatch; ++j) {
+      bool from_img = src_is_img ^ (j & 1);
+      thin_kernel<<<grid, kThinThreads, 0, c->stream>>>(from_img ? map_img : map_scr, P, from_img ? scratch : img,
+                                                        j == 0 ? nullptr : d_counts + j - 1, d_counts + j);
+    }
+    AOS_CUDA_OK(c, cudaGetLastError());
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_counts, sizeof(int) * kThinBatch, cudaMemcpyDeviceToHost, c->stream));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    int conv = -1;
+    for (int j = 0; j < kThinBatch; ++j)
+      if (c->h_flag[j] == 0) {
+        conv = j;
+        break;
+      }
+    if (conv >= 0) {
+      total += conv + 1;
+      // launch `conv` wrote an unchanged copy: its destination holds the skeleton
+      bool from_img = src_is_img ^ (conv & 1);
+      bool result_in_img = !from_img;
+      if (!result_in_img)
+        AOS_CUDA_OK(c, cudaMemcpyAsync(img, scratch, (size_t)P.pitch * h * 4, cudaMemcpyDeviceToDevice, c->stream));
+      break;
+    }
+    total += kThinBatch;
+    // kThinBatch is even: the next batch reads from the same buffer kind as this one did
+  }
+  if (launches) *launches = total;
+  if (subiters) *subiters = total * kSub;
+  return AOS_OK;
+}
+
+}  // namespace aos

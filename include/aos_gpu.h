@@ -1,0 +1,159 @@
+/*
+ * aos_gpu.h -- C-ABI of libaos_gpu: the B200-native map -> GvdGraph hot path of Active-orchard-slam.
+ *
+ * The reference has no plugin seam on this path: everything is a private member of a ROS 2 node
+ * class.  The two cut lines are the bodies of
+ *     AosSeedGenNode::processPointCloud   (src/aos_seed_gen_node.cpp:452-579, callers :247, :284)
+ *     AosGvdNode::processGraph            (src/aos_gvd_node.cpp:255-318, callers :127,149,170,176,182)
+ * and these entry points are what a C++ node would call in their place (INTEGRATION.md shows the
+ * shim).  Plain pointers and sizes only; no exceptions cross the boundary; every call returns an
+ * aos_status and aos_last_error() gives the text.  A context is re-entrant per handle, not
+ * thread-safe per handle (the reference runs one callback at a time per process:
+ * rclcpp::spin single-threaded executor, seed_gen:2676, gvd:1648).
+ *
+ * All file:line citations are into the reference repository.
+ */
+#ifndef AOS_GPU_H
+#define AOS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AOS_API __attribute__((visibility("default")))
+
+typedef struct aos_ctx aos_ctx;
+
+typedef enum {
+  AOS_OK = 0,
+  AOS_ERR_INVALID = -1,   /* bad argument */
+  AOS_ERR_CUDA = -2,      /* CUDA runtime/driver error; see aos_last_error */
+  AOS_ERR_CAPACITY = -3,  /* a caller-provided buffer is too small */
+  AOS_ERR_STATE = -4,     /* stage called before its inputs exist (reference: silent early return, gvd:257) */
+  AOS_ERR_NO_DEVICE = -5
+} aos_status;
+
+/* Where a caller-provided buffer lives. */
+typedef enum { AOS_MEM_HOST = 0, AOS_MEM_DEVICE = 1 } aos_mem;
+
+/* Parameters of aos_seed_gen_node that reach the path.  Names and defaults follow
+ * config/aos_planner_params.yaml and the declare_parameter calls at seed_gen:69-83; the node keeps
+ * them in float members (seed_gen:2605-2612), hence float here. */
+typedef struct {
+  float clipping_minz, clipping_maxz;                 /* -0.4, 0.5  (yaml :86-89) */
+  float clipping_minx, clipping_maxx;                 /* -5, 72   used only when the polygon is empty */
+  float clipping_miny, clipping_maxy;                 /* -10, 20 */
+  float grid_resolution;                              /* 0.05 */
+  float inflation_radius;                             /* 0.8 */
+  double cluster_min_length;                          /* 2.0 (seed_gen:83,100) */
+  int32_t n_polygon;                                  /* exploration polygon vertices (seed_gen:193-215, :250-277) */
+  const double *polygon;                              /* host, x,y pairs */
+  int32_t n_exclusion;                                /* exclusion discs (seed_gen:487-499 hard-codes 11) */
+  const float *exclusion;                             /* host, x,y,r triples */
+} aos_seed_params;
+
+/* nav_msgs/OccupancyGrid.info subset (seed_gen:590-600). */
+typedef struct {
+  int32_t width, height;
+  float resolution;
+  double origin_x, origin_y;
+} aos_grid_info;
+
+/* Which grid of the seed stage (all W*H, row-major x + y*W, y up). */
+typedef enum {
+  AOS_GRID_RAW = 0,             /* generateOccupancyGrid             seed_gen:581-622 */
+  AOS_GRID_INFLATED = 1,        /* applyInflation                    seed_gen:933-967 */
+  AOS_GRID_OCCUPANCY = 2,       /* + markBoundariesAsOccupied -> /occupancy_grid   seed_gen:708-757 */
+  AOS_GRID_OPENED = 3,          /* morphologyEx(OPEN) inside skeletonizeOccupancyGrid seed_gen:678-680 */
+  AOS_GRID_SKELETON = 4,        /* skeletonizeOccupancyGrid, un-framed (ray casts use this) seed_gen:560-566 */
+  AOS_GRID_SKELETON_FRAMED = 5  /* + markPolygonBoundaryAsOccupied -> /skeletonized_occupancy_grid seed_gen:772-825 */
+} aos_grid_id;
+
+typedef enum {
+  AOS_FMT_INT8 = 0,  /* nav_msgs/OccupancyGrid data: 0 / 100, one byte per cell */
+  AOS_FMT_BITS = 1   /* 32 cells per uint32 word, LSB = lowest x, row pitch = aos_bits_pitch_words() words */
+} aos_grid_fmt;
+
+/* Cluster (seed_gen:35-41) in discovery order == raster order of the first cell. */
+typedef struct {
+  int32_t label;        /* canonical label: min linear index (x + y*W) of the component */
+  int32_t size;
+  float center_x, center_y; /* grid units, float32 as in seed_gen:1053-1059 */
+  float length;         /* metres, seed_gen:1062-1074 */
+  int32_t reserved;
+  int64_t sum_x, sum_y; /* exact integer sums */
+  int64_t max_d2;       /* exact max pairwise squared cell distance */
+} aos_cluster;
+
+/* TreeRowFromCluster (seed_gen:44-49) plus the index of its cluster. */
+typedef struct {
+  double center_x, center_y;
+  double start_x, start_y;
+  double end_x, end_y;
+  double length;
+  int32_t cluster;
+  int32_t reserved;
+} aos_tree_row;
+
+typedef struct {
+  aos_grid_info info;
+  int32_t n_clusters;   /* all components (before the cluster_min_length filter) */
+  int32_t n_rows;       /* all_tree_rows == exploration_tree_rows (seed_gen:1405-1419) */
+  int32_t thinning_launches, thinning_subiters; /* diagnostics */
+  int64_t n_points_in;  /* points that survived the filters (diagnostic) */
+} aos_seed_summary;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+AOS_API aos_status aos_create(int device, aos_ctx **out);
+AOS_API void aos_destroy(aos_ctx *ctx);
+AOS_API const char *aos_last_error(const aos_ctx *ctx);
+AOS_API const char *aos_version(void);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*); default is a context-owned stream. */
+AOS_API aos_status aos_set_stream(aos_ctx *ctx, void *cuda_stream);
+AOS_API aos_status aos_synchronize(aos_ctx *ctx);
+/* Words per row of an AOS_FMT_BITS grid of this width. */
+AOS_API int32_t aos_bits_pitch_words(int32_t width);
+
+/* ---- grid geometry: getActiveBounds + generateOccupancyGrid header (seed_gen:874-890, 587-600) - */
+AOS_API aos_status aos_grid_geometry(const aos_seed_params *p, aos_grid_info *info);
+
+/* ---- the seed-gen half: replaces the body of processPointCloud (seed_gen:452-579) up to and
+ *      including clusterOccupiedCells / convertClustersToTreeRows' row extraction (:1309-1406).
+ *      `points` is the post-RadiusOutlierRemoval cloud as PointCloud2 bytes: n_points records of
+ *      point_step bytes with float32 x,y,z at byte offsets off_x/off_y/off_z (pcl::fromROSMsg,
+ *      seed_gen:232-233).  point_step==16 with offsets 0/4/8 and a 16-byte aligned base is the
+ *      vectorised fast path.  Asynchronous on the context stream; results stay on the device until
+ *      fetched with the getters below (each getter synchronises). ------------------------------- */
+AOS_API aos_status aos_seed_stage(aos_ctx *ctx, const aos_seed_params *p, const void *points,
+                                  size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y,
+                                  uint32_t off_z, aos_mem points_mem);
+AOS_API aos_status aos_seed_summary_get(aos_ctx *ctx, aos_seed_summary *out);
+AOS_API aos_status aos_get_grid(aos_ctx *ctx, aos_grid_id which, aos_grid_fmt fmt, void *dst,
+                                size_t dst_bytes, aos_mem dst_mem);
+/* Device pointer of the context-owned bit grid (valid until the next aos_seed_stage). */
+AOS_API aos_status aos_grid_device_bits(aos_ctx *ctx, aos_grid_id which, const uint32_t **bits,
+                                        int32_t *pitch_words);
+/* Per-cell canonical cluster label (min linear index of the component; -1 elsewhere), int32 W*H. */
+AOS_API aos_status aos_get_labels(aos_ctx *ctx, int32_t *dst, size_t dst_count, aos_mem dst_mem);
+AOS_API aos_status aos_get_clusters(aos_ctx *ctx, aos_cluster *dst, int32_t capacity, int32_t *n_out);
+AOS_API aos_status aos_get_tree_rows(aos_ctx *ctx, aos_tree_row *dst, int32_t capacity, int32_t *n_out);
+
+/* ---- stand-alone steps (unit tests, parameter sweeps; same kernels as aos_seed_stage) -------- */
+/* Each takes/returns AOS_FMT_BITS grids in DEVICE memory with pitch aos_bits_pitch_words(width). */
+AOS_API aos_status aos_inflate_bits(aos_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t *out_border,
+                                    int32_t width, int32_t height, int32_t radius_cells);
+AOS_API aos_status aos_open_bits(aos_ctx *ctx, const uint32_t *in, uint32_t *out, int32_t width, int32_t height);
+AOS_API aos_status aos_thin_bits(aos_ctx *ctx, uint32_t *inout, int32_t width, int32_t height,
+                                 int32_t *launches, int32_t *subiters);
+AOS_API aos_status aos_pack_int8(aos_ctx *ctx, const int8_t *src, aos_mem src_mem, uint32_t *dst_bits,
+                                 int32_t width, int32_t height);
+AOS_API aos_status aos_unpack_int8(aos_ctx *ctx, const uint32_t *src_bits, int8_t *dst, aos_mem dst_mem,
+                                   int32_t width, int32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOS_GPU_H */

@@ -1,0 +1,46 @@
+"""CPU-side checks of the C-ABI boundary: the library loads and exports every symbol of include/aos_gpu.h."""
+import ctypes
+import os
+import re
+
+from aos_gpu import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "aos_gpu.h")).read()
+    return sorted(set(re.findall(r"AOS_API\s+[\w\s\*]+?\b(aos_\w+)\s*\(", hdr)))
+
+
+def test_library_built_and_exports_header_symbols():
+    import __graft_entry__ as g
+    g.build()
+    L = ctypes.CDLL(lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/aos_gpu.h but not exported"
+    assert sorted(lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_grid_geometry_matches_baseline_sizes():
+    """generateOccupancyGrid dims (seed_gen:587-596): pure host code, no GPU needed."""
+    from aos_gpu import synth
+    for name, wh in (("C1", (1000, 600)), ("C2", (2000, 1200)), ("C3", (20000, 20000)), ("C4", (40000, 40000))):
+        spec = synth.config(name)
+        gi = lib.grid_geometry(lib.SeedParams(grid_resolution=spec.grid_resolution, polygon=spec.polygon))
+        assert (gi.width, gi.height) == wh
+    gi = lib.grid_geometry(lib.SeedParams(polygon=synth.REFERENCE_POLYGON))
+    assert (gi.width, gi.height) == (1546, 296)  # the field map of the default polygon
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        lib.Context(0)
+    except lib.AosError:
+        return
+    raise AssertionError("Context() must raise without a CUDA device (no CPU fallback)")

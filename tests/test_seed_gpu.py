@@ -1,0 +1,82 @@
+"""GPU parity of the seed-gen half against the oracle, through the C-ABI (bit-exact)."""
+import numpy as np
+import pytest
+
+from aos_gpu import lib, synth
+from helpers import assert_seed_parity, params_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,seed", [("TINY", 0), ("TINY", 1), ("SMALL", 0), ("SMALL", 3)])
+def test_seed_stage_small(gpu_ctx, oracle, name, seed):
+    spec = synth.config(name, seed=seed)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r)
+
+
+def test_seed_stage_c1(gpu_ctx, oracle):
+    spec = synth.config("C1", n_points=400_000)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r)
+
+
+def test_seed_stage_c2_device_points(gpu_ctx, oracle):
+    import torch
+    spec = synth.config("C2", n_points=600_000)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    dpts = torch.from_numpy(pts).cuda()
+    gpu_ctx.seed_stage(pl, dpts)
+    assert_seed_parity(gpu_ctx, r)
+
+
+def test_reference_polygon_and_exclusion_discs(gpu_ctx, oracle):
+    """The reference's own field constants: default polygon (seed_gen:196-199, negative origin,
+    non-rectangular) and the 11 exclusion discs (seed_gen:487-499)."""
+    spec = synth.OrchardSpec(extent_x=77.0, extent_y=14.0, origin_x=-4.5, origin_y=-2.4, row_pitch=3.5,
+                             n_points=300_000, seed=5, exclusion=synth.REFERENCE_EXCLUSION_DISCS)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle, polygon=synth.REFERENCE_POLYGON)
+    r = oracle.seed_stage(po, pts)
+    assert (r["w"], r["h"]) == (1546, 296)
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r)
+
+
+def test_generic_point_step(gpu_ctx, oracle):
+    """32-byte XYZI-style records with the fields at odd offsets (PointCloud2 point_step path)."""
+    spec = synth.config("TINY", seed=2)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    rec = np.zeros((len(pts), 8), np.float32)
+    rec[:, 1], rec[:, 2], rec[:, 5] = pts[:, 0], pts[:, 1], pts[:, 2]
+    gpu_ctx.seed_stage(pl, rec, point_step=32, offsets=(4, 8, 20))
+    assert_seed_parity(gpu_ctx, r)
+
+
+def test_empty_and_no_polygon(gpu_ctx, oracle):
+    po = oracle.SeedParams(clipping_minx=-1.0, clipping_maxx=9.0, clipping_miny=-2.0, clipping_maxy=5.0)
+    pl = lib.SeedParams(clipping_minx=-1.0, clipping_maxx=9.0, clipping_miny=-2.0, clipping_maxy=5.0)
+    pts = np.zeros((0, 4), np.float32)
+    r = oracle.seed_stage(po, np.zeros((1, 4), np.float32) + np.float32(np.nan))
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r)
+    rng = np.random.default_rng(0)
+    pts = np.zeros((5000, 4), np.float32)
+    pts[:, 0] = rng.uniform(-2, 10, 5000)
+    pts[:, 1] = rng.uniform(-3, 6, 5000)
+    pts[:, 2] = rng.uniform(-1, 1, 5000)
+    pts[::97, 0] = np.nan
+    pts[5::101, 2] = np.inf
+    r = oracle.seed_stage(po, pts)
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r)
