@@ -19,6 +19,7 @@ GRID_RAW, GRID_INFLATED, GRID_OCCUPANCY, GRID_OPENED, GRID_SKELETON, GRID_SKELET
 FMT_INT8, FMT_BITS = 0, 1
 
 EXPORTED_SYMBOLS = [
+    "aos_set_profiling", "aos_get_stage_times",
     "aos_create", "aos_destroy", "aos_last_error", "aos_version", "aos_set_stream", "aos_synchronize",
     "aos_bits_pitch_words", "aos_grid_geometry", "aos_seed_stage", "aos_seed_summary_get", "aos_get_grid",
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
@@ -59,6 +60,10 @@ class CTreeRow(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class CStageTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_float)]
+
+
 class CSeedSummary(C.Structure):
     _fields_ = [("info", CGridInfo), ("n_clusters", C.c_int32), ("n_rows", C.c_int32),
                 ("thinning_launches", C.c_int32), ("thinning_subiters", C.c_int32), ("n_points_in", C.c_int64)]
@@ -91,6 +96,8 @@ def load() -> C.CDLL:
     L.aos_set_stream.argtypes = [vp, vp]
     L.aos_synchronize.argtypes = [vp]
     L.aos_bits_pitch_words.argtypes = [i32]
+    L.aos_set_profiling.argtypes = [vp, C.c_int]
+    L.aos_get_stage_times.argtypes = [vp, vp, i32, C.POINTER(i32)]
     L.aos_grid_geometry.argtypes = [C.POINTER(CSeedParams), C.POINTER(CGridInfo)]
     L.aos_seed_stage.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.aos_seed_summary_get.argtypes = [vp, C.POINTER(CSeedSummary)]
@@ -171,6 +178,16 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self.L.aos_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "aos_set_stream")
+
+    def set_profiling(self, on: bool):
+        self._check(self.L.aos_set_profiling(self.h, int(on)), "aos_set_profiling")
+
+    def stage_times(self):
+        n = C.c_int32()
+        self._check(self.L.aos_get_stage_times(self.h, None, 0, C.byref(n)), "aos_get_stage_times")
+        arr = (CStageTime * max(n.value, 1))()
+        self._check(self.L.aos_get_stage_times(self.h, arr, n.value, C.byref(n)), "aos_get_stage_times")
+        return [(arr[i].name.decode(), float(arr[i].ms)) for i in range(n.value)]
 
     def synchronize(self):
         self._check(self.L.aos_synchronize(self.h), "aos_synchronize")

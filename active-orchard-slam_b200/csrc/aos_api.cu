@@ -104,6 +104,7 @@ void aos_destroy(aos_ctx *c) {
                     &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
                     &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf};
   for (DevBuf *b : bufs) b->release();
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -119,6 +120,29 @@ aos_status aos_set_stream(aos_ctx *c, void *cuda_stream) {
   }
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
+  return AOS_OK;
+}
+
+aos_status aos_set_profiling(aos_ctx *c, int enabled) {
+  if (!c) return AOS_ERR_INVALID;
+  c->profile = enabled != 0;
+  return AOS_OK;
+}
+
+aos_status aos_get_stage_times(aos_ctx *c, aos_stage_time *dst, int32_t capacity, int32_t *n_out) {
+  if (!c) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  int n = c->marks.empty() ? 0 : (int)c->marks.size() - 1;
+  if (n_out) *n_out = n;
+  if (!dst) return AOS_OK;
+  if (capacity < n) return AOS_ERR_CAPACITY;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_pool[c->marks[i].second], c->ev_pool[c->marks[i + 1].second]);
+    memset(dst[i].name, 0, sizeof(dst[i].name));
+    strncpy(dst[i].name, c->marks[i + 1].first.c_str(), sizeof(dst[i].name) - 1);
+    dst[i].ms = ms;
+  }
   return AOS_OK;
 }
 
@@ -187,29 +211,36 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   AOS_CUDA_OK(c, cudaMemsetAsync(c->g_scratch.p, 0, gbytes, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(c->misc.p, 0, 4096, st));
 
+  c->marks.clear();
+  c->mark("start");
   const void *dpoints = points;
   if (points_mem == AOS_MEM_HOST && n_points) {
     AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, st));
     dpoints = c->points_stage.p;
   }
+  c->mark("h2d_points");
   unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->misc.as<char>() + 1024);
   s = launch_bin(c, P, dpoints, n_points, point_step, off_x, off_y, off_z, c->g_raw.as<uint32_t>(), d_kept);
   if (s != AOS_OK) return s;
 
+  c->mark("bin");
   // applyInflation: int(inflation_radius / grid_resolution) in float (seed_gen:936)
   const int R = static_cast<int>(p->inflation_radius / p->grid_resolution);
   AOS_REQUIRE(c, R >= 0, "negative inflation radius");
   s = launch_inflate(c, c->g_raw.as<uint32_t>(), c->g_infl.as<uint32_t>(), c->g_occ.as<uint32_t>(), P.w, P.h, R);
   if (s != AOS_OK) return s;
+  c->mark("inflate");
   // skeletonizeOccupancyGrid runs on the inflated grid WITHOUT the frame (seed_gen:560)
   s = launch_open(c, c->g_infl.as<uint32_t>(), c->g_open.as<uint32_t>(), P.w, P.h);
   if (s != AOS_OK) return s;
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_open.p, gbytes, cudaMemcpyDeviceToDevice, st));
+  c->mark("open");
   int launches = 0, subiters = 0;
   s = launch_thin(c, c->g_skel.as<uint32_t>(), c->g_scratch.as<uint32_t>(), P.w, P.h, &launches, &subiters);
   if (s != AOS_OK) return s;
 
+  c->mark("thin");
   // markPolygonBoundaryAsOccupied (seed_gen:772-825)
   if (p->n_polygon > 0) {
     double bx0 = p->polygon[0], bx1 = bx0, by0 = p->polygon[1], by1 = by0;
@@ -230,8 +261,10 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   }
   if (s != AOS_OK) return s;
 
+  c->mark("frame");
   s = run_clusters(c, P, c->g_skel.as<uint32_t>(), static_cast<float>(p->cluster_min_length));
   if (s != AOS_OK) return s;
+  c->mark("cluster_tail");
 
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag + 32, d_kept, 8, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));

@@ -176,6 +176,22 @@ aos_status launch_labels(Ctx *c, int32_t *dst);
 
 struct Ctx {
   int device = 0;
+  // per-stage CUDA-event timers (aos_set_profiling)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<std::string, int>> marks;  // (stage that ENDS at this event, event index)
+  void mark(const char *name) {
+    if (!profile) return;
+    int i = (int)marks.size();
+    if (i >= (int)ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    cudaEventRecord(ev_pool[i], stream);
+    marks.emplace_back(name, i);
+  }
+
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;

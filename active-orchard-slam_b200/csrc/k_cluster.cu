@@ -15,6 +15,10 @@
 //              filters, farthest / opposite-farthest cells (row start / end).
 // Order-dependent details of the reference (float32 running sums once they pass 2^24, first-in-BFS-order
 // tie breaks) are resolved by an exact BFS-order replay of the flagged clusters (bfs_replay_kernel).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "aos_common.cuh"
 
 namespace aos {
@@ -387,16 +391,19 @@ __device__ __forceinline__ long long d2ll(int ax, int ay, int bx, int by) {
 __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
     const __grid_constant__ SeedDeviceParams P, const ClusterAcc *__restrict__ acc, const uint32_t *__restrict__ offsets,
     const int *__restrict__ grouped, const int *__restrict__ root_cellpos, float min_length,
-    const float *__restrict__ replay_centre /* 2 per cluster or null */, const int *__restrict__ order_rank,
+    const int *__restrict__ flagged /* null: all clusters; else the replayed ones */,
+    const int *__restrict__ bfs_cells /* BFS-ordered cells of replayed clusters (same offsets) */,
+    const float *__restrict__ replay_centre /* 2 per cluster, valid for replayed clusters */,
     aos_cluster *__restrict__ out_clusters, RowOut *__restrict__ out_rows) {
   __shared__ unsigned long long s_u64[kClThreads / 32];
   __shared__ long long s_i64[kClThreads / 32];
   __shared__ int s_int[kClThreads / 32];
-  const int c = blockIdx.x;
+  const bool replayed = flagged != nullptr;
+  const int c = replayed ? flagged[blockIdx.x] : (int)blockIdx.x;
   const ClusterAcc a = acc[c];
   const int n = (int)a.size;
-  const int *cells = grouped + offsets[c];
-  const int *ranks = order_rank ? order_rank + offsets[c] : nullptr;
+  // a replayed cluster's cell list is in BFS order, so the list index is the BFS rank
+  const int *cells = (replayed ? bfs_cells : grouped) + offsets[c];
   const int w = P.w;
 
   // ---- exact max pairwise squared distance -------------------------------------------------------
@@ -441,13 +448,13 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
   int flags = 0;
   float cx, cy;
   const bool exact_sum = a.sumx < (1ull << 24) && a.sumy < (1ull << 24);
-  if (exact_sum || replay_centre == nullptr) {
+  if (replayed) {
+    cx = replay_centre[2 * c];
+    cy = replay_centre[2 * c + 1];
+  } else {
     cx = __fdiv_rn((float)a.sumx, (float)(unsigned long long)n);
     cy = __fdiv_rn((float)a.sumy, (float)(unsigned long long)n);
     if (!exact_sum) flags |= kFlagNeedsOrder;
-  } else {
-    cx = replay_centre[2 * c];
-    cy = replay_centre[2 * c + 1];
   }
   // length (seed_gen:1068,1074): float( sqrt(int d2) [double] * res [float->double] )
   float length = maxd2 > 0 ? (float)(sqrt((double)maxd2) * (double)P.res) : 0.0f;
@@ -484,7 +491,7 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
       double d2 = dx * dx + dy * dy;
       if ((unsigned long long)__double_as_longlong(d2) == max1 && max1 != 0ull) {
         ++ties;
-        long long key = ((long long)(ranks ? ranks[i] : 0) << 32) | (unsigned int)p;
+        long long key = ((long long)(replayed ? i : 0) << 32) | (unsigned int)p;
         pick = key < pick ? key : pick;
       }
     }
@@ -497,7 +504,7 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
       first_pos = root_cellpos[c];
     } else {
       first_pos = (int)(pick1 & 0xffffffffll);
-      if (nties1 > 1 && !ranks) flags |= kFlagTie;
+      if (nties1 > 1 && !replayed) flags |= kFlagTie;
       int y = first_pos / w, x = first_pos - y * w;
       double dx = (double)cell_world(P.ox, x, P.res) - rcx, dy = (double)cell_world(P.oy, y, P.res) - rcy;
       double s = sqrt(dx * dx + dy * dy);
@@ -540,14 +547,14 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
         double dot = (dx / s) * fdx + (dy / s) * fdy;
         if (dot < 0.0) {
           ++ties;
-          long long key = ((long long)(ranks ? ranks[i] : 0) << 32) | (unsigned int)p;
+          long long key = ((long long)(replayed ? i : 0) << 32) | (unsigned int)p;
           pick = key < pick ? key : pick;
         }
       }
       const int nties2 = block_reduce_sum(ties, s_int);
       const long long pick2 = block_reduce_min<long long>(pick, s_i64);
       second_pos = (int)(pick2 & 0xffffffffll);
-      if (nties2 > 1 && !ranks) flags |= kFlagTie;
+      if (nties2 > 1 && !replayed) flags |= kFlagTie;
     } else {
       // seed_gen:1388-1399: no opposite cell -> farthest from the first cell (second_idx starts at 0)
       const int fy = first_pos / w, fx = first_pos - fy * w;
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
         double dx = (double)cell_world(P.ox, x, P.res) - fwx, dy = (double)cell_world(P.oy, y, P.res) - fwy;
         if ((unsigned long long)__double_as_longlong(dx * dx + dy * dy) == max3 && max3 != 0ull) {
           ++ties;
-          long long key = ((long long)(ranks ? ranks[i] : 0) << 32) | (unsigned int)p;
+          long long key = ((long long)(replayed ? i : 0) << 32) | (unsigned int)p;
           pick = key < pick ? key : pick;
         }
       }
@@ -580,7 +587,7 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
       if (max3 == 0ull) second_pos = root_cellpos[c];  // second_idx stays 0
       else {
         second_pos = (int)(pick3 & 0xffffffffll);
-        if (nties3 > 1 && !ranks) flags |= kFlagTie;
+        if (nties3 > 1 && !replayed) flags |= kFlagTie;
       }
     }
     if (threadIdx.x == 0) {
@@ -620,60 +627,120 @@ __global__ void root_cellpos_kernel(const uint32_t *__restrict__ is_root_rank, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// BFS-order replay (seed_gen:1008-1049): one warp per flagged cluster walks the component exactly as
-// the reference's queue does (neighbour order dx,dy = (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1))
-// and accumulates the float32 sums in that order.  `visited` is a scratch copy of the masked grid whose
-// bits are cleared on first visit.  Emits the BFS rank of every grouped cell.
+// BFS-order replay (seed_gen:1008-1049): one warp per flagged cluster walks the component exactly as the
+// reference's FIFO does (neighbour order dx,dy = (-1,-1),(-1,0),(-1,1),(0,-1),(0,1),(1,-1),(1,0),(1,1)),
+// accumulates the float32 sums in that order and emits the cells in BFS order.  The not-yet-visited bitmap
+// of the cluster's bounding box lives in shared memory (staged from the masked grid), the FIFO head is
+// served from a shared-memory ring, so a step costs shared-memory latency, not L2 latency.  Up to four
+// queue entries are expanded per step: lanes 8k..8k+7 own the k-th popped cell's neighbours and a lane
+// yields to any lower lane that claims the same cell, which is what sequential expansion would do.
+// Clusters whose bounding box does not fit the launch's shared memory use the global bitmap instead.
 // ---------------------------------------------------------------------------------------------------
-__global__ void bfs_replay_kernel(const __grid_constant__ SeedDeviceParams P, const int *__restrict__ flagged, int n_flagged,
-                                  const ClusterAcc *__restrict__ acc, const uint32_t *__restrict__ offsets,
-                                  const int *__restrict__ root_cellpos, uint32_t *visited, int *__restrict__ queue,
-                                  float *__restrict__ centre_out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n_flagged) return;
-  const int c = flagged[warp];
+constexpr int kRingN = 512;  // FIFO ring entries per warp (the frontier of a skeleton is a handful of cells)
+
+struct ReplayJob {
+  int cluster;
+  int wx0, y0, ww, hh;  // bounding box in words / rows
+};
+
+// Cells travel through the ring as bounding-box-relative packed coordinates  rx | ry << 20.
+template <bool SMEM>
+__global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ SeedDeviceParams P,
+                                                        const ReplayJob *__restrict__ jobs,
+                                                        const ClusterAcc *__restrict__ acc,
+                                                        const uint32_t *__restrict__ offsets,
+                                                        const int *__restrict__ root_cellpos,
+                                                        const uint32_t *__restrict__ mask, uint32_t *gvisited,
+                                                        int *__restrict__ queue, float *__restrict__ centre_out) {
+  extern __shared__ uint32_t sm[];  // ring[kRingN] | bitmap ww*hh words (SMEM only)
+  const int lane = threadIdx.x;
+  const ReplayJob job = jobs[blockIdx.x];
+  const int c = job.cluster;
   const int n = (int)acc[c].size;
-  int *q = queue + offsets[c];  // BFS order of cell positions
-  const int w = P.w, h = P.h, pitch = P.pitch;
-  const int ddx[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-  const int ddy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-  int head = 0, tail = 0;
+  int *q = queue + offsets[c];
+  const int w = P.w, pitch = P.pitch;
+  uint32_t *ring = sm;
+  uint32_t *bm = sm + kRingN;
+  const int ww = job.ww, hh = job.hh, bx0 = job.wx0 << 5, by0 = job.y0;
+  const unsigned wlim = min(ww << 5, w - bx0);  // cells of the box that exist in the image
+  if (SMEM) {
+    const uint32_t *src = mask + (size_t)by0 * pitch + job.wx0;
+    for (int ry = 0; ry < hh; ++ry)
+      for (int rx = lane; rx < ww; rx += 32) bm[ry * ww + rx] = src[(size_t)ry * pitch + rx];
+    __syncwarp();
+  }
+  // the not-yet-visited bitmap: shared copy of the box, or the global scratch copy of the whole mask
+  auto word_ptr = [&](int rx, int ry) -> uint32_t * {
+    return SMEM ? bm + ry * ww + (rx >> 5) : gvisited + (size_t)(ry + by0) * pitch + job.wx0 + (rx >> 5);
+  };
+  // neighbour k of the reference's tables dx = {-1,-1,-1,0,0,1,1,1}, dy = {-1,0,1,-1,1,-1,0,1}
+  const int sub = lane >> 3, k8 = lane & 7;
+  const int kk = k8 + (k8 >= 4);  // 0..8 without the centre (4)
+  const int mydx = kk / 3 - 1, mydy = kk % 3 - 1;
+  const unsigned lt = (1u << lane) - 1u;
+  int head = 0, tail = 1;
   float sum_x = 0.f, sum_y = 0.f;
   {
     int start = root_cellpos[c];
+    int y = start / w, x = start - y * w;
     if (lane == 0) {
       q[0] = start;
-      int y = start / w, x = start - y * w;
-      atomicAnd(&visited[(size_t)y * pitch + (x >> 5)], ~(1u << (x & 31)));
+      ring[0] = (uint32_t)(x - bx0) | ((uint32_t)(y - by0) << 20);
+      atomicAnd(word_ptr(x - bx0, y - by0), ~(1u << (x & 31)));
     }
-    tail = 1;
     __syncwarp();
   }
   while (head < tail) {
-    int cur = q[head];
-    ++head;
-    int cy = cur / w, cx = cur - cy * w;
-    sum_x = __fadd_rn(sum_x, (float)cx);
-    sum_y = __fadd_rn(sum_y, (float)cy);
-    bool take = false;
-    int nx = 0, ny = 0;
-    if (lane < 8) {
-      nx = cx + ddx[lane];
-      ny = cy + ddy[lane];
-      if (nx >= 0 && nx < w && ny >= 0 && ny < h) {
-        uint32_t word = __ldcg(&visited[(size_t)ny * pitch + (nx >> 5)]);  // atomics live in L2: bypass L1
-        take = (word >> (nx & 31)) & 1u;
+    const int avail = min(tail - head, 4);
+    // pop up to four cells in FIFO order; lanes 8k..8k+7 expand the k-th one
+    uint32_t cur = 0xffffffffu;
+    if (sub < avail) {
+      int idx = head + sub;
+      if (tail - idx <= kRingN) cur = ring[idx & (kRingN - 1)];
+      else {  // fell out of the ring (very wide frontier): re-read from the global queue
+        int pos = __ldcg(q + idx);
+        int y = pos / w;
+        cur = (uint32_t)(pos - y * w - bx0) | ((uint32_t)(y - by0) << 20);
       }
     }
-    unsigned m = __ballot_sync(0xffffffffu, take);
-    if (take) {
-      int k = __popc(m & ((1u << lane) - 1u));
-      q[tail + k] = ny * w + nx;
-      atomicAnd(&visited[(size_t)ny * pitch + (nx >> 5)], ~(1u << (nx & 31)));
+    const int rx = (int)(cur & 0xfffffu) + mydx, ry = (int)(cur >> 20) + mydy;
+    bool take = false;
+    if (sub < avail && (unsigned)rx < wlim && (unsigned)ry < (unsigned)hh) {
+      uint32_t word = SMEM ? *word_ptr(rx, ry) : __ldcg(word_ptr(rx, ry));
+      take = (word >> (rx & 31)) & 1u;
     }
+    // cells popped earlier in this step claim shared neighbours first (what sequential expansion does)
+    const uint32_t c0 = __shfl_sync(0xffffffffu, cur, 0), c1 = __shfl_sync(0xffffffffu, cur, 8),
+                   c2 = __shfl_sync(0xffffffffu, cur, 16), c3 = __shfl_sync(0xffffffffu, cur, 24);
+    auto near = [&](uint32_t p) { return abs(rx - (int)(p & 0xfffffu)) <= 1 && abs(ry - (int)(p >> 20)) <= 1; };
+    if (sub >= 1 && near(c0)) take = false;
+    if (sub >= 2 && near(c1)) take = false;
+    if (sub >= 3 && near(c2)) take = false;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (take) {
+      int slot = tail + __popc(m & lt);
+      ring[slot & (kRingN - 1)] = (uint32_t)rx | ((uint32_t)ry << 20);
+      q[slot] = (ry + by0) * w + rx + bx0;
+      atomicAnd(word_ptr(rx, ry), ~(1u << (rx & 31)));
+    }
+    // float32 running sums in FIFO order (seed_gen:1053-1057); every lane keeps the same copy
+    sum_x = __fadd_rn(sum_x, (float)((int)(c0 & 0xfffffu) + bx0));
+    sum_y = __fadd_rn(sum_y, (float)((int)(c0 >> 20) + by0));
+    if (avail > 1) {
+      sum_x = __fadd_rn(sum_x, (float)((int)(c1 & 0xfffffu) + bx0));
+      sum_y = __fadd_rn(sum_y, (float)((int)(c1 >> 20) + by0));
+    }
+    if (avail > 2) {
+      sum_x = __fadd_rn(sum_x, (float)((int)(c2 & 0xfffffu) + bx0));
+      sum_y = __fadd_rn(sum_y, (float)((int)(c2 >> 20) + by0));
+    }
+    if (avail > 3) {
+      sum_x = __fadd_rn(sum_x, (float)((int)(c3 & 0xfffffu) + bx0));
+      sum_y = __fadd_rn(sum_y, (float)((int)(c3 >> 20) + by0));
+    }
+    head += avail;
     tail += __popc(m);
     __syncwarp();
-    __threadfence_block();
   }
   if (lane == 0) {
     centre_out[2 * c] = __fdiv_rn(sum_x, (float)(unsigned long long)n);
@@ -712,6 +779,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   if (s != AOS_OK) return s;
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  c->mark("cc_mask_scan");
   const int n = c->h_flag[0];
   c->n_skel_cells = n;
   if (n == 0) return AOS_OK;
@@ -730,6 +798,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   if (s != AOS_OK) return s;
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  c->mark("cc_link_rank");
   const int nc = c->h_flag[0];
   c->n_clusters = nc;
 
@@ -746,14 +815,12 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   uint32_t *offsets = reinterpret_cast<uint32_t *>(aux + off_offsets);
   int *root_cellpos = reinterpret_cast<int *>(aux + off_rootpos);
   float *centre = reinterpret_cast<float *>(aux + off_centre);
-  int *flagged = reinterpret_cast<int *>(aux + off_flagged);
 
-  // cell_cluster int[n] | grouped int[n] | order queue int[n] | rank int[n]
-  AOS_CUDA_OK(c, c->cand_buf.reserve(sizeof(int) * 4 * (size_t)n));
+  // cell_cluster int[n] | grouped int[n] | BFS-order queue int[n]
+  AOS_CUDA_OK(c, c->cand_buf.reserve(sizeof(int) * 3 * (size_t)n));
   int *cell_cluster = c->cand_buf.as<int>();
   int *grouped = cell_cluster + n;
   int *queue = grouped + n;
-  int *rank = queue + n;
   c->d_cell_cluster = cell_cluster;
   c->d_root_cellpos = root_cellpos;
 
@@ -766,11 +833,12 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   if (s != AOS_OK) return s;
   cc_group_kernel<<<grid_for(n, 256), 256, 0, st>>>(cell_cluster, cellpos, n, offsets, acc, grouped);
 
+  c->mark("cc_stats_group");
   AOS_CUDA_OK(c, c->cl_table.reserve(sizeof(aos_cluster) * (size_t)nc + sizeof(RowOut) * (size_t)nc));
   aos_cluster *d_clusters = c->cl_table.as<aos_cluster>();
   RowOut *d_rows = reinterpret_cast<RowOut *>(d_clusters + nc);
   cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, nullptr,
-                                                     nullptr, d_clusters, d_rows);
+                                                     nullptr, nullptr, d_clusters, d_rows);
   AOS_CUDA_OK(c, cudaGetLastError());
 
   c->h_clusters.resize(nc);
@@ -780,66 +848,88 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
 
+  c->mark("cc_finalize");
   // ---- order-dependent clusters: replay the reference's BFS and finalise again --------------------
   // needed when a float32 partial sum can round (sum >= 2^24) or an arg-max tie must be broken by BFS order
   std::vector<int> need;
   for (int i = 0; i < nc; ++i)
     if (h_rows[i].flags & (kFlagNeedsOrder | kFlagTie)) need.push_back(i);
   if (!need.empty()) {
-    // visited = scratch copy of the mask (cc_prefix is free now: compact indices are no longer needed)
-    uint32_t *visited = prefix;
-    AOS_CUDA_OK(c, cudaMemcpyAsync(visited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(flagged, need.data(), sizeof(int) * need.size(), cudaMemcpyHostToDevice, st));
-    int nf = (int)need.size();
-    bfs_replay_kernel<<<(nf * 32 + 127) / 128, 128, 0, st>>>(P, flagged, nf, acc, offsets, root_cellpos, visited, queue,
-                                                             centre);
-    AOS_CUDA_OK(c, cudaGetLastError());
-    // the replayed queue becomes the cluster's cell list; its index is the BFS rank
-    // (grouped[] of flagged clusters is overwritten by the queue; rank = position)
-    // simple: copy queue segment over grouped segment and build identity ranks on the host side sizes
-    std::vector<uint32_t> h_off(nc + 1);
-    AOS_CUDA_OK(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint32_t) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    // bounding boxes come from the directional extremes already on the host-side? no: take them from acc
+    std::vector<ClusterAcc> h_acc(nc);
+    AOS_CUDA_OK(c, cudaMemcpyAsync(h_acc.data(), acc, sizeof(ClusterAcc) * (size_t)nc, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-    h_off[nc] = (uint32_t)n;
+    // shared-memory classes: bitmap words <= 2K (8 KB), <= 12K (48 KB), <= 50K (200 KB), else global bitmap
+    const size_t class_words[3] = {2048, 12288, 51200};
+    std::vector<ReplayJob> jobs[4];
     for (int i : need) {
-      size_t b = h_off[i], e = (i + 1 < nc) ? h_off[i + 1] : (size_t)n;
-      AOS_CUDA_OK(c, cudaMemcpyAsync(grouped + b, queue + b, sizeof(int) * (e - b), cudaMemcpyDeviceToDevice, st));
-    }
-    // rank[i] = i - offset  for every grouped slot (only meaningful for replayed clusters)
-    {
-      std::vector<int> h_rank(n);
-      for (int i = 0; i < nc; ++i) {
-        size_t b = h_off[i], e = (i + 1 < nc) ? h_off[i + 1] : (size_t)n;
-        for (size_t k = b; k < e; ++k) h_rank[k] = (int)(k - b);
+      const ClusterAcc &a = h_acc[i];
+      auto px = [&](int k) { int pos = (int)(a.ext[k] & 0xffffffffull); return pos % P.w; };
+      auto py = [&](int k) { int pos = (int)(a.ext[k] & 0xffffffffull); return pos / P.w; };
+      ReplayJob j;
+      j.cluster = i;
+      int x0 = px(4), x1 = px(0), y0 = py(5), y1 = py(1);
+      j.wx0 = x0 >> 5;
+      j.ww = (x1 >> 5) - j.wx0 + 1;
+      j.y0 = y0;
+      j.hh = y1 - y0 + 1;
+      size_t words = (size_t)j.ww * j.hh;
+      int cls = words <= class_words[0] ? 0 : words <= class_words[1] ? 1 : words <= class_words[2] ? 2 : 3;
+      if (j.ww >= 32768 || j.hh >= 4096) {
+        set_error(c, "cluster bounding box exceeds the replay packing limits");
+        return AOS_ERR_CAPACITY;
       }
-      AOS_CUDA_OK(c, cudaMemcpyAsync(rank, h_rank.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
-      AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+      jobs[cls].push_back(j);
     }
-    // re-run the finaliser for everything (cheap) with replayed centres where available:
-    // centre[] is only valid for flagged clusters, so un-flagged ones must keep the exact-sum path.
-    // Mark by writing NaN-free data: fill centre for un-flagged clusters from the first pass.
-    {
-      std::vector<float> h_c(2 * (size_t)nc);
-      AOS_CUDA_OK(c, cudaMemcpyAsync(h_c.data(), centre, sizeof(float) * 2 * (size_t)nc, cudaMemcpyDeviceToHost, st));
-      AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-      std::vector<char> isf(nc, 0);
-      for (int i : need) isf[i] = 1;
-      for (int i = 0; i < nc; ++i)
-        if (!isf[i]) {
-          h_c[2 * i] = c->h_clusters[i].center_x;
-          h_c[2 * i + 1] = c->h_clusters[i].center_y;
-        }
-      AOS_CUDA_OK(c, cudaMemcpyAsync(centre, h_c.data(), sizeof(float) * 2 * (size_t)nc, cudaMemcpyHostToDevice, st));
-      AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    size_t total_jobs = need.size();
+    if (getenv("AOS_DEBUG")) {
+      size_t mx[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 4; ++k)
+        for (const ReplayJob &j : jobs[k]) mx[k] = std::max(mx[k], (size_t)h_acc[j.cluster].size);
+      fprintf(stderr, "[aos] replay classes: %zu/%zu/%zu/%zu jobs, max cells %zu/%zu/%zu/%zu\n", jobs[0].size(), jobs[1].size(),
+              jobs[2].size(), jobs[3].size(), mx[0], mx[1], mx[2], mx[3]);
     }
-    cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, centre, rank,
-                                                       d_clusters, d_rows);
+    AOS_CUDA_OK(c, c->cl_stats.reserve(sizeof(ReplayJob) * total_jobs + sizeof(int) * total_jobs));
+    ReplayJob *d_jobs = c->cl_stats.as<ReplayJob>();
+    int *d_flagged = reinterpret_cast<int *>(d_jobs + total_jobs);
+    std::vector<ReplayJob> all;
+    std::vector<int> order;
+    for (int k = 0; k < 4; ++k)
+      for (const ReplayJob &j : jobs[k]) {
+        all.push_back(j);
+        order.push_back(j.cluster);
+      }
+    AOS_CUDA_OK(c, cudaMemcpyAsync(d_jobs, all.data(), sizeof(ReplayJob) * total_jobs, cudaMemcpyHostToDevice, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(d_flagged, order.data(), sizeof(int) * total_jobs, cudaMemcpyHostToDevice, st));
+    uint32_t *gvisited = prefix;  // compact indices are no longer needed: reuse as the global "unvisited" bitmap
+    if (!jobs[3].empty()) AOS_CUDA_OK(c, cudaMemcpyAsync(gvisited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
+    c->mark("replay_prep");
+    size_t done = 0;
+    for (int k = 0; k < 4; ++k) {
+      if (jobs[k].empty()) continue;
+      size_t smem = kRingN * 4 + (k < 3 ? class_words[k] * 4 : 0);
+      if (k < 3) {
+        if (smem > 48 * 1024)
+          AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, smem, st>>>(P, d_jobs + done, acc, offsets, root_cellpos,
+                                                                            mask, gvisited, queue, centre);
+      } else {
+        bfs_replay_kernel<false><<<(unsigned)jobs[k].size(), 32, smem, st>>>(P, d_jobs + done, acc, offsets, root_cellpos,
+                                                                             mask, gvisited, queue, centre);
+      }
+      done += jobs[k].size();
+    }
+    AOS_CUDA_OK(c, cudaGetLastError());
+    c->mark("replay_bfs");
+    cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length,
+                                                                         d_flagged, queue, centre, d_clusters, d_rows);
     AOS_CUDA_OK(c, cudaGetLastError());
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_clusters.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc,
                                    cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
   }
+  c->mark("replay_finalize");
   for (int i = 0; i < nc; ++i)
     if (h_rows[i].valid) c->h_rows.push_back(h_rows[i].row);
   return AOS_OK;

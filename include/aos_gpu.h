@@ -117,6 +117,16 @@ AOS_API aos_status aos_synchronize(aos_ctx *ctx);
 /* Words per row of an AOS_FMT_BITS grid of this width. */
 AOS_API int32_t aos_bits_pitch_words(int32_t width);
 
+/* ---- per-stage device timing (CUDA events on the context stream; SURVEY.md section 5 "tracing") ------
+ * When enabled, every stage call records events between its kernels; aos_get_stage_times returns the
+ * elapsed milliseconds of the last stage call, in execution order. */
+typedef struct {
+  char name[32];
+  float ms;
+} aos_stage_time;
+AOS_API aos_status aos_set_profiling(aos_ctx *ctx, int enabled);
+AOS_API aos_status aos_get_stage_times(aos_ctx *ctx, aos_stage_time *dst, int32_t capacity, int32_t *n_out);
+
 /* ---- grid geometry: getActiveBounds + generateOccupancyGrid header (seed_gen:874-890, 587-600) - */
 AOS_API aos_status aos_grid_geometry(const aos_seed_params *p, aos_grid_info *info);
 

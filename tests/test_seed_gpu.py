@@ -80,3 +80,29 @@ def test_empty_and_no_polygon(gpu_ctx, oracle):
     r = oracle.seed_stage(po, pts)
     gpu_ctx.seed_stage(pl, pts)
     assert_seed_parity(gpu_ctx, r)
+
+
+def test_long_rows_bfs_order_replay(gpu_ctx, oracle):
+    """1 km rows: float32 running sums pass 2^24, so the centre depends on the reference's BFS order
+    (seed_gen:1053-1059); the library replays that order (bfs_replay_kernel)."""
+    spec = synth.OrchardSpec(extent_x=1000.0, extent_y=16.0, row_pitch=4.0, n_points=500_000, gap_prob=0.0,
+                             jitter=0.0, outlier_count=4, seed=11)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    assert r["cl_sumx"].max() >= (1 << 24)
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r, check_labels=False)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_min_length_zero_tie_breaks(gpu_ctx, oracle, seed):
+    """cluster_min_length = 0 turns every fragment into a row, including tiny symmetric ones whose
+    farthest-cell arg-max ties are broken by BFS order in the reference (seed_gen:1359-1367)."""
+    spec = synth.config("TINY", seed=seed)
+    spec.outlier_count = 12
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle, cluster_min_length=0.0)
+    r = oracle.seed_stage(po, pts)
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r)
