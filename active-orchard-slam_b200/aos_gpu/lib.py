@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "aos_bits_pitch_words", "aos_grid_geometry", "aos_seed_stage", "aos_seed_summary_get", "aos_get_grid",
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
+    "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
 ]
 
 
@@ -111,6 +112,10 @@ def load() -> C.CDLL:
     L.aos_thin_bits.argtypes = [vp, vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.aos_pack_int8.argtypes = [vp, vp, C.c_int, vp, i32, i32]
     L.aos_unpack_int8.argtypes = [vp, vp, vp, C.c_int, i32, i32]
+    L.aos_select_seeds.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.aos_get_seeds.argtypes = [vp, vp, i32, C.POINTER(i32)]
+    L.aos_get_rows_info.argtypes = [vp, vp, i32, C.POINTER(i32)]
+    L.aos_get_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -250,6 +255,62 @@ class Context:
         if n.value:
             self._check(self.L.aos_get_clusters(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_clusters")
         return out
+
+    # ---- the whole path -----------------------------------------------------------------------
+    def map_to_graph(self, params: SeedParams, points, fetch=None) -> dict:
+        """map -> GvdGraph: seed stage (GPU), seed selection (host), gvd stage.  With `fetch` (a dict
+        that may hold preallocated, e.g. pinned, uint32 arrays "occ_bits"/"skel_bits") the published grids
+        come back bit-packed together with clusters, rows, seeds and the graph; returns a summary dict."""
+        s = self.seed_stage(params, points)
+        seeds, counts, rows_info = self.select_seeds()
+        info = {"pipeline": "seed_stage+select_seeds", "width": s.info.width, "height": s.info.height,
+                "n_clusters": s.n_clusters, "n_rows": s.n_rows, "n_seeds": len(seeds), "graph": None}
+        graph = None
+        if hasattr(self, "gvd_stage"):
+            graph = self.gvd_stage(seeds, rows_info)
+            info["pipeline"] = "seed_stage+select_seeds+gvd_stage"
+            info["graph"] = {"nodes": int(len(graph["nodes"])), "edges": int(len(graph["edges"]))}
+        if fetch is not None:
+            if fetch is True:
+                fetch = {}
+            d2h = 0
+            pitch = self.L.aos_bits_pitch_words(s.info.width)
+            for key, gid in (("occ_bits", GRID_OCCUPANCY), ("skel_bits", GRID_SKELETON_FRAMED)):
+                buf = fetch.get(key)
+                if buf is None or buf.shape != (s.info.height, pitch):
+                    buf = fetch[key] = np.empty((s.info.height, pitch), np.uint32)
+                self._check(self.L.aos_get_grid(self.h, gid, FMT_BITS, buf.ctypes.data_as(C.c_void_p), buf.nbytes,
+                                                AOS_MEM_HOST), "aos_get_grid")
+                d2h += buf.nbytes
+            cl, rows = self.clusters(), self.tree_rows()
+            d2h += cl.nbytes + rows.nbytes + seeds.nbytes + rows_info.nbytes
+            if graph is not None:
+                d2h += sum(v.nbytes for v in graph.values() if isinstance(v, np.ndarray))
+            info["d2h_bytes"] = d2h
+            info["fetched"] = fetch
+        return info
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self.L.aos_get_launch_count(self.h, C.byref(n)), "aos_get_launch_count")
+        return n.value
+
+    # ---- host seed selection ----------------------------------------------------------------
+    def select_seeds(self):
+        """Returns (seeds [S,2] float64 in /voronoi_seeds publish order, (n_virtual, n_ray, n_endpoint),
+        rows_info [R,4] float64 sorted by centre)."""
+        n = C.c_int32()
+        counts = (C.c_int32 * 3)()
+        self._check(self.L.aos_select_seeds(self.h, C.byref(n), counts), "aos_select_seeds")
+        seeds = np.zeros((n.value, 2), np.float64)
+        if n.value:
+            self._check(self.L.aos_get_seeds(self.h, seeds.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_seeds")
+        m = C.c_int32()
+        self._check(self.L.aos_get_rows_info(self.h, None, 0, C.byref(m)), "aos_get_rows_info")
+        rows = np.zeros((m.value, 4), np.float64)
+        if m.value:
+            self._check(self.L.aos_get_rows_info(self.h, rows.ctypes.data_as(C.c_void_p), m.value, C.byref(m)), "aos_get_rows_info")
+        return seeds, tuple(counts), rows
 
     def tree_rows(self) -> np.ndarray:
         n = C.c_int32()

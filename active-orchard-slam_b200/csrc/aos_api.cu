@@ -182,6 +182,7 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
               "point_step / field offsets do not describe float32 x,y,z inside a record");
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
   c->have_seed = false;
+  c->have_seeds = false;
 
   aos_grid_info gi;
   aos_grid_geometry(p, &gi);
@@ -366,6 +367,54 @@ aos_status aos_get_tree_rows(aos_ctx *c, aos_tree_row *dst, int32_t capacity, in
   if (!dst) return AOS_OK;
   if (capacity < n) return AOS_ERR_CAPACITY;
   if (n) memcpy(dst, c->h_rows.data(), sizeof(aos_tree_row) * (size_t)n);
+  return AOS_OK;
+}
+
+aos_status aos_get_launch_count(aos_ctx *c, int64_t *out) {
+  if (!c || !out) return AOS_ERR_INVALID;
+  *out = c->launches;
+  return AOS_OK;
+}
+
+aos_status aos_select_seeds(aos_ctx *c, int32_t *n_seeds, int32_t counts[3]) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_seed) {
+    set_error(c, "aos_seed_stage has not completed");
+    return AOS_ERR_STATE;
+  }
+  const SeedDeviceParams &P = c->P;
+  const size_t words = (size_t)P.pitch * P.h;
+  c->h_skel_bits.resize(words);
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_skel_bits.data(), c->g_skel.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  host_select_seeds(c->h_skel_bits.data(), P.w, P.h, P.pitch, P.ox, P.oy, P.res, c->h_rows, P.poly, P.n_poly, &c->h_seeds,
+                    c->seed_counts, &c->h_rows_info);
+  c->have_seeds = true;
+  if (n_seeds) *n_seeds = (int32_t)(c->h_seeds.size() / 2);
+  if (counts)
+    for (int k = 0; k < 3; ++k) counts[k] = c->seed_counts[k];
+  return AOS_OK;
+}
+
+aos_status aos_get_seeds(aos_ctx *c, double *dst, int32_t capacity, int32_t *n_out) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_seeds) return AOS_ERR_STATE;
+  int n = (int)(c->h_seeds.size() / 2);
+  if (n_out) *n_out = n;
+  if (!dst) return AOS_OK;
+  if (capacity < n) return AOS_ERR_CAPACITY;
+  if (n) memcpy(dst, c->h_seeds.data(), sizeof(double) * 2 * (size_t)n);
+  return AOS_OK;
+}
+
+aos_status aos_get_rows_info(aos_ctx *c, double *dst, int32_t capacity_rows, int32_t *n_out) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_seeds) return AOS_ERR_STATE;
+  int n = (int)(c->h_rows_info.size() / 4);
+  if (n_out) *n_out = n;
+  if (!dst) return AOS_OK;
+  if (capacity_rows < n) return AOS_ERR_CAPACITY;
+  if (n) memcpy(dst, c->h_rows_info.data(), sizeof(double) * 4 * (size_t)n);
   return AOS_OK;
 }
 

@@ -173,9 +173,14 @@ aos_status launch_pack(Ctx *c, const int8_t *src, uint32_t *dst, int w, int h);
 aos_status launch_unpack(Ctx *c, const uint32_t *src, int8_t *dst, int w, int h);
 aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel, float min_length);
 aos_status launch_labels(Ctx *c, int32_t *dst);
+void host_select_seeds(const uint32_t *skel_bits, int w, int h, int pitch, double ox, double oy, float res,
+                       const std::vector<aos_tree_row> &rows, const double *poly, int n_poly,
+                       std::vector<double> *seeds, int counts[3], std::vector<double> *rows_info);
+void host_merge_seeds(const double *seeds, int n, std::vector<double> *out);
 
 struct Ctx {
   int device = 0;
+  long long launches = 0;  // kernels launched by this context (aos_get_launch_count)
   // per-stage CUDA-event timers (aos_set_profiling)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -218,6 +223,13 @@ struct Ctx {
   std::vector<aos_cluster> h_clusters;
   std::vector<aos_tree_row> h_rows;
   std::vector<int32_t> h_cluster_root;  // compact index of each cluster's root
+
+  // host seed selection (host_seeds.cu)
+  bool have_seeds = false;
+  std::vector<uint32_t> h_skel_bits;  // un-framed skeleton, host copy for the ray casts
+  std::vector<double> h_seeds;        // /voronoi_seeds, x,y pairs in publish order
+  int seed_counts[3] = {0, 0, 0};     // virtual, ray, endpoint
+  std::vector<double> h_rows_info;    // /exploration_tree_rows_info: start x,y,end x,y per row, sorted
 };
 
 }  // namespace aos

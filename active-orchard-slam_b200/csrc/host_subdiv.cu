@@ -1,0 +1,340 @@
+// host_subdiv.cu -- incremental Delaunay triangulation / Voronoi facets with the arithmetic and the
+// bookkeeping of cv::Subdiv2D, which aos::VoronoiDiagram::compute drives
+// (src/utils/voronoi_diagram.cpp:51-94: Subdiv2D(rect), insert() per seed in order, getVoronoiFacetList).
+//
+// Why this runs on the host, sequentially: the reference's graph is a function of Subdiv2D's *history*, not
+// only of the Delaunay triangulation.  (1) Every facet is emitted starting at vtx.firstEdge, which is the
+// last quad-edge whose end points were (re)assigned at that vertex; extractBoundaryPoints
+// (voronoi_diagram.cpp:149-207) then merges Voronoi vertices first-come within 5 cm, so the start of each
+// cycle decides which of two nearby vertices survives.  (2) A Voronoi vertex is the intersection of the
+// bisectors of the first two edges of its triangle in quad-edge index order, evaluated from float32
+// differences and sums, so its float32 value depends on edge numbering (ulp of float32 at 1 km is 6e-5 m,
+// above the 1e-5 m position tolerance).  Both are products of the insertion order, the walking point
+// location and the free lists.  A parallel Delaunay construction produces the same triangles but neither
+// the same vertex values nor the same merge winners, so this file replays the published Guibas-Stolfi
+// quad-edge algorithm step for step (same predicates in double, same walk, same edge/vertex numbering).
+// tests/test_subdiv_cpu.py pins it bit-for-bit against the real cv2.Subdiv2D.
+//
+// Quad-edge encoding: edge id = 4 * quad + rot (rot 0..3); sym = id ^ 2; rot +1 = dual edge.
+#include <float.h>
+#include <math.h>
+
+#include <utility>
+
+#include "host_subdiv.h"
+
+namespace aos {
+
+namespace {
+enum {
+  NEXT_AROUND_ORG = 0x00,
+  NEXT_AROUND_DST = 0x22,
+  PREV_AROUND_ORG = 0x11,
+  PREV_AROUND_DST = 0x33,
+  NEXT_AROUND_LEFT = 0x13,
+  NEXT_AROUND_RIGHT = 0x31,
+  PREV_AROUND_LEFT = 0x20,
+  PREV_AROUND_RIGHT = 0x02
+};
+enum { LOC_ERROR = -2, LOC_INSIDE = 0, LOC_VERTEX = 1, LOC_ON_EDGE = 2 };
+
+inline double tri_area(float ax, float ay, float bx, float by, float cx, float cy) {
+  return ((double)bx - ax) * ((double)cy - ay) - ((double)by - ay) * ((double)cx - ax);
+}
+
+inline int pt_in_circle3(float px, float py, float ax, float ay, float bx, float by, float cx, float cy) {
+  const double eps = FLT_EPSILON * 0.125;
+  double val = ((double)ax * ax + (double)ay * ay) * tri_area(bx, by, cx, cy, px, py);
+  val -= ((double)bx * bx + (double)by * by) * tri_area(ax, ay, cx, cy, px, py);
+  val += ((double)cx * cx + (double)cy * cy) * tri_area(ax, ay, bx, by, px, py);
+  val -= ((double)px * px + (double)py * py) * tri_area(ax, ay, bx, by, cx, cy);
+  return val > eps ? 1 : val < -eps ? -1 : 0;
+}
+}  // namespace
+
+void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
+  vtx_.clear();
+  q_.clear();
+  const float big = 3.f * (float)(rw > rh ? rw : rh);
+  const float rx = (float)rx_i, ry = (float)ry_i;
+  tlx_ = rx;
+  tly_ = ry;
+  brx_ = rx + rw;
+  bry_ = ry + rh;
+  vtx_.push_back(Vertex{0, -1, 0.f, 0.f});
+  q_.push_back(QuadEdge{{0, 0, 0, 0}, {0, 0, 0, 0}});
+  free_q_ = 0;
+  free_pt_ = 0;
+  int pA = new_point(rx + big, ry, false);
+  int pB = new_point(rx, ry + big, false);
+  int pC = new_point(rx - big, ry - big, false);
+  int eAB = new_edge(), eBC = new_edge(), eCA = new_edge();
+  set_edge_points(eAB, pA, pB);
+  set_edge_points(eBC, pB, pC);
+  set_edge_points(eCA, pC, pA);
+  splice(eAB, eCA ^ 2);
+  splice(eBC, eAB ^ 2);
+  splice(eCA, eBC ^ 2);
+  recent_ = eAB;
+}
+
+int Subdiv::get_edge(int edge, int type) const {
+  edge = q_[edge >> 2].next[(edge + type) & 3];
+  return (edge & ~3) + ((edge + (type >> 4)) & 3);
+}
+
+int Subdiv::new_edge() {
+  if (free_q_ <= 0) {
+    q_.push_back(QuadEdge{{0, 0, 0, 0}, {0, 0, 0, 0}});
+    free_q_ = (int)q_.size() - 1;
+  }
+  int edge = free_q_ * 4;
+  free_q_ = q_[edge >> 2].next[1];
+  q_[edge >> 2] = QuadEdge{{edge, edge + 3, edge + 2, edge + 1}, {0, 0, 0, 0}};
+  return edge;
+}
+
+void Subdiv::delete_edge(int edge) {
+  splice(edge, get_edge(edge, PREV_AROUND_ORG));
+  int sedge = edge ^ 2;
+  splice(sedge, get_edge(sedge, PREV_AROUND_ORG));
+  edge >>= 2;
+  q_[edge].next[0] = 0;
+  q_[edge].next[1] = free_q_;
+  free_q_ = edge;
+}
+
+int Subdiv::new_point(float x, float y, bool is_virtual) {
+  if (free_pt_ == 0) {
+    vtx_.push_back(Vertex{0, -1, 0.f, 0.f});
+    free_pt_ = (int)vtx_.size() - 1;
+  }
+  int v = free_pt_;
+  free_pt_ = vtx_[v].first_edge;
+  vtx_[v] = Vertex{0, is_virtual ? 1 : 0, x, y};
+  return v;
+}
+
+void Subdiv::splice(int a, int b) {
+  int &a_next = q_[a >> 2].next[a & 3];
+  int &b_next = q_[b >> 2].next[b & 3];
+  int a_rot = (a_next & ~3) + ((a_next + 1) & 3);
+  int b_rot = (b_next & ~3) + ((b_next + 1) & 3);
+  int &a_rot_next = q_[a_rot >> 2].next[a_rot & 3];
+  int &b_rot_next = q_[b_rot >> 2].next[b_rot & 3];
+  std::swap(a_next, b_next);
+  std::swap(a_rot_next, b_rot_next);
+}
+
+void Subdiv::set_edge_points(int edge, int org, int dst) {
+  q_[edge >> 2].pt[edge & 3] = org;
+  q_[edge >> 2].pt[(edge + 2) & 3] = dst;
+  vtx_[org].first_edge = edge;
+  vtx_[dst].first_edge = edge ^ 2;
+}
+
+int Subdiv::connect_edges(int a, int b) {
+  int edge = new_edge();
+  splice(edge, get_edge(a, NEXT_AROUND_LEFT));
+  splice(edge ^ 2, b);
+  set_edge_points(edge, dst(a), org(b));
+  return edge;
+}
+
+void Subdiv::swap_edges(int edge) {
+  int sedge = edge ^ 2;
+  int a = get_edge(edge, PREV_AROUND_ORG);
+  int b = get_edge(sedge, PREV_AROUND_ORG);
+  splice(edge, a);
+  splice(sedge, b);
+  set_edge_points(edge, dst(a), dst(b));
+  splice(edge, get_edge(a, NEXT_AROUND_LEFT));
+  splice(sedge, get_edge(b, NEXT_AROUND_LEFT));
+}
+
+int Subdiv::is_right_of(float px, float py, int edge) const {
+  const Vertex &o = vtx_[org(edge)], &d = vtx_[dst(edge)];
+  double cw = tri_area(px, py, d.x, d.y, o.x, o.y);
+  return (cw > 0) - (cw < 0);
+}
+
+int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
+  int vertex = 0;
+  const int max_edges = (int)(q_.size() * 4);
+  if (px < tlx_ || py < tly_ || px >= brx_ || py >= bry_) return LOC_ERROR;  // cv::Exception(StsOutOfRange)
+  int edge = recent_;
+  int location = LOC_ERROR;
+  int right_of_curr = is_right_of(px, py, edge);
+  if (right_of_curr > 0) {
+    edge ^= 2;
+    right_of_curr = -right_of_curr;
+  }
+  for (int i = 0; i < max_edges; ++i) {
+    int onext = q_[edge >> 2].next[edge & 3];
+    int dprev = get_edge(edge, PREV_AROUND_DST);
+    int right_of_onext = is_right_of(px, py, onext);
+    int right_of_dprev = is_right_of(px, py, dprev);
+    if (right_of_dprev > 0) {
+      if (right_of_onext > 0 || (right_of_onext == 0 && right_of_curr == 0)) {
+        location = LOC_INSIDE;
+        break;
+      }
+      right_of_curr = right_of_onext;
+      edge = onext;
+    } else {
+      if (right_of_onext > 0) {
+        if (right_of_dprev == 0 && right_of_curr == 0) {
+          location = LOC_INSIDE;
+          break;
+        }
+        right_of_curr = right_of_dprev;
+        edge = dprev;
+      } else if (right_of_curr == 0 && is_right_of(vtx_[dst(onext)].x, vtx_[dst(onext)].y, edge) >= 0) {
+        edge ^= 2;
+      } else {
+        right_of_curr = right_of_onext;
+        edge = onext;
+      }
+    }
+  }
+  recent_ = edge;
+  if (location == LOC_INSIDE) {
+    const Vertex &o = vtx_[org(edge)], &d = vtx_[dst(edge)];
+    double t1 = fabs(px - o.x);  // float differences, as cv::Point2f arithmetic
+    t1 += fabs(py - o.y);
+    double t2 = fabs(px - d.x);
+    t2 += fabs(py - d.y);
+    double t3 = fabs(o.x - d.x);
+    t3 += fabs(o.y - d.y);
+    if (t1 < FLT_EPSILON) {
+      location = LOC_VERTEX;
+      vertex = org(edge);
+      edge = 0;
+    } else if (t2 < FLT_EPSILON) {
+      location = LOC_VERTEX;
+      vertex = dst(edge);
+      edge = 0;
+    } else if ((t1 < t3 || t2 < t3) && fabs(tri_area(px, py, o.x, o.y, d.x, d.y)) < FLT_EPSILON) {
+      location = LOC_ON_EDGE;
+      vertex = 0;
+    }
+  }
+  if (location == LOC_ERROR) {
+    edge = 0;
+    vertex = 0;
+  }
+  *out_edge = edge;
+  *out_vertex = vertex;
+  return location;
+}
+
+int Subdiv::insert(float px, float py) {
+  int curr_point = 0, curr_edge = 0;
+  int location = locate(px, py, &curr_edge, &curr_point);
+  if (location == LOC_ERROR) return -1;  // cv::Exception; the reference skips the seed (voronoi_diagram.cpp:83-88)
+  if (location == LOC_VERTEX) return curr_point;
+  if (location == LOC_ON_EDGE) {
+    int deleted = curr_edge;
+    recent_ = curr_edge = get_edge(curr_edge, PREV_AROUND_ORG);
+    delete_edge(deleted);
+  }
+  valid_geometry_ = false;
+  curr_point = new_point(px, py, false);
+  int base_edge = new_edge();
+  int first_point = org(curr_edge);
+  set_edge_points(base_edge, first_point, curr_point);
+  splice(base_edge, curr_edge);
+  do {
+    base_edge = connect_edges(curr_edge, base_edge ^ 2);
+    curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
+  } while (dst(curr_edge) != first_point);
+  curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
+  const int max_edges = (int)(q_.size() * 4);
+  for (int i = 0; i < max_edges; ++i) {
+    int temp_edge = get_edge(curr_edge, PREV_AROUND_ORG);
+    int temp_dst = dst(temp_edge);
+    int curr_org = org(curr_edge);
+    int curr_dst = dst(curr_edge);
+    if (is_right_of(vtx_[temp_dst].x, vtx_[temp_dst].y, curr_edge) > 0 &&
+        pt_in_circle3(vtx_[curr_org].x, vtx_[curr_org].y, vtx_[temp_dst].x, vtx_[temp_dst].y, vtx_[curr_dst].x,
+                      vtx_[curr_dst].y, vtx_[curr_point].x, vtx_[curr_point].y) < 0) {
+      swap_edges(curr_edge);
+      curr_edge = get_edge(curr_edge, PREV_AROUND_ORG);
+    } else if (curr_org == first_point) {
+      break;
+    } else {
+      curr_edge = get_edge(q_[curr_edge >> 2].next[curr_edge & 3], PREV_AROUND_LEFT);
+    }
+  }
+  return curr_point;
+}
+
+// intersection of the bisectors of (org0,dst0) and (org1,dst1): float differences and sums, double solve
+bool Subdiv::voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y) {
+  double a0 = d0.x - o0.x;
+  double b0 = d0.y - o0.y;
+  double c0 = -0.5 * (a0 * (d0.x + o0.x) + b0 * (d0.y + o0.y));
+  double a1 = d1.x - o1.x;
+  double b1 = d1.y - o1.y;
+  double c1 = -0.5 * (a1 * (d1.x + o1.x) + b1 * (d1.y + o1.y));
+  double det = a0 * b1 - a1 * b0;
+  if (det != 0) {
+    det = 1. / det;
+    *x = (float)((b0 * c1 - b1 * c0) * det);
+    *y = (float)((a1 * c0 - a0 * c1) * det);
+  } else {
+    *x = FLT_MAX;
+    *y = FLT_MAX;
+  }
+  return fabs(*x) < FLT_MAX * 0.5 && fabs(*y) < FLT_MAX * 0.5;
+}
+
+void Subdiv::calc_voronoi() {
+  if (valid_geometry_) return;
+  // clearVoronoi: nothing to clear, the structure is built once per compute()
+  const int total = (int)q_.size();
+  for (int i = 4; i < total; ++i) {
+    if (q_[i].next[0] <= 0) continue;  // free quad-edge
+    const int edge0 = i * 4;
+    if (!q_[i].pt[3]) {
+      int edge1 = get_edge(edge0, NEXT_AROUND_LEFT);
+      int edge2 = get_edge(edge1, NEXT_AROUND_LEFT);
+      float x, y;
+      if (voronoi_point(vtx_[org(edge0)], vtx_[dst(edge0)], vtx_[org(edge1)], vtx_[dst(edge1)], &x, &y)) {
+        int v = new_point(x, y, true);
+        q_[i].pt[3] = q_[edge1 >> 2].pt[3 - (edge1 & 2)] = q_[edge2 >> 2].pt[3 - (edge2 & 2)] = v;
+      }
+    }
+    if (!q_[i].pt[1]) {
+      int edge1 = get_edge(edge0, NEXT_AROUND_RIGHT);
+      int edge2 = get_edge(edge1, NEXT_AROUND_RIGHT);
+      float x, y;
+      if (voronoi_point(vtx_[org(edge0)], vtx_[dst(edge0)], vtx_[org(edge1)], vtx_[dst(edge1)], &x, &y)) {
+        int v = new_point(x, y, true);
+        q_[i].pt[1] = q_[edge1 >> 2].pt[1 + (edge1 & 2)] = q_[edge2 >> 2].pt[1 + (edge2 & 2)] = v;
+      }
+    }
+  }
+  valid_geometry_ = true;
+}
+
+void Subdiv::voronoi_facets(std::vector<float> *xy, std::vector<int32_t> *off) {
+  calc_voronoi();
+  xy->clear();
+  off->clear();
+  off->push_back(0);
+  const size_t total = vtx_.size();
+  for (size_t k = 4; k < total; ++k) {
+    if (vtx_[k].type != 0) continue;  // free or virtual
+    int edge = (vtx_[k].first_edge & ~3) + ((vtx_[k].first_edge + 1) & 3), t = edge;
+    do {
+      const Vertex &v = vtx_[org(t)];
+      xy->push_back(v.x);
+      xy->push_back(v.y);
+      t = get_edge(t, NEXT_AROUND_LEFT);
+    } while (t != edge);
+    off->push_back((int32_t)(xy->size() / 2));
+  }
+}
+
+}  // namespace aos

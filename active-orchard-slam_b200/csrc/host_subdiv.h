@@ -1,0 +1,50 @@
+// host_subdiv.h -- quad-edge incremental Delaunay / Voronoi facets (see host_subdiv.cu).
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+namespace aos {
+
+class Subdiv {
+ public:
+  // integer rectangle, as cv::Subdiv2D(Rect) receives it
+  void init(int rx, int ry, int rw, int rh);
+  // vertex id, or -1 where cv::Subdiv2D::insert would throw (point outside the rectangle / walk failure)
+  int insert(float x, float y);
+  // getVoronoiFacetList(idx = {}): one polygon per inserted vertex in insertion order, flat x,y + offsets
+  void voronoi_facets(std::vector<float> *xy, std::vector<int32_t> *off);
+
+ private:
+  struct QuadEdge {
+    int next[4];
+    int pt[4];
+  };
+  struct Vertex {
+    int first_edge;
+    int type;  // -1 free, 0 real, 1 virtual (Voronoi vertex)
+    float x, y;
+  };
+  int org(int e) const { return q_[e >> 2].pt[e & 3]; }
+  int dst(int e) const { return q_[e >> 2].pt[(e + 2) & 3]; }
+  int get_edge(int edge, int type) const;
+  int new_edge();
+  void delete_edge(int edge);
+  int new_point(float x, float y, bool is_virtual);
+  void splice(int a, int b);
+  void set_edge_points(int edge, int org, int dst);
+  int connect_edges(int a, int b);
+  void swap_edges(int edge);
+  int is_right_of(float px, float py, int edge) const;
+  int locate(float px, float py, int *edge, int *vertex);
+  static bool voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y);
+  void calc_voronoi();
+
+  std::vector<QuadEdge> q_;
+  std::vector<Vertex> vtx_;
+  int free_q_ = 0, free_pt_ = 0, recent_ = 0;
+  bool valid_geometry_ = false;
+  float tlx_ = 0, tly_ = 0, brx_ = 0, bry_ = 0;
+};
+
+}  // namespace aos

@@ -109,11 +109,13 @@ aos_status launch_bin(Ctx *c, const SeedDeviceParams &P, const void *points, siz
     size_t want = (n + per_block - 1) / per_block;
     int grid = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
     bin_points_xyz16<<<grid, kBinThreads, 0, c->stream>>>(P, reinterpret_cast<const float4 *>(points), n, bits, n_kept);
+  ++c->launches;
   } else {
     size_t want = (n + kBinThreads - 1) / kBinThreads;
     int grid = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
     bin_points_generic<<<grid, kBinThreads, 0, c->stream>>>(P, reinterpret_cast<const uint8_t *>(points), n, step, offx,
                                                             offy, offz, bits, n_kept);
+  ++c->launches;
   }
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;

@@ -109,8 +109,11 @@ static aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &b
   AOS_CUDA_OK(c, blocksum_buf.reserve(sizeof(uint32_t) * (size_t)nb));
   uint32_t *bs = blocksum_buf.as<uint32_t>();
   scan_reduce_kernel<<<nb, kScanThreads, 0, c->stream>>>(data, n, bs);
+  ++c->launches;
   scan_blocksums_kernel<<<1, kScanThreads, 0, c->stream>>>(bs, nb, d_total);
+  ++c->launches;
   scan_apply_kernel<<<nb, kScanThreads, 0, c->stream>>>(data, n, bs);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
 }
@@ -774,6 +777,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   uint32_t *d_tot = c->misc.as<uint32_t>();  // [0] skeleton cells, [1] clusters
 
   mask_count_kernel<<<grid_for(words, 256), 256, 0, st>>>(P, skel, mask, prefix);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   aos_status s = exclusive_scan_u32(c, prefix, words, c->cc_blocksum, d_tot);
   if (s != AOS_OK) return s;
@@ -791,8 +795,11 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   int *cellpos = c->cc_cellpos.as<int>();
   uint32_t *rootrank = c->cc_rootrank.as<uint32_t>();
   cc_init_kernel<<<grid_for(words, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, parent, cellpos);
+  ++c->launches;
   cc_link_kernel<<<grid_for(words, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, parent);
+  ++c->launches;
   cc_flatten_kernel<<<grid_for(n, 256), 256, 0, st>>>(parent, rootrank, n);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   s = exclusive_scan_u32(c, rootrank, (size_t)n, c->cc_blocksum, d_tot + 1);
   if (s != AOS_OK) return s;
@@ -825,13 +832,18 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   c->d_root_cellpos = root_cellpos;
 
   acc_init_kernel<<<(nc + 127) / 128, 128, 0, st>>>(acc, nc);
+  ++c->launches;
   root_cellpos_kernel<<<grid_for(n, 256), 256, 0, st>>>(rootrank, parent, cellpos, n, root_cellpos);
+  ++c->launches;
   cc_accumulate_kernel<<<grid_for(n, 256), 256, 0, st>>>(parent, rootrank, cellpos, n, P.w, cell_cluster, acc);
+  ++c->launches;
   acc_sizes_kernel<<<(nc + 127) / 128, 128, 0, st>>>(acc, nc, offsets);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   s = exclusive_scan_u32(c, offsets, (size_t)nc, c->cc_blocksum, d_tot + 2);
   if (s != AOS_OK) return s;
   cc_group_kernel<<<grid_for(n, 256), 256, 0, st>>>(cell_cluster, cellpos, n, offsets, acc, grouped);
+  ++c->launches;
 
   c->mark("cc_stats_group");
   AOS_CUDA_OK(c, c->cl_table.reserve(sizeof(aos_cluster) * (size_t)nc + sizeof(RowOut) * (size_t)nc));
@@ -839,6 +851,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   RowOut *d_rows = reinterpret_cast<RowOut *>(d_clusters + nc);
   cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, nullptr,
                                                      nullptr, nullptr, d_clusters, d_rows);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
 
   c->h_clusters.resize(nc);
@@ -913,9 +926,11 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
           AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, smem, st>>>(P, d_jobs + done, acc, offsets, root_cellpos,
                                                                             mask, gvisited, queue, centre);
+  ++c->launches;
       } else {
         bfs_replay_kernel<false><<<(unsigned)jobs[k].size(), 32, smem, st>>>(P, d_jobs + done, acc, offsets, root_cellpos,
                                                                              mask, gvisited, queue, centre);
+  ++c->launches;
       }
       done += jobs[k].size();
     }
@@ -923,6 +938,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     c->mark("replay_bfs");
     cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length,
                                                                          d_flagged, queue, centre, d_clusters, d_rows);
+  ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_clusters.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc,
                                    cudaMemcpyDeviceToHost, st));
@@ -948,6 +964,7 @@ aos_status launch_labels(Ctx *c, int32_t *dst) {
   if (c->n_skel_cells > 0) {
     labels_kernel<<<grid_for((size_t)c->n_skel_cells, 256), 256, 0, c->stream>>>(
         c->d_cell_cluster, c->cc_cellpos.as<int>(), c->d_root_cellpos, c->n_skel_cells, dst);
+  ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
   }
   return AOS_OK;

@@ -128,6 +128,7 @@ aos_status launch_inflate(Ctx *c, const uint32_t *in, uint32_t *out, uint32_t *o
   size_t smem = (size_t)box_h * kTileBoxW * 4;
   AOS_CUDA_OK(c, cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   inflate_kernel<<<grid, kInfThreads, smem, c->stream>>>(tmap, P, out, out_border);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
 }
@@ -198,6 +199,7 @@ aos_status launch_open(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h) 
   int words_used = (w + 31) >> 5;
   dim3 grid((words_used + kTileOwnW - 1) / kTileOwnW, (h + kOpenRows - 1) / kOpenRows);
   open_kernel<<<grid, kOpenThreads, 0, c->stream>>>(tmap, w, h, pitch, out);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
 }

@@ -110,6 +110,7 @@ aos_status launch_pack(Ctx *c, const int8_t *src, uint32_t *dst, int w, int h) {
   int pitch = pitch_words_for(w);
   dim3 grid((pitch + 127) / 128, h);
   pack_kernel<<<grid, 128, 0, c->stream>>>(src, dst, w, h, pitch);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
 }
@@ -122,10 +123,12 @@ aos_status launch_unpack(Ctx *c, const uint32_t *src, int8_t *dst, int w, int h)
     int grid = (int)((t4 + 255) / 256 < (size_t)kNumSMs * 32 ? (t4 + 255) / 256 : (size_t)kNumSMs * 32);
     if (grid < 1) grid = 1;
     unpack4_kernel<<<grid, 256, 0, c->stream>>>(src, reinterpret_cast<uint32_t *>(dst), w / 4, h, pitch);
+  ++c->launches;
   } else {
     int grid = (int)((total + 255) / 256 < (size_t)kNumSMs * 32 ? (total + 255) / 256 : (size_t)kNumSMs * 32);
     if (grid < 1) grid = 1;
     unpack_kernel<<<grid, 256, 0, c->stream>>>(src, dst, w, h, pitch);
+  ++c->launches;
   }
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
@@ -138,6 +141,7 @@ aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h,
   int grid = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
   if (grid < 1) grid = 1;
   frame_kernel<<<grid, 256, 0, c->stream>>>(in, out, w, h, pitch, gx0, gy0, gx1, gy1, t);
+  ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
 }

@@ -160,6 +160,7 @@ aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, i
       bool from_img = src_is_img ^ (j & 1);
       thin_kernel<<<grid, kThinThreads, 0, c->stream>>>(from_img ? map_img : map_scr, P, from_img ? scratch : img,
                                                         j == 0 ? nullptr : d_counts + j - 1, d_counts + j);
+  ++c->launches;
     }
     AOS_CUDA_OK(c, cudaGetLastError());
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_counts, sizeof(int) * kThinBatch, cudaMemcpyDeviceToHost, c->stream));

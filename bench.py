@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- map -> GvdGraph throughput of libaos_gpu on B200 (BASELINE.json metric: Mcells/s, ms/map).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|...] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one synthetic orchard map (SURVEY.md section 8(d) generator):
+point cloud -> occupancy grid -> inflation -> skeleton -> row clusters -> seeds -> Voronoi/GVD graph.
+N > 1 (torchrun, one rank per GPU): every rank processes its own independent map (BASELINE.json config 5,
+"one map per GPU"; no data-path collective), value = cells of all ranks / max-over-ranks time, weak scaling.
+
+  value : inputs resident in HBM, CUDA events on the library's stream, max over ranks
+  e2e   : the same call with HOST (pinned) points, H2D inside the timed region, and the results
+          (published grids bit-packed, clusters, rows, seeds, graph) copied back to the host
+  roofline / cpu_baseline / clocks : see DESIGN.md "Measurement"
+
+--impl reference times the CPU restatement of the reference (oracle/, the reference itself cannot be built
+here: ROS 2 / PCL / OpenCV-dev are absent) on the host cores, on a bounded crop of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "active-orchard-slam_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "map_to_gvdgraph_throughput"
+UNIT = "Mcells/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_params(lib, spec):
+    return lib.SeedParams(grid_resolution=spec.grid_resolution, inflation_radius=spec.inflation_radius,
+                          polygon=spec.polygon, exclusion=spec.exclusion)
+
+
+# ---------------------------------------------------------------------------------------------------
+def bench_ours(args):
+    import torch
+
+    from aos_gpu import lib, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libaos_gpu has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spec = synth.config(args.workload, seed=rank, n_points=args.points)
+    params = make_params(lib, spec)
+    gi = lib.grid_geometry(params)
+    cells = gi.width * gi.height
+    t0 = time.time()
+    pts = synth.make_orchard_torch(spec, dev)
+    torch.cuda.synchronize()
+    n_pts = pts.shape[0]
+    host_pts = torch.empty(pts.shape, dtype=pts.dtype, pin_memory=True)
+    host_pts.copy_(pts)
+    host_np = host_pts.numpy()
+    gen_s = time.time() - t0
+
+    ctx = lib.Context(local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    def step_device():
+        return ctx.map_to_graph(params, pts)
+
+    def step_host():
+        return ctx.map_to_graph(params, host_np, fetch=True)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            info = step_device()
+        # ---- value: device-resident inputs -------------------------------------------------------
+        l0 = ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with ClockSampler(local) as clk:
+            ev0.record(stream)
+            for _ in range(args.steps):
+                info = step_device()
+            ev1.record(stream)
+            barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+        launches = (ctx.launch_count() - l0) / max(args.steps, 1)
+        # ---- e2e: host points in, host results out ---------------------------------------------------
+        for _ in range(min(args.warmup, 2)):
+            info_h = step_host()
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record(stream)
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            info_h = step_host()
+        ev3.record(stream)
+        barrier()
+        e2e_wall_ms = (time.perf_counter() - w0) * 1e3
+        e2e_ms = max(ev2.elapsed_time(ev3), e2e_wall_ms)
+        # ---- per-stage device times (CUDA events recorded by the library on the same stream) ----------
+        ctx.set_profiling(True)
+        stage_acc = {}
+        reps = 3
+        for _ in range(reps):
+            step_device()
+            for name, ms in ctx.stage_times():
+                stage_acc[name] = stage_acc.get(name, 0.0) + ms / reps
+        ctx.set_profiling(False)
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = dev_ms / args.steps
+    value = world * cells / (ms_per_step * 1e-3) / 1e6
+    e2e_value = world * cells / (e2e_ms / args.steps * 1e-3) / 1e6
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        # dominant HBM kernel by algorithmic bytes: the point-binning pass reads 16 B per point once
+        bin_ms = stage_acc.get("bin", float("nan"))
+        bin_bytes = 16.0 * n_pts
+        achieved = bin_bytes / (bin_ms * 1e-3) / 1e9 if bin_ms == bin_ms and bin_ms > 0 else None
+        b_alg = 16.0 * n_pts + 9.125 * cells  # compulsory bytes of the whole map
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec.grid_resolution} m, "
+                                   f"{n_pts} points, one map per GPU",
+                       "l2": "inputs (16 B x points) larger than L2 at C3; each step re-reads them from HBM",
+                       "pipeline": info.get("pipeline", "seed_stage"), "graph": info.get("graph")},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "h2d_bytes_per_step": int(n_pts * 16), "d2h_bytes_per_step": int(info_h.get("d2h_bytes", 0))},
+            "gpu_launches": int(round(launches)),
+            "roofline": {"bound": "hbm", "kernel": "bin_points_xyz16", "achieved": round(achieved, 1) if achieved else None,
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "whole_map": {"algorithmic_bytes": int(b_alg),
+                                       "achieved_gbs": round(b_alg / (ms_per_step * 1e-3) / 1e9, 1),
+                                       "frac": round(b_alg / (ms_per_step * 1e-3) / 1e9 / peak, 4)}},
+            "stages_ms": {k: round(v, 4) for k, v in stage_acc.items()},
+            "clocks": clk.summary(),
+            "gen_s": round(gen_s, 2),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cores=1, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's algorithms) on a bounded crop of the workload
+# ---------------------------------------------------------------------------------------------------
+def crop_spec(workload: str, seed: int):
+    """A 100 m x 60 m window (the extent of BASELINE configs 1-2) of the workload's orchard (same row pitch, tree model, point density)."""
+    from aos_gpu import synth
+    full = synth.config(workload, seed=seed)
+    ex, ey = min(full.extent_x, 100.0), min(full.extent_y, 60.0)
+    density = full.n_points / (full.extent_x * full.extent_y)
+    s = synth.OrchardSpec(extent_x=ex, extent_y=ey, row_pitch=full.row_pitch, tree_spacing=full.tree_spacing,
+                          tree_radius=full.tree_radius, n_points=int(density * ex * ey), seed=seed,
+                          grid_resolution=full.grid_resolution, inflation_radius=full.inflation_radius)
+    return s
+
+
+def _cpu_one(args_tuple):
+    workload, seed, reps = args_tuple
+    from aos_gpu import synth
+    from oracle import oracle as O
+    spec = crop_spec(workload, seed)
+    pts = synth.make_orchard(spec)
+    p = O.SeedParams(grid_resolution=spec.grid_resolution, inflation_radius=spec.inflation_radius, polygon=spec.polygon)
+    times = []
+    cells = 0
+    for _ in range(reps):
+        t = time.perf_counter()
+        r = O.seed_stage(p, pts)
+        O.gvd_stage(r["seeds"], r["skel_framed"], r["origin_x"], r["origin_y"], r["res"], r["rows_info"])
+        times.append(time.perf_counter() - t)
+        cells = r["w"] * r["h"]
+    return cells, times, len(pts)
+
+
+def cpu_baseline(args, cores: int, budget_s: float):
+    """Oracle timed on `cores` host processes, one crop map each; returns the cpu_baseline object."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    t0 = time.perf_counter()
+    cells, times, npts = _cpu_one((args.workload, 1000, 1))  # also sizes the repetitions
+    reps = max(1, min(8, int(budget_s / max(times[0], 1e-3)) - 1))
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            t1 = time.perf_counter()
+            res = pool.map(_cpu_one, [(args.workload, 1000 + i, reps) for i in range(cores)])
+            wall = time.perf_counter() - t1
+        total_cells = sum(c * len(t) for c, t, _ in res)
+        value = total_cells / wall / 1e6
+    else:
+        _, t2, _ = _cpu_one((args.workload, 1000, reps))
+        value = cells * len(t2) / sum(t2) / 1e6
+    spec = crop_spec(args.workload, 1000)
+    return {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{spec.extent_x:g}x{spec.extent_y:g} m crop of {args.workload} ({cells} cells, {npts} points), "
+                      f"oracle port (C, -O2) seed stage + gvd stage incl. cv2.Subdiv2D, {reps} rep(s) per core",
+            "ms_per_map": round(1e3 * cells / (value * 1e6) * (cores if cores > 1 else 1), 2),
+            "wall_s": round(time.perf_counter() - t0, 1)}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 32))
+    steps = args.steps
+    vals = []
+    cb = None
+    for i in range(args.warmup + steps):
+        cb = cpu_baseline(args, cores=cores, budget_s=max(2.0, args.cpu_budget / max(steps, 1)))
+        if i >= args.warmup:
+            vals.append(cb["value"])
+        if i == 0 and cb["wall_s"] * (args.warmup + steps) > 240:  # keep the whole arm within minutes
+            vals = [cb["value"]]
+            break
+    value = float(np.mean(vals))
+    cells = crop_cells(args)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": round(cells / (value * 1e6) * 1e3 * cores, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8 grids / f32,f64 geometry",
+            "data": "synthetic", "config": {"workload": f"{args.workload} (bounded crop, see cpu_baseline.sample)"},
+            "cpu_baseline": dict(cb, value=round(value, 3)),
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def crop_cells(args):
+    from aos_gpu import lib
+    spec = crop_spec(args.workload, 1000)
+    gi = lib.grid_geometry(make_params(lib, spec))
+    return gi.width * gi.height
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--points", type=int, default=None, help="override the workload's point count")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

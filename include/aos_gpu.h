@@ -151,6 +151,74 @@ AOS_API aos_status aos_get_labels(aos_ctx *ctx, int32_t *dst, size_t dst_count, 
 AOS_API aos_status aos_get_clusters(aos_ctx *ctx, aos_cluster *dst, int32_t capacity, int32_t *n_out);
 AOS_API aos_status aos_get_tree_rows(aos_ctx *ctx, aos_tree_row *dst, int32_t capacity, int32_t *n_out);
 
+/* ---- seed selection: generateVirtualSeeds / raycastToOccupiedCell / generateRayPointsFromEndpoints /
+ *      castRayFromEndpoint / endpoint seeds (seed_gen:1434-1511, 1730-1891, 1894-1982, 1987-2268) and the
+ *      sorted /exploration_tree_rows_info (seed_gen:2546-2582).  Stays on the HOST (north star); the ray casts
+ *      read the un-framed skeleton bit grid, fetched once from the device (W*H/8 bytes).  Seeds come out in
+ *      /voronoi_seeds publish order: virtual, ray, endpoint (seed_gen:1670-1710); counts[3] = those sizes. -- */
+AOS_API aos_status aos_select_seeds(aos_ctx *ctx, int32_t *n_seeds, int32_t counts[3]);
+AOS_API aos_status aos_get_seeds(aos_ctx *ctx, double *dst_xy, int32_t capacity, int32_t *n_out);
+/* 4 doubles per row: start x, y, end x, y; rows sorted by centre (y, then x). */
+AOS_API aos_status aos_get_rows_info(aos_ctx *ctx, double *dst, int32_t capacity_rows, int32_t *n_out);
+
+/* ---- the gvd half: replaces the body of AosGvdNode::processGraph (gvd:255-318) together with the seed
+ *      merge of voronoiSeedsCallback (gvd:84-128):
+ *        merge seeds (0.5 m greedy, centroid)                          gvd:93-125
+ *        VoronoiDiagram::compute  (Subdiv2D replay on the host, see csrc/host_subdiv.cu)   vd:16-114
+ *        extractBoundaryPoints    (first-come 5 cm merge -> nodes)      vd:149-207
+ *        buildGraphFromBoundaryPoints (edges, skeleton crossing test, 0.5 m proximity edges)  gvd:794-895, 320-359
+ *        filterNodesAndEdgesOutsideGrid                                 gvd:420-483
+ *        findClusterEndpointVoronoiBoundaryPoints (TL/TR/BL/BR)         gvd:485-556, 686-790, 558-684
+ *        publishGraph's arrays                                          gvd:897-1010
+ *      seeds_xy  : /voronoi_seeds positions (un-merged), host, x,y pairs
+ *      rows_info : /exploration_tree_rows_info, host, 4 doubles per row (start x,y, end x,y) in message order
+ *      skeleton  : /skeletonized_occupancy_grid data (int8, 100 = occupied), host, with its `info`; pass NULL
+ *                  (and info NULL) to use the framed skeleton this context produced in aos_seed_stage.
+ *      Returns AOS_ERR_STATE when seeds or skeleton are missing (the reference returns silently, gvd:257). - */
+typedef struct {
+  /* aos/msg/GvdGraph.msg field for field (msg/GvdGraph.msg:4-58); pointers are context-owned host memory,
+   * valid until the next aos_gvd_stage / aos_destroy */
+  float resolution;
+  double origin_x, origin_y;
+  int32_t n_nodes;
+  const double *nodes_xyz;             /* geometry_msgs/Point[]: x, y, z (= 0) */
+  const int32_t *node_labels;          /* bitmask TL=1 TR=2 BL=4 BR=8 */
+  const int32_t *node_cluster_indices; /* first row that labelled the node, -1 if none */
+  const int32_t *node_label_counts;
+  int32_t n_label_entries;
+  const int32_t *node_label_clusters, *node_label_types;
+  int32_t n_edges;
+  const int32_t *edges;                /* flat (from, to) pairs, from < to */
+  const float *edge_lengths;
+  const float *edge_clearances;        /* 0.0f, as the reference publishes (gvd:856,890) */
+  /* diagnostics */
+  int32_t n_merged_seeds, n_voronoi_edges, n_boundary_points;
+  const double *corner_points;         /* per row TL,TR,BL,BR x,y (8 doubles) */
+  int32_t n_rows;
+} aos_gvd_graph;
+
+AOS_API aos_status aos_gvd_stage(aos_ctx *ctx, const double *seeds_xy, int32_t n_seeds, const double *rows_info,
+                                 int32_t n_rows, const int8_t *skeleton, const aos_grid_info *info);
+AOS_API aos_status aos_get_graph(aos_ctx *ctx, aos_gvd_graph *out);
+
+/* The whole path in one call: aos_seed_stage, aos_select_seeds, aos_gvd_stage on the context's own grids. */
+AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, const void *points, size_t n_points,
+                                    uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                                    aos_mem points_mem);
+
+/* Stand-alone host steps of the gvd half (unit tests; no device needed). */
+/* voronoiSeedsCallback's merge; out_xy must hold 2*n doubles; *n_out = merged count. */
+AOS_API aos_status aos_merge_seeds(const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out);
+/* VoronoiDiagram::compute up to getVoronoiFacetList: float32 polygons, flat x,y + offsets[n_facets+1].
+ * Call with facet_xy == NULL to size the buffers (*n_facets, *n_points). */
+AOS_API aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, double min_x, double max_x,
+                                      double min_y, double max_y, float *facet_xy, int32_t xy_capacity_points,
+                                      int32_t *facet_off, int32_t off_capacity, int32_t *n_facets,
+                                      int32_t *n_points);
+
+/* Kernels launched by this context since aos_create (bench.py's gpu_launches). */
+AOS_API aos_status aos_get_launch_count(aos_ctx *ctx, int64_t *out);
+
 /* ---- stand-alone steps (unit tests, parameter sweeps; same kernels as aos_seed_stage) -------- */
 /* Each takes/returns AOS_FMT_BITS grids in DEVICE memory with pitch aos_bits_pitch_words(width). */
 AOS_API aos_status aos_inflate_bits(aos_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t *out_border,

@@ -55,3 +55,13 @@ def assert_seed_parity(ctx, r, check_labels=True):
         got = [row["center_x"], row["center_y"], row["start_x"], row["start_y"], row["end_x"], row["end_y"], row["length"]]
         assert list(o) == got, f"row {i}: {got} vs {list(o)}"
         assert int(row["cluster"]) == int(r["row_cluster"][i])
+    assert_seed_selection_parity(ctx, r)
+
+
+def assert_seed_selection_parity(ctx, r):
+    """Host seed selection (/voronoi_seeds, /exploration_tree_rows_info) against the oracle, bit-exact."""
+    seeds, counts, rows_info = ctx.select_seeds()
+    assert counts == (r["n_virtual"], r["n_ray"], r["n_endpoint"]), f"{counts} vs {(r['n_virtual'], r['n_ray'], r['n_endpoint'])}"
+    assert seeds.shape == r["seeds"].shape
+    assert np.array_equal(seeds, r["seeds"]), f"seeds differ at {np.argwhere(seeds != r['seeds'])[:5].tolist()}"
+    assert np.array_equal(rows_info, r["rows_info"])
