@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
+    "aos_gvd_stage", "aos_get_graph", "aos_map_to_graph", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
 ]
 
 
@@ -63,6 +64,18 @@ class CTreeRow(C.Structure):
 
 class CStageTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("ms", C.c_float)]
+
+
+class CGvdGraph(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("origin_x", C.c_double), ("origin_y", C.c_double),
+                ("n_nodes", C.c_int32), ("nodes_xyz", C.POINTER(C.c_double)),
+                ("node_labels", C.POINTER(C.c_int32)), ("node_cluster_indices", C.POINTER(C.c_int32)),
+                ("node_label_counts", C.POINTER(C.c_int32)), ("n_label_entries", C.c_int32),
+                ("node_label_clusters", C.POINTER(C.c_int32)), ("node_label_types", C.POINTER(C.c_int32)),
+                ("n_edges", C.c_int32), ("edges", C.POINTER(C.c_int32)), ("edge_lengths", C.POINTER(C.c_float)),
+                ("edge_clearances", C.POINTER(C.c_float)), ("n_merged_seeds", C.c_int32),
+                ("n_voronoi_edges", C.c_int32), ("n_boundary_points", C.c_int32),
+                ("corner_points", C.POINTER(C.c_double)), ("n_rows", C.c_int32)]
 
 
 class CSeedSummary(C.Structure):
@@ -116,6 +129,13 @@ def load() -> C.CDLL:
     L.aos_get_seeds.argtypes = [vp, vp, i32, C.POINTER(i32)]
     L.aos_get_rows_info.argtypes = [vp, vp, i32, C.POINTER(i32)]
     L.aos_get_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.aos_gvd_stage.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(CGridInfo)]
+    L.aos_get_graph.argtypes = [vp, C.POINTER(CGvdGraph)]
+    L.aos_map_to_graph.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    L.aos_set_subdiv_outer_factor.argtypes = [C.c_float]
+    L.aos_merge_seeds.argtypes = [vp, i32, vp, C.POINTER(i32)]
+    L.aos_voronoi_facets.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, vp, i32, vp, i32,
+                                     C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L
 
@@ -257,19 +277,34 @@ class Context:
         return out
 
     # ---- the whole path -----------------------------------------------------------------------
-    def map_to_graph(self, params: SeedParams, points, fetch=None) -> dict:
-        """map -> GvdGraph: seed stage (GPU), seed selection (host), gvd stage.  With `fetch` (a dict
-        that may hold preallocated, e.g. pinned, uint32 arrays "occ_bits"/"skel_bits") the published grids
-        come back bit-packed together with clusters, rows, seeds and the graph; returns a summary dict."""
-        s = self.seed_stage(params, points)
-        seeds, counts, rows_info = self.select_seeds()
-        info = {"pipeline": "seed_stage+select_seeds", "width": s.info.width, "height": s.info.height,
-                "n_clusters": s.n_clusters, "n_rows": s.n_rows, "n_seeds": len(seeds), "graph": None}
-        graph = None
-        if hasattr(self, "gvd_stage"):
-            graph = self.gvd_stage(seeds, rows_info)
-            info["pipeline"] = "seed_stage+select_seeds+gvd_stage"
-            info["graph"] = {"nodes": int(len(graph["nodes"])), "edges": int(len(graph["edges"]))}
+    def _points_args(self, points, n_points, point_step):
+        if hasattr(points, "data_ptr"):
+            self._keep_points = points
+            return (points.data_ptr(), AOS_MEM_DEVICE, points.shape[0] if n_points is None else n_points,
+                    points.stride(0) * points.element_size() if point_step is None else point_step)
+        pts = np.ascontiguousarray(points)
+        self._keep_points = pts
+        return (pts.ctypes.data, AOS_MEM_HOST, pts.shape[0] if n_points is None else n_points,
+                pts.strides[0] if point_step is None else point_step)
+
+    def map_to_graph(self, params: SeedParams, points, fetch=None, n_points=None, point_step=None,
+                     offsets=(0, 4, 8)) -> dict:
+        """aos_map_to_graph: seed stage (GPU), seed selection (host), gvd stage (host Voronoi + GPU graph).
+        With `fetch` (True or a dict of preallocated uint32 arrays "occ_bits"/"skel_bits") the published grids
+        come back bit-packed together with clusters, rows, seeds and the graph arrays.  Returns a summary."""
+        cp = params.to_c()
+        ptr, mem, n, step = self._points_args(points, n_points, point_step)
+        rc = self.L.aos_map_to_graph(self.h, C.byref(cp), C.c_void_p(ptr), n, step, offsets[0], offsets[1], offsets[2], mem)
+        s = self.seed_summary() if rc in (0, -4) else None
+        if rc == -4 and s is not None:   # AOS_ERR_STATE: no rows/seeds on this map, the reference publishes no graph
+            graph = None
+        else:
+            self._check(rc, "aos_map_to_graph")
+            graph = self.graph(copy=fetch is not None)
+        info = {"pipeline": "aos_map_to_graph (seed_stage + select_seeds + gvd_stage)", "width": s.info.width,
+                "height": s.info.height, "n_clusters": s.n_clusters, "n_rows": s.n_rows,
+                "graph": None if graph is None else {"nodes": int(graph["n_nodes"]), "edges": int(graph["n_edges"]),
+                                                     "merged_seeds": int(graph["n_merged_seeds"])}}
         if fetch is not None:
             if fetch is True:
                 fetch = {}
@@ -283,12 +318,55 @@ class Context:
                                                 AOS_MEM_HOST), "aos_get_grid")
                 d2h += buf.nbytes
             cl, rows = self.clusters(), self.tree_rows()
-            d2h += cl.nbytes + rows.nbytes + seeds.nbytes + rows_info.nbytes
+            d2h += cl.nbytes + rows.nbytes
             if graph is not None:
                 d2h += sum(v.nbytes for v in graph.values() if isinstance(v, np.ndarray))
             info["d2h_bytes"] = d2h
             info["fetched"] = fetch
+            info["graph_arrays"] = graph
         return info
+
+    # ---- gvd stage ---------------------------------------------------------------------------
+    def gvd_stage(self, seeds, rows_info, skeleton=None, info=None) -> dict:
+        """seeds: /voronoi_seeds positions [S,2] (un-merged); rows_info [R,4]; skeleton: int8 [H,W] of
+        /skeletonized_occupancy_grid with info=(resolution, origin_x, origin_y), or None to use this context's."""
+        sd = np.ascontiguousarray(seeds, np.float64).reshape(-1, 2)
+        rw = np.ascontiguousarray(rows_info, np.float64).reshape(-1, 4)
+        if skeleton is not None:
+            sk = np.ascontiguousarray(skeleton, np.int8)
+            gi = CGridInfo(sk.shape[1], sk.shape[0], float(info[0]), float(info[1]), float(info[2]))
+            rc = self.L.aos_gvd_stage(self.h, sd.ctypes.data_as(C.c_void_p), len(sd), rw.ctypes.data_as(C.c_void_p), len(rw),
+                                      sk.ctypes.data_as(C.c_void_p), C.byref(gi))
+        else:
+            rc = self.L.aos_gvd_stage(self.h, sd.ctypes.data_as(C.c_void_p), len(sd), rw.ctypes.data_as(C.c_void_p), len(rw),
+                                      None, None)
+        self._check(rc, "aos_gvd_stage")
+        return self.graph()
+
+    def graph(self, copy=True) -> dict:
+        g = CGvdGraph()
+        self._check(self.L.aos_get_graph(self.h, C.byref(g)), "aos_get_graph")
+
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            a = np.ctypeslib.as_array(ptr, shape=(n,))
+            return a.astype(dt, copy=True) if copy else a
+
+        xyz = arr(g.nodes_xyz, 3 * g.n_nodes, np.float64).reshape(-1, 3)
+        return dict(resolution=float(g.resolution), origin_x=g.origin_x, origin_y=g.origin_y, n_nodes=g.n_nodes,
+                    n_edges=g.n_edges, nodes_xyz=xyz, nodes=xyz[:, :2],
+                    node_labels=arr(g.node_labels, g.n_nodes, np.int32),
+                    node_cluster_indices=arr(g.node_cluster_indices, g.n_nodes, np.int32),
+                    node_label_counts=arr(g.node_label_counts, g.n_nodes, np.int32),
+                    node_label_clusters=arr(g.node_label_clusters, g.n_label_entries, np.int32),
+                    node_label_types=arr(g.node_label_types, g.n_label_entries, np.int32),
+                    edges=arr(g.edges, 2 * g.n_edges, np.int32).reshape(-1, 2),
+                    edge_lengths=arr(g.edge_lengths, g.n_edges, np.float32),
+                    edge_clearances=arr(g.edge_clearances, g.n_edges, np.float32),
+                    corner_points=arr(g.corner_points, 8 * g.n_rows, np.float64).reshape(-1, 4, 2),
+                    n_merged_seeds=g.n_merged_seeds, n_voronoi_edges=g.n_voronoi_edges,
+                    n_boundary_points=g.n_boundary_points)
 
     def launch_count(self) -> int:
         n = C.c_int64()
@@ -319,6 +397,35 @@ class Context:
         if n.value:
             self._check(self.L.aos_get_tree_rows(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_tree_rows")
         return out
+
+
+def merge_seeds(seeds) -> np.ndarray:
+    """aos_merge_seeds: voronoiSeedsCallback's greedy 0.5 m merge (host, no device needed)."""
+    sd = np.ascontiguousarray(seeds, np.float64).reshape(-1, 2)
+    out = np.zeros_like(sd)
+    n = C.c_int32()
+    rc = load().aos_merge_seeds(sd.ctypes.data_as(C.c_void_p), len(sd), out.ctypes.data_as(C.c_void_p), C.byref(n))
+    if rc != 0:
+        raise AosError(f"aos_merge_seeds -> {rc}")
+    return out[:n.value].copy()
+
+
+def voronoi_facets(seeds, minx, maxx, miny, maxy):
+    """aos_voronoi_facets: VoronoiDiagram::compute on the host.  Returns (xy float32 [K,2], off int32 [F+1])."""
+    sd = np.ascontiguousarray(seeds, np.float64).reshape(-1, 2)
+    L = load()
+    nf, npts = C.c_int32(), C.c_int32()
+    args = (sd.ctypes.data_as(C.c_void_p), len(sd), minx, maxx, miny, maxy)
+    rc = L.aos_voronoi_facets(*args, None, 0, None, 0, C.byref(nf), C.byref(npts))
+    if rc != 0:
+        raise AosError(f"aos_voronoi_facets -> {rc}")
+    xy = np.zeros((npts.value, 2), np.float32)
+    off = np.zeros(nf.value + 1, np.int32)
+    rc = L.aos_voronoi_facets(*args, xy.ctypes.data_as(C.c_void_p), npts.value, off.ctypes.data_as(C.c_void_p),
+                              len(off), C.byref(nf), C.byref(npts))
+    if rc != 0:
+        raise AosError(f"aos_voronoi_facets -> {rc}")
+    return xy, off
 
 
 def unpack_bits(bits: np.ndarray, width: int) -> np.ndarray:

@@ -102,7 +102,8 @@ void aos_destroy(aos_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch,
                     &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
-                    &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf};
+                    &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf,
+                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel};
   for (DevBuf *b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_flag) cudaFreeHost(c->h_flag);

@@ -177,6 +177,41 @@ void host_select_seeds(const uint32_t *skel_bits, int w, int h, int pitch, doubl
                        const std::vector<aos_tree_row> &rows, const double *poly, int n_poly,
                        std::vector<double> *seeds, int counts[3], std::vector<double> *rows_info);
 void host_merge_seeds(const double *seeds, int n, std::vector<double> *out);
+aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum_buf, uint32_t *d_total);
+
+// ---- gvd half --------------------------------------------------------------------------------------
+// VoronoiDiagram::compute (vd:16-94) on the host: facets as flat float32 x,y + offsets; false when the
+// reference returns early (no seeds / invalid bounds).
+bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
+                         std::vector<float> *facet_xy, std::vector<int32_t> *facet_off);
+
+struct GraphInputs {
+  std::vector<float> facet_xy;  // one x,y per facet-vertex slot; slot e also is Voronoi edge e (vd:97-114)
+  std::vector<int> enext;       // slot of the edge's end point (next vertex of the same facet)
+  const double *rows_info = nullptr;  // host, 4 per row
+  int n_rows = 0;
+  const uint32_t *skel_bits = nullptr;  // device, framed skeleton
+  int w = 0, h = 0, pitch = 0;
+  double ox = 0, oy = 0;
+  float res = 0;
+};
+
+struct GraphHost {  // GvdGraph.msg arrays, host side
+  float resolution = 0;
+  double origin_x = 0, origin_y = 0;
+  std::vector<double> nodes_xyz;
+  std::vector<int32_t> node_labels, node_cluster_indices, node_label_counts, node_label_clusters, node_label_types, edges;
+  std::vector<float> edge_lengths, edge_clearances;
+  std::vector<double> corner_points;
+  int n_merged_seeds = 0, n_voronoi_edges = 0, n_boundary_points = 0, n_rows = 0;
+  void clear() {
+    nodes_xyz.clear(); node_labels.clear(); node_cluster_indices.clear(); node_label_counts.clear();
+    node_label_clusters.clear(); node_label_types.clear(); edges.clear(); edge_lengths.clear();
+    edge_clearances.clear(); corner_points.clear();
+    n_voronoi_edges = n_boundary_points = n_rows = 0;
+  }
+};
+aos_status run_graph(Ctx *c, const GraphInputs &in);
 
 struct Ctx {
   int device = 0;
@@ -223,6 +258,12 @@ struct Ctx {
   std::vector<aos_cluster> h_clusters;
   std::vector<aos_tree_row> h_rows;
   std::vector<int32_t> h_cluster_root;  // compact index of each cluster's root
+
+  // gvd half (host_gvd.cu, k_graph.cu)
+  bool have_graph = false;
+  GraphHost graph;
+  DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel;
+  std::vector<double> h_merged;
 
   // host seed selection (host_seeds.cu)
   bool have_seeds = false;

@@ -1,0 +1,214 @@
+// host_gvd.cu -- C-ABI of the gvd half (include/aos_gpu.h): aos_gvd_stage replaces the body of
+// AosGvdNode::processGraph (src/aos_gvd_node.cpp:255-318) plus the seed merge of voronoiSeedsCallback
+// (gvd:84-128).  Host side: seed merge, VoronoiDiagram::compute (src/utils/voronoi_diagram.cpp:16-114, the
+// Subdiv2D replay of host_subdiv.cu); device side: k_graph.cu.
+#include <math.h>
+
+#include <algorithm>
+
+#include "aos_common.cuh"
+#include "host_subdiv.h"
+
+namespace aos {
+
+// VoronoiDiagram::compute, vd:16-94.
+bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
+                         std::vector<float> *facet_xy, std::vector<int32_t> *facet_off) {
+  facet_xy->clear();
+  facet_off->assign(1, 0);
+  if (n <= 0) return false;
+  if (!std::isfinite(min_x) || !std::isfinite(max_x) || !std::isfinite(min_y) || !std::isfinite(max_y)) return false;
+  if (min_x > max_x) std::swap(min_x, max_x);
+  if (min_y > max_y) std::swap(min_y, max_y);
+  const double min_size = 1.0;
+  if (max_x - min_x < min_size) {
+    double c = (min_x + max_x) / 2.0;
+    min_x = c - min_size / 2.0;
+    max_x = c + min_size / 2.0;
+  }
+  if (max_y - min_y < min_size) {
+    double c = (min_y + max_y) / 2.0;
+    min_y = c - min_size / 2.0;
+    max_y = c + min_size / 2.0;
+  }
+  // cv::Rect2f bounding_rect (vd:51-56)
+  const float rx = (float)(min_x - 1.0), ry = (float)(min_y - 1.0);
+  const float rw = (float)(fabs(max_x - min_x) + 2.0), rh = (float)(fabs(max_y - min_y) + 2.0);
+  if (rw <= 0 || rh <= 0) return false;
+  // cv::Subdiv2D(Rect): the Rect2f converts to the int Rect through saturate_cast<int> == cvRound
+  // (round-half-even), OpenCV 4.5.4 as shipped with ROS 2 Humble (package.xml:48)
+  Subdiv sd;
+  sd.init((int)lrint((double)rx), (int)lrint((double)ry), (int)lrint((double)rw), (int)lrint((double)rh));
+  const float margin = 0.1f;
+  for (int i = 0; i < n; ++i) {
+    double sx = seeds[2 * i], sy = seeds[2 * i + 1];
+    if (!std::isfinite(sx) || !std::isfinite(sy)) continue;
+    float x = (float)sx, y = (float)sy;
+    x = std::max(rx + margin, std::min(rx + rw - margin, x));
+    y = std::max(ry + margin, std::min(ry + rh - margin, y));
+    sd.insert(x, y);  // -1 where cv::Subdiv2D::insert throws: the reference skips the seed (vd:83-88)
+  }
+  sd.voronoi_facets(facet_xy, facet_off);
+  return true;
+}
+
+}  // namespace aos
+
+using namespace aos;
+struct aos_ctx : public aos::Ctx {};
+
+extern "C" {
+
+aos_status aos_set_subdiv_outer_factor(float factor) {
+  if (!(factor >= 1.f) || !std::isfinite(factor)) return AOS_ERR_INVALID;
+  aos::g_outer_factor = factor;
+  return AOS_OK;
+}
+
+aos_status aos_merge_seeds(const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out) {
+  if (n < 0 || (n > 0 && (!seeds_xy || !out_xy))) return AOS_ERR_INVALID;
+  std::vector<double> out;
+  host_merge_seeds(seeds_xy, n, &out);
+  if (!out.empty()) memcpy(out_xy, out.data(), sizeof(double) * out.size());
+  if (n_out) *n_out = (int32_t)(out.size() / 2);
+  return AOS_OK;
+}
+
+aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, double min_x, double max_x, double min_y,
+                              double max_y, float *facet_xy, int32_t xy_capacity_points, int32_t *facet_off,
+                              int32_t off_capacity, int32_t *n_facets, int32_t *n_points) {
+  if (n_seeds < 0 || (n_seeds > 0 && !seeds_xy)) return AOS_ERR_INVALID;
+  std::vector<float> xy;
+  std::vector<int32_t> off;
+  host_voronoi_facets(seeds_xy, n_seeds, min_x, max_x, min_y, max_y, &xy, &off);
+  if (n_facets) *n_facets = (int32_t)off.size() - 1;
+  if (n_points) *n_points = (int32_t)(xy.size() / 2);
+  if (!facet_xy && !facet_off) return AOS_OK;
+  if (!facet_xy || !facet_off || xy_capacity_points < (int32_t)(xy.size() / 2) || off_capacity < (int32_t)off.size())
+    return AOS_ERR_CAPACITY;
+  if (!xy.empty()) memcpy(facet_xy, xy.data(), sizeof(float) * xy.size());
+  memcpy(facet_off, off.data(), sizeof(int32_t) * off.size());
+  return AOS_OK;
+}
+
+aos_status aos_gvd_stage(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
+                         const int8_t *skeleton, const aos_grid_info *info) {
+  if (!c) return AOS_ERR_INVALID;
+  AOS_REQUIRE(c, n_seeds >= 0 && n_rows >= 0, "negative count");
+  AOS_REQUIRE(c, n_seeds == 0 || seeds_xy != nullptr, "seeds pointer is null");
+  AOS_REQUIRE(c, n_rows == 0 || rows_info != nullptr, "rows pointer is null");
+  AOS_REQUIRE(c, (skeleton == nullptr) == (info == nullptr), "skeleton and info must be given together");
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->have_graph = false;
+  c->marks.clear();
+  c->mark("start");
+
+  GraphInputs in;
+  if (skeleton) {
+    AOS_REQUIRE(c, info->width > 0 && info->height > 0 && info->resolution > 0.f, "bad grid info");
+    in.w = info->width;
+    in.h = info->height;
+    in.pitch = pitch_words_for(in.w);
+    in.ox = info->origin_x;
+    in.oy = info->origin_y;
+    in.res = info->resolution;
+    const size_t cells = (size_t)in.w * in.h;
+    AOS_CUDA_OK(c, c->gvd_skel.reserve((size_t)in.pitch * in.h * 4));
+    AOS_CUDA_OK(c, c->points_stage.reserve(cells));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, skeleton, cells, cudaMemcpyHostToDevice, c->stream));
+    aos_status s = launch_pack(c, c->points_stage.as<int8_t>(), c->gvd_skel.as<uint32_t>(), in.w, in.h);
+    if (s != AOS_OK) return s;
+    in.skel_bits = c->gvd_skel.as<uint32_t>();
+  } else {
+    if (!c->have_seed) {  // gvd:257: no skeleton yet
+      set_error(c, "no skeleton: pass one or run aos_seed_stage on this context first");
+      return AOS_ERR_STATE;
+    }
+    in.w = c->P.w;
+    in.h = c->P.h;
+    in.pitch = c->P.pitch;
+    in.ox = c->P.ox;
+    in.oy = c->P.oy;
+    in.res = c->P.res;
+    in.skel_bits = c->g_framed.as<uint32_t>();
+  }
+  c->mark("gvd_skeleton_in");
+
+  // voronoiSeedsCallback merge (gvd:93-125); processGraph drops non-finite seeds (gvd:266-270)
+  host_merge_seeds(seeds_xy, n_seeds, &c->h_merged);
+  c->graph.n_merged_seeds = (int)(c->h_merged.size() / 2);
+  if (c->h_merged.empty()) {  // gvd:257 / :273: nothing to do
+    set_error(c, "no valid seeds");
+    return AOS_ERR_STATE;
+  }
+  // bounds, gvd:278-281: uint32 * float -> float, widened
+  const double minx = in.ox, maxx = in.ox + (double)(float)((float)(unsigned)in.w * in.res);
+  const double miny = in.oy, maxy = in.oy + (double)(float)((float)(unsigned)in.h * in.res);
+  std::vector<float> fxy;
+  std::vector<int32_t> foff;
+  host_voronoi_facets(c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy, &fxy, &foff);
+  c->mark("gvd_host_voronoi");
+  // facets -> edge slots (vd:97-114); facets with fewer than 2 vertices contribute nothing
+  const int nf = (int)foff.size() - 1;
+  in.facet_xy.reserve(fxy.size());
+  in.enext.reserve(fxy.size() / 2);
+  for (int f = 0; f < nf; ++f) {
+    const int b = foff[f], k = foff[f + 1] - b;
+    if (k < 2) continue;
+    const int base = (int)in.enext.size();
+    for (int j = 0; j < k; ++j) {
+      in.facet_xy.push_back(fxy[2 * (size_t)(b + j)]);
+      in.facet_xy.push_back(fxy[2 * (size_t)(b + j) + 1]);
+      in.enext.push_back(base + (j + 1) % k);
+    }
+  }
+  in.rows_info = rows_info;
+  in.n_rows = n_rows;
+  aos_status s = run_graph(c, in);
+  if (s != AOS_OK) return s;
+  c->have_graph = true;
+  return AOS_OK;
+}
+
+aos_status aos_get_graph(aos_ctx *c, aos_gvd_graph *out) {
+  if (!c || !out) return AOS_ERR_INVALID;
+  if (!c->have_graph) {
+    set_error(c, "aos_gvd_stage has not completed");
+    return AOS_ERR_STATE;
+  }
+  const GraphHost &G = c->graph;
+  memset(out, 0, sizeof(*out));
+  out->resolution = G.resolution;
+  out->origin_x = G.origin_x;
+  out->origin_y = G.origin_y;
+  out->n_nodes = (int32_t)G.node_labels.size();
+  out->nodes_xyz = G.nodes_xyz.data();
+  out->node_labels = G.node_labels.data();
+  out->node_cluster_indices = G.node_cluster_indices.data();
+  out->node_label_counts = G.node_label_counts.data();
+  out->n_label_entries = (int32_t)G.node_label_clusters.size();
+  out->node_label_clusters = G.node_label_clusters.data();
+  out->node_label_types = G.node_label_types.data();
+  out->n_edges = (int32_t)G.edge_lengths.size();
+  out->edges = G.edges.data();
+  out->edge_lengths = G.edge_lengths.data();
+  out->edge_clearances = G.edge_clearances.data();
+  out->n_merged_seeds = G.n_merged_seeds;
+  out->n_voronoi_edges = G.n_voronoi_edges;
+  out->n_boundary_points = G.n_boundary_points;
+  out->corner_points = G.corner_points.data();
+  out->n_rows = G.n_rows;
+  return AOS_OK;
+}
+
+aos_status aos_map_to_graph(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points, uint32_t point_step,
+                            uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  aos_status s = aos_seed_stage(c, p, points, n_points, point_step, off_x, off_y, off_z, points_mem);
+  if (s != AOS_OK) return s;
+  s = aos_select_seeds(c, nullptr, nullptr);
+  if (s != AOS_OK) return s;
+  return aos_gvd_stage(c, c->h_seeds.data(), (int32_t)(c->h_seeds.size() / 2), c->h_rows_info.data(),
+                       (int32_t)(c->h_rows_info.size() / 4), nullptr, nullptr);
+}
+
+}  // extern "C"

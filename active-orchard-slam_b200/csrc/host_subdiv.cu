@@ -52,10 +52,13 @@ inline int pt_in_circle3(float px, float py, float ax, float ay, float bx, float
 }
 }  // namespace
 
+float g_outer_factor = 6.f;  // see aos_set_subdiv_outer_factor
+
 void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   vtx_.clear();
   q_.clear();
-  const float big = 3.f * (float)(rw > rh ? rw : rh);
+  // initDelaunay: the three outer vertices sit big_coord away (3 x max side up to OpenCV 4.5.x, 6 x in 4.13)
+  const float big = g_outer_factor * (float)(rw > rh ? rw : rh);
   const float rx = (float)rx_i, ry = (float)ry_i;
   tlx_ = rx;
   tly_ = ry;

@@ -6,6 +6,8 @@
 
 namespace aos {
 
+extern float g_outer_factor;
+
 class Subdiv {
  public:
   // integer rectangle, as cv::Subdiv2D(Rect) receives it

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__re
 }
 
 // in-place exclusive scan; total written to d_total (device)
-static aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum_buf, uint32_t *d_total) {
+aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum_buf, uint32_t *d_total) {
   int nb = (int)((n + kScanBlock - 1) / kScanBlock);
   if (nb < 1) nb = 1;
   AOS_CUDA_OK(c, blocksum_buf.reserve(sizeof(uint32_t) * (size_t)nb));

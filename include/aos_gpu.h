@@ -206,6 +206,13 @@ AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, cons
                                     uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
                                     aos_mem points_mem);
 
+/* cv::Subdiv2D::initDelaunay places its three outer vertices big_coord = factor * max(rect.width, rect.height)
+ * away.  factor is 6 in the OpenCV this library is validated against bit-for-bit (4.13, tests/test_subdiv_cpu.py)
+ * and, to the best of our knowledge, 3 up to OpenCV 4.5.x (ROS 2 Humble's libopencv-dev, package.xml:48); it
+ * only moves the far-away Voronoi vertices of hull cells, which filterNodesAndEdgesOutsideGrid crops.
+ * Process-wide; default 6. */
+AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
+
 /* Stand-alone host steps of the gvd half (unit tests; no device needed). */
 /* voronoiSeedsCallback's merge; out_xy must hold 2*n doubles; *n_out = merged count. */
 AOS_API aos_status aos_merge_seeds(const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out);

@@ -65,3 +65,25 @@ def assert_seed_selection_parity(ctx, r):
     assert seeds.shape == r["seeds"].shape
     assert np.array_equal(seeds, r["seeds"]), f"seeds differ at {np.argwhere(seeds != r['seeds'])[:5].tolist()}"
     assert np.array_equal(rows_info, r["rows_info"])
+
+
+GRAPH_KEYS = ("node_labels", "node_cluster_indices", "node_label_counts", "node_label_clusters", "node_label_types",
+              "edges", "edge_lengths", "edge_clearances")
+
+
+def assert_graph_parity(got, ref):
+    """GvdGraph.msg arrays of the library against the oracle: bit-exact, reference order."""
+    assert got["n_merged_seeds"] == len(ref["merged_seeds"])
+    assert got["n_voronoi_edges"] == ref["n_voro_edges"]
+    assert got["n_boundary_points"] == ref["n_boundary_points_precrop"]
+    assert got["nodes"].shape == ref["nodes"].shape, f"nodes {got['nodes'].shape} vs {ref['nodes'].shape}"
+    assert np.array_equal(got["nodes"], ref["nodes"]), f"node coordinates differ at {np.argwhere(got['nodes'] != ref['nodes'])[:4].tolist()}"
+    assert np.all(got["nodes_xyz"][:, 2] == 0.0)
+    assert got["edges"].shape == ref["edges"].shape, f"edges {got['edges'].shape} vs {ref['edges'].shape}"
+    if len(ref.get("corner_points", [])):
+        assert np.array_equal(got["corner_points"], ref["corner_points"]), \
+            f"corner points differ at rows {np.unique(np.argwhere(got['corner_points'] != ref['corner_points'])[:, 0])[:6].tolist()}"
+    for k in GRAPH_KEYS:
+        assert got[k].shape == ref[k].shape, f"{k}: {got[k].shape} vs {ref[k].shape}"
+        assert np.array_equal(got[k], ref[k]), f"{k} differs at {np.argwhere(got[k] != ref[k])[:4].tolist()}"
+    assert got["resolution"] == float(ref["resolution"]) and got["origin_x"] == ref["origin_x"] and got["origin_y"] == ref["origin_y"]

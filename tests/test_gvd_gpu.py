@@ -1,0 +1,93 @@
+"""GPU parity of the gvd half (aos_gvd_stage / aos_map_to_graph) against the oracle (C restatement of
+aos_gvd_node around the real cv2.Subdiv2D): GvdGraph.msg arrays bit-exact, in the reference's order."""
+import numpy as np
+import pytest
+
+from aos_gpu import lib, synth
+from helpers import assert_graph_parity, params_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_graph(oracle, r):
+    return oracle.gvd_stage(r["seeds"], r["skel_framed"], r["origin_x"], r["origin_y"], r["res"], r["rows_info"])
+
+
+@pytest.mark.parametrize("name,seed,npts", [("TINY", 0, None), ("TINY", 3, None), ("SMALL", 1, None), ("C1", 0, 400_000),
+                                            ("C2", 0, 600_000)])
+def test_map_to_graph(gpu_ctx, oracle, name, seed, npts):
+    spec = synth.config(name, seed=seed, n_points=npts)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    ref = _oracle_graph(oracle, r)
+    info = gpu_ctx.map_to_graph(pl, pts)
+    assert info["graph"] is not None
+    assert_graph_parity(gpu_ctx.graph(), ref)
+
+
+def test_gvd_stage_from_messages(gpu_ctx, oracle):
+    """The aos_gvd_node side of the drop-in: seeds, rows and the int8 skeleton arrive as messages
+    (a separate process, no seed stage on this context)."""
+    spec = synth.config("SMALL", seed=2)
+    pts = synth.make_orchard(spec)
+    po, _ = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    ref = _oracle_graph(oracle, r)
+    ctx = lib.Context(0)
+    got = ctx.gvd_stage(r["seeds"], r["rows_info"], skeleton=r["skel_framed"], info=(r["res"], r["origin_x"], r["origin_y"]))
+    assert_graph_parity(got, ref)
+    ctx.close()
+
+
+def test_reference_polygon_graph(gpu_ctx, oracle):
+    """Negative, non-integer origin (the reference's default polygon): Subdiv2D's integer rectangle, clipping
+    margin and the crop bounds all differ from the grid extent."""
+    spec = synth.OrchardSpec(extent_x=77.0, extent_y=14.0, origin_x=-4.5, origin_y=-2.4, row_pitch=3.5,
+                             n_points=300_000, seed=5, exclusion=synth.REFERENCE_EXCLUSION_DISCS)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle, polygon=synth.REFERENCE_POLYGON)
+    r = oracle.seed_stage(po, pts)
+    ref = _oracle_graph(oracle, r)
+    gpu_ctx.map_to_graph(pl, pts)
+    assert_graph_parity(gpu_ctx.graph(), ref)
+
+
+def test_gvd_stage_random_seeds_and_obstacles(gpu_ctx, oracle):
+    """Seeds that do not come from rows: random seeds (many within 0.5 m of each other -> merges, near-duplicate
+    Voronoi vertices, proximity edges), a random obstacle raster, random rows near the border (ray-cast corner
+    fallback, gvd:558-684)."""
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        w, h, res = 640, 400, np.float32(0.05)
+        skel = np.zeros((h, w), np.int8)
+        for _ in range(30):   # random line obstacles
+            x0, y0 = rng.integers(0, w), rng.integers(0, h)
+            L = rng.integers(5, 120)
+            if rng.random() < 0.5:
+                skel[y0, x0:x0 + L] = 100
+            else:
+                skel[y0:y0 + L, x0] = 100
+        skel[0, :] = skel[-1, :] = 100
+        skel[:, 0] = skel[:, -1] = 100
+        ox, oy = -3.25 + trial, 1.5 * trial
+        n = 400
+        seeds = np.stack([ox + rng.uniform(0, w * 0.05, n), oy + rng.uniform(0, h * 0.05, n)], 1)
+        seeds[::9] += 30.0          # some seeds outside the grid (clipped by Subdiv2D's rectangle margin)
+        rows = np.zeros((6, 4))
+        rows[:, 0] = ox + rng.uniform(0.2, 5, 6)
+        rows[:, 2] = ox + rng.uniform(20, 31.5, 6)
+        rows[:, 1] = rows[:, 3] = oy + rng.uniform(0.3, h * 0.05 - 0.3, 6)
+        rows[5] = rows[5, [2, 3, 0, 1]]   # start.x > end.x: swapped by the node (gvd:140-145)
+        ref = oracle.gvd_stage(seeds, skel, ox, oy, res, rows)
+        got = gpu_ctx.gvd_stage(seeds, rows, skeleton=skel, info=(res, ox, oy))
+        assert_graph_parity(got, ref)
+
+
+def test_gvd_stage_needs_inputs(oracle):
+    ctx = lib.Context(0)
+    with pytest.raises(lib.AosError):   # no skeleton on this context (gvd:257)
+        ctx.gvd_stage(np.zeros((3, 2)), np.zeros((0, 4)))
+    with pytest.raises(lib.AosError):   # no valid seeds (gvd:273)
+        ctx.gvd_stage(np.full((2, 2), np.nan), np.zeros((0, 4)), skeleton=np.zeros((8, 8), np.int8), info=(0.05, 0.0, 0.0))
+    ctx.close()

@@ -1,0 +1,69 @@
+"""Host Voronoi step of the gvd half (csrc/host_subdiv.cu: replay of cv::Subdiv2D) pinned bit-for-bit
+against the real OpenCV implementation (cv2.Subdiv2D through oracle/subdiv.py), and the 0.5 m seed merge
+(gvd:84-128) against the oracle's literal O(S^2) loop.  No GPU needed: these C-ABI entry points are host code."""
+import numpy as np
+import pytest
+
+from aos_gpu import lib
+
+
+def _seed_sets(rng, trial):
+    n = int(rng.integers(1, 400))
+    mode = trial % 5
+    if mode == 0:    # uniform
+        return rng.uniform(0, 50, (n, 2))
+    if mode == 1:    # lattice: four co-circular points everywhere, with / without a tiny perturbation
+        s = np.stack([rng.integers(0, 30, n) * 1.0, rng.integers(0, 20, n) * 2.0], 1)
+        return s + rng.normal(0, 1e-3, (n, 2)) * (trial % 10 < 5)
+    if mode == 2:    # exactly collinear rows, 0.7 m spacing (points on existing edges)
+        return np.stack([np.arange(n) * 0.7 % 45, (np.arange(n) // 60) * 4.0 + 3], 1)
+    if mode == 3:    # duplicates and points outside the rectangle (clipped with the 0.1 m margin)
+        s = rng.uniform(-3, 53, (n, 2))
+        s[::7] = s[0]
+        return s
+    # orchard-like: rows along x, 1 m seeds, slight slope
+    rows = []
+    for r in range(int(rng.integers(1, 8))):
+        x = np.arange(int(rng.integers(5, 45))) * 1.0 + rng.uniform(0, 1)
+        rows.append(np.stack([x, 3 + 4 * r + 0.01 * x * rng.uniform(-1, 1)], 1))
+    return np.concatenate(rows)
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_voronoi_facets_match_cv2_bit_for_bit(oracle, block):
+    from oracle import subdiv
+    rng = np.random.default_rng(100 + block)
+    for trial in range(40):
+        s = _seed_sets(rng, trial)
+        b = (0.0, 50.0, 0.0, 40.0) if trial % 3 else (-4.5, 72.8, -2.4, 12.4)   # second: non-integer rectangle
+        fx, fo, _ = subdiv.voronoi_facets(s, *b)
+        gx, go = lib.voronoi_facets(s, *b)
+        assert np.array_equal(fo, go), f"facet sizes differ (block {block} trial {trial})"
+        assert np.array_equal(fx.view(np.uint32), gx.view(np.uint32)), f"facet vertices differ (block {block} trial {trial})"
+
+
+def test_voronoi_facets_empty_and_invalid_bounds():
+    xy, off = lib.voronoi_facets(np.zeros((0, 2)), 0, 10, 0, 10)
+    assert len(xy) == 0 and list(off) == [0]
+    xy, off = lib.voronoi_facets(np.array([[1.0, 2.0]]), float("nan"), 10, 0, 10)
+    assert len(xy) == 0
+    # non-finite seeds are skipped (vd:66-70), degenerate bounds are widened to 1 m (vd:36-47)
+    from oracle import subdiv
+    s = np.array([[0.2, 0.3], [np.nan, 1.0], [0.4, 0.1], [np.inf, 0.0], [0.3, 0.6]])
+    fx, fo, _ = subdiv.voronoi_facets(s, 0.0, 0.5, 0.0, 0.5)
+    gx, go = lib.voronoi_facets(s, 0.0, 0.5, 0.0, 0.5)
+    assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32))
+
+
+def test_merge_seeds_matches_reference_loop(oracle):
+    rng = np.random.default_rng(7)
+    for trial in range(30):
+        n = int(rng.integers(0, 600))
+        s = rng.uniform(0, 12, (n, 2))
+        if n > 10:
+            s[5] = s[4] + [0.5, 0.0]      # exactly at the merge distance (<=)
+            s[9] = [np.nan, 1.0]
+        want = oracle.merge_seeds(s)
+        got = lib.merge_seeds(s)
+        want = want[np.isfinite(want).all(axis=1)]   # processGraph drops non-finite merged seeds (gvd:266-270)
+        assert got.shape == want.shape and np.array_equal(got, want)
