@@ -391,6 +391,7 @@ aos_status aos_select_seeds(aos_ctx *c, int32_t *n_seeds, int32_t counts[3]) {
   host_select_seeds(c->h_skel_bits.data(), P.w, P.h, P.pitch, P.ox, P.oy, P.res, c->h_rows, P.poly, P.n_poly, &c->h_seeds,
                     c->seed_counts, &c->h_rows_info);
   c->have_seeds = true;
+  c->mark("select_seeds_host");
   if (n_seeds) *n_seeds = (int32_t)(c->h_seeds.size() / 2);
   if (counts)
     for (int k = 0; k < 3; ++k) counts[k] = c->seed_counts[k];

@@ -218,6 +218,7 @@ struct Ctx {
   long long launches = 0;  // kernels launched by this context (aos_get_launch_count)
   // per-stage CUDA-event timers (aos_set_profiling)
   bool profile = false;
+  bool composite = false;  // inside aos_map_to_graph: stages append to one timer list
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<std::string, int>> marks;  // (stage that ENDS at this event, event index)
   void mark(const char *name) {

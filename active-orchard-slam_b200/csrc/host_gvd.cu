@@ -100,8 +100,10 @@ aos_status aos_gvd_stage(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, co
   AOS_REQUIRE(c, (skeleton == nullptr) == (info == nullptr), "skeleton and info must be given together");
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
   c->have_graph = false;
-  c->marks.clear();
-  c->mark("start");
+  if (!c->composite) {
+    c->marks.clear();
+    c->mark("start");
+  }
 
   GraphInputs in;
   if (skeleton) {
@@ -203,12 +205,16 @@ aos_status aos_get_graph(aos_ctx *c, aos_gvd_graph *out) {
 
 aos_status aos_map_to_graph(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points, uint32_t point_step,
                             uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  if (!c) return AOS_ERR_INVALID;
   aos_status s = aos_seed_stage(c, p, points, n_points, point_step, off_x, off_y, off_z, points_mem);
   if (s != AOS_OK) return s;
+  c->composite = true;  // keep one list of stage timers for the whole call
   s = aos_select_seeds(c, nullptr, nullptr);
-  if (s != AOS_OK) return s;
-  return aos_gvd_stage(c, c->h_seeds.data(), (int32_t)(c->h_seeds.size() / 2), c->h_rows_info.data(),
-                       (int32_t)(c->h_rows_info.size() / 4), nullptr, nullptr);
+  if (s == AOS_OK)
+    s = aos_gvd_stage(c, c->h_seeds.data(), (int32_t)(c->h_seeds.size() / 2), c->h_rows_info.data(),
+                      (int32_t)(c->h_rows_info.size() / 4), nullptr, nullptr);
+  c->composite = false;
+  return s;
 }
 
 }  // extern "C"

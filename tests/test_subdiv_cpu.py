@@ -1,10 +1,16 @@
 """Host Voronoi step of the gvd half (csrc/host_subdiv.cu: replay of cv::Subdiv2D) pinned bit-for-bit
 against the real OpenCV implementation (cv2.Subdiv2D through oracle/subdiv.py), and the 0.5 m seed merge
 (gvd:84-128) against the oracle's literal O(S^2) loop.  No GPU needed: these C-ABI entry points are host code."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
 from aos_gpu import lib
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden  # noqa: E402
 
 
 def _seed_sets(rng, trial):
@@ -67,3 +73,14 @@ def test_merge_seeds_matches_reference_loop(oracle):
         got = lib.merge_seeds(s)
         want = want[np.isfinite(want).all(axis=1)]   # processGraph drops non-finite merged seeds (gvd:266-270)
         assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_host_voronoi_reproduces_golden_facets():
+    """Host step only (no kernel): facets of the golden merged seeds, bit for bit."""
+    for name in sorted(make_golden.CASES):
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+        minx, miny = float(g["origin_x"]), float(g["origin_y"])
+        maxx = minx + float(np.float32(np.float32(int(g["w"])) * np.float32(g["res"])))
+        maxy = miny + float(np.float32(np.float32(int(g["h"])) * np.float32(g["res"])))
+        xy, off = lib.voronoi_facets(g["g_merged_seeds"], minx, maxx, miny, maxy)
+        assert np.array_equal(off, g["g_facet_off"]) and np.array_equal(xy.view(np.uint32), g["g_facets_xy"].view(np.uint32))
