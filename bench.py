@@ -175,13 +175,12 @@ def bench_ours(args):
                 stage_acc[name] = stage_acc.get(name, 0.0) + ms / reps
         ctx.set_profiling(False)
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    from aos_gpu import dist as adist
+    dev_ms, total_cells = adist.reduce_stats(dev_ms, cells * args.steps, device=dev)   # MAX over ranks, SUM of cells
+    e2e_ms, _ = adist.reduce_stats(e2e_ms, cells * args.steps, device=dev)
     ms_per_step = dev_ms / args.steps
-    value = world * cells / (ms_per_step * 1e-3) / 1e6
-    e2e_value = world * cells / (e2e_ms / args.steps * 1e-3) / 1e6
+    value = adist.throughput_mcells(total_cells, dev_ms)
+    e2e_value = adist.throughput_mcells(total_cells, e2e_ms)
 
     line = None
     if rank == 0:
