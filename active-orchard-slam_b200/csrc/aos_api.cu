@@ -1,6 +1,7 @@
 // aos_api.cu -- the C-ABI of libaos_gpu (include/aos_gpu.h): context, the seed-gen stage pipeline
 // (processPointCloud, src/aos_seed_gen_node.cpp:452-579) and the getters.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <new>
@@ -103,7 +104,7 @@ void aos_destroy(aos_ctx *c) {
   DevBuf *bufs[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch,
                     &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
                     &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf,
-                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel};
+                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2};
   for (DevBuf *b : bufs) b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -384,14 +385,22 @@ aos_status aos_select_seeds(aos_ctx *c, int32_t *n_seeds, int32_t counts[3]) {
     return AOS_ERR_STATE;
   }
   const SeedDeviceParams &P = c->P;
-  const size_t words = (size_t)P.pitch * P.h;
-  c->h_skel_bits.resize(words);
-  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_skel_bits.data(), c->g_skel.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
-  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  host_select_seeds(c->h_skel_bits.data(), P.w, P.h, P.pitch, P.ox, P.oy, P.res, c->h_rows, P.poly, P.n_poly, &c->h_seeds,
-                    c->seed_counts, &c->h_rows_info);
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  static const bool on_host = getenv("AOS_SEEDS_ON_HOST") != nullptr;  // debugging aid: the plain host loops
+  if (on_host) {
+    const size_t words = (size_t)P.pitch * P.h;
+    c->h_skel_bits.resize(words);
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_skel_bits.data(), c->g_skel.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    host_select_seeds(c->h_skel_bits.data(), P.w, P.h, P.pitch, P.ox, P.oy, P.res, c->h_rows, P.poly, P.n_poly, &c->h_seeds,
+                      c->seed_counts, &c->h_rows_info);
+  } else {
+    aos_status s = device_select_seeds(c);
+    if (s != AOS_OK) return s;
+    host_rows_info(c->h_rows, &c->h_rows_info);
+  }
   c->have_seeds = true;
-  c->mark("select_seeds_host");
+  c->mark("select_seeds");
   if (n_seeds) *n_seeds = (int32_t)(c->h_seeds.size() / 2);
   if (counts)
     for (int k = 0; k < 3; ++k) counts[k] = c->seed_counts[k];

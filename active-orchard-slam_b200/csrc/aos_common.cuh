@@ -176,6 +176,8 @@ aos_status launch_labels(Ctx *c, int32_t *dst);
 void host_select_seeds(const uint32_t *skel_bits, int w, int h, int pitch, double ox, double oy, float res,
                        const std::vector<aos_tree_row> &rows, const double *poly, int n_poly,
                        std::vector<double> *seeds, int counts[3], std::vector<double> *rows_info);
+void host_rows_info(const std::vector<aos_tree_row> &rows, std::vector<double> *rows_info);
+aos_status device_select_seeds(Ctx *c);
 void host_merge_seeds(const double *seeds, int n, std::vector<double> *out);
 aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum_buf, uint32_t *d_total);
 
@@ -263,7 +265,7 @@ struct Ctx {
   // gvd half (host_gvd.cu, k_graph.cu)
   bool have_graph = false;
   GraphHost graph;
-  DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel;
+  DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel, seed_buf, seed_buf2;
   std::vector<double> h_merged;
 
   // host seed selection (host_seeds.cu)

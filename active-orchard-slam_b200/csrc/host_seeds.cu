@@ -239,8 +239,12 @@ void host_select_seeds(const uint32_t *skel_bits, int w, int h, int pitch, doubl
   counts[1] = (int)(ray.points().size() / 2);
   counts[2] = (int)(endp.points().size() / 2);
 
-  // publishExplorationTreeRowsInfoFromClusters: sort by centre (y, then x if |dy| < 1e-6); stable, so rows
-  // with equal keys keep cluster order
+  host_rows_info(rows, rows_info);
+}
+
+// publishExplorationTreeRowsInfoFromClusters (seed_gen:2546-2582): sort by centre (y, then x if |dy| < 1e-6);
+// stable, so rows with equal keys keep cluster order
+void host_rows_info(const std::vector<aos_tree_row> &rows, std::vector<double> *rows_info) {
   std::vector<int> ord(rows.size());
   for (size_t i = 0; i < rows.size(); ++i) ord[i] = (int)i;
   std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {

@@ -1,0 +1,403 @@
+// k_seeds.cu -- seed selection on the device: the ray casts and first-come
+// 0.5 m de-duplications of aos_seed_gen_node
+//   generateVirtualSeeds             src/aos_seed_gen_node.cpp:1987-2268   (+ raycastToOccupiedCell :1730-1771)
+//   generateRayPointsFromEndpoints   :1894-1982                            (+ castRayFromEndpoint :1774-1891)
+//   endpoint seeds                   :1450-1496
+// Every candidate (row, sample, side) is independent: one thread walks one ray over the un-framed skeleton bit
+// grid with the reference's arithmetic (double steps, float worldToGrid, glibc cos/sin of 0 and pi/2 evaluated
+// on the host).  The reference then filters each candidate list first-come ("is an earlier accepted seed
+// closer than 0.5 m"): that greedy rule is resolved exactly by monotone rounds over a 0.5 m hash grid, as for
+// the graph nodes (k_graph.cu), and the survivors are emitted in order by a prefix sum.
+// host_seeds.cu holds the same logic as plain host code; AOS_SEEDS_ON_HOST=1 selects it (debugging aid).
+#include <math.h>
+
+#include <algorithm>
+
+#include "aos_common.cuh"
+#include "dev_hash.cuh"
+
+namespace aos {
+
+struct RowDev {
+  double cx, cy, sx, sy, ex, ey;
+};
+
+struct SeedGrid {
+  const uint32_t *bits;  // un-framed skeleton
+  int w, h, pitch;
+  double ox, oy;
+  float res;
+};
+
+__device__ __forceinline__ bool sg_occ(const SeedGrid &g, int x, int y) {
+  return (__ldg(g.bits + (size_t)y * g.pitch + (x >> 5)) >> (x & 31)) & 1u;
+}
+
+// isPointInPolygon, seed_gen:1231-1255
+__device__ __forceinline__ bool in_polygon_dev(const SeedDeviceParams &P, double px, double py) {
+  if (P.n_poly < 3) return false;
+  bool inside = false;
+  int j = P.n_poly - 1;
+  for (int i = 0; i < P.n_poly; ++i) {
+    double pix = P.poly[2 * i], piy = P.poly[2 * i + 1], pjx = P.poly[2 * j], pjy = P.poly[2 * j + 1];
+    double dy = pjy - piy;
+    if (fabs(dy) > 1e-9) {
+      if (((piy > py) != (pjy > py)) && (px < (pjx - pix) * (py - piy) / dy + pix)) inside = !inside;
+    }
+    j = i;
+  }
+  return inside;
+}
+
+// worldToGrid, seed_gen:760-769
+__device__ __forceinline__ void world_to_grid_dev(const SeedGrid &g, float wx, float wy, int *gx, int *gy) {
+  float rel_x = (float)(((double)wx - g.ox) / (double)g.res);
+  float rel_y = (float)(((double)wy - g.oy) / (double)g.res);
+  *gx = max(0, min(g.w - 1, (int)floorf(rel_x)));
+  *gy = max(0, min(g.h - 1, (int)floorf(rel_y)));
+}
+
+// raycastToOccupiedCell, seed_gen:1730-1771
+__device__ bool raycast_to_occupied_dev(const SeedGrid &g, double sx, double sy, double dx, double dy, double max_distance,
+                                        double *hx, double *hy) {
+  const double step = (double)g.res * 0.5;
+  const int max_steps = (int)(max_distance / step);
+  double cx = sx, cy = sy;
+  for (int i = 0; i < max_steps; ++i) {
+    cx += dx * step;
+    cy += dy * step;
+    double ex = cx - sx, ey = cy - sy;
+    if (sqrt(ex * ex + ey * ey) < 1.0) continue;
+    int gx, gy;
+    world_to_grid_dev(g, (float)cx, (float)cy, &gx, &gy);
+    if (sg_occ(g, gx, gy)) {
+      *hx = cx;
+      *hy = cy;
+      return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ void normalize2_dev(double &x, double &y) {
+  double z = x * x + y * y;
+  if (z > 0) {
+    double s = sqrt(z);
+    x /= s;
+    y /= s;
+  }
+}
+
+struct RayConsts {
+  double c[3], s[3];  // cos / sin as castRayFromEndpoint evaluates them for angle 0, -90, +90 (glibc, host)
+  double gw, gh;      // float(width * resolution), float(height * resolution)
+};
+
+// castRayFromEndpoint, seed_gen:1774-1891
+__device__ double2 cast_ray_from_endpoint_dev(const SeedGrid &g, const RayConsts &K, double spx, double spy, double opx,
+                                              double opy, int ang /* 0: 0 deg, 1: -90, 2: +90 */, double min_distance) {
+  double ex = opx - spx, ey = opy - spy;
+  if (sqrt(ex * ex + ey * ey) < 1e-6) {
+    ex = 1.0;
+    ey = 0.0;
+  } else {
+    normalize2_dev(ex, ey);
+  }
+  const double outx = -ex, outy = -ey, perpx = -ey, perpy = ex;
+  double rdx, rdy;
+  if (ang == 2) {  // angle > 0
+    rdx = K.c[2] * outx + K.s[2] * perpx;
+    rdy = K.c[2] * outy + K.s[2] * perpy;
+  } else {
+    rdx = K.c[ang] * outx + K.s[ang] * (-perpx);
+    rdy = K.c[ang] * outy + K.s[ang] * (-perpy);
+  }
+  normalize2_dev(rdx, rdy);
+  const double minx = g.ox, maxx = g.ox + K.gw, miny = g.oy, maxy = g.oy + K.gh;
+  const double resolution = (double)g.res;
+  const double abs_max = sqrt(K.gw * K.gw + K.gh * K.gh) * 3.0;
+  double cur = min_distance;
+  while (cur <= abs_max) {
+    double px = spx + rdx * cur, py = spy + rdy * cur;
+    if (!(px >= minx && px <= maxx && py >= miny && py <= maxy))
+      return make_double2(fmax(minx, fmin(maxx, px)), fmax(miny, fmin(maxy, py)));
+    int mx = (int)((px - g.ox) / resolution), my = (int)((py - g.oy) / resolution);
+    if (mx >= 0 && mx < g.w && my >= 0 && my < g.h && sg_occ(g, mx, my)) return make_double2(px, py);
+    cur += 0.1;
+  }
+  double fx = spx + rdx * abs_max, fy = spy + rdy * abs_max;
+  if (!(fx >= minx && fx <= maxx && fy >= miny && fy <= maxy)) {
+    fx = fmax(minx, fmin(maxx, fx));
+    fy = fmax(miny, fmin(maxy, fy));
+  }
+  return make_double2(fx, fy);
+}
+
+enum : unsigned char { kSeedUndecided = 0, kSeedAccept = 1, kSeedReject = 2 };
+
+// ---- generateVirtualSeeds ------------------------------------------------------------------------------
+__global__ void vs_count_kernel(const __grid_constant__ SeedDeviceParams P, const RowDev *__restrict__ rows, int n_rows,
+                                uint32_t *__restrict__ counts) {
+  const double interval = 1.0;  // virtual_seed_interval_, seed_gen:2666
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_rows; r += gridDim.x * blockDim.x) {
+    uint32_t c = 0;
+    if (r < n_rows) {
+      const RowDev R = rows[r];
+      bool ok = !(P.n_poly > 0 && !in_polygon_dev(P, R.cx, R.cy));
+      double dx = R.ex - R.sx, dy = R.ey - R.sy;
+      double distance = sqrt(dx * dx + dy * dy);
+      if (distance < interval) ok = false;
+      if (distance < 1e-6) ok = false;
+      if (ok) c = 3u * (uint32_t)(int)floor(distance / interval);
+    }
+    counts[r] = c;
+  }
+}
+
+__global__ void vs_generate_kernel(const __grid_constant__ SeedDeviceParams P, SeedGrid g, const RowDev *__restrict__ rows,
+                                   int n_rows, const uint32_t *__restrict__ offs, int n_cand, double2 *__restrict__ pts,
+                                   unsigned char *__restrict__ state) {
+  const double interval = 1.0;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_cand; idx += gridDim.x * blockDim.x) {
+    // row of this candidate: last r with offs[r] <= idx
+    int lo = 0, hi = n_rows - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (offs[mid] <= (uint32_t)idx) lo = mid;
+      else hi = mid - 1;
+    }
+    const RowDev R = rows[lo];
+    const int local = idx - (int)offs[lo];
+    const int i = local / 3 + 1, which = local % 3;
+    const double dx = R.ex - R.sx, dy = R.ey - R.sy;
+    const double distance = sqrt(dx * dx + dy * dy);
+    const double rdx = dx / distance, rdy = dy / distance;
+    const int num = (int)floor(distance / interval);
+    const double t = (double)i / (double)(num + 1);
+    const double bx = R.sx + t * dx, by = R.sy + t * dy;
+    double2 out;
+    bool valid = true;
+    if (which == 0) {
+      out = make_double2(bx, by);
+    } else {
+      const double pdx = which == 1 ? -rdy : rdy, pdy = which == 1 ? rdx : -rdx;
+      double hx, hy;
+      if (raycast_to_occupied_dev(g, bx, by, pdx, pdy, 4.0, &hx, &hy)) out = make_double2(hx, hy);
+      else out = make_double2(bx + pdx * 4.0, by + pdy * 4.0);
+      if (P.n_poly > 0 && in_polygon_dev(P, out.x, out.y)) valid = false;
+    }
+    pts[idx] = out;
+    state[idx] = valid ? kSeedUndecided : kSeedReject;
+  }
+}
+
+// ---- generateRayPointsFromEndpoints + endpoint seeds ---------------------------------------------------------
+__global__ void ray_points_kernel(const __grid_constant__ SeedDeviceParams P, SeedGrid g, RayConsts K,
+                                  const RowDev *__restrict__ rows, int n_rows, double2 *__restrict__ ray_pts,
+                                  unsigned char *__restrict__ ray_state, double2 *__restrict__ end_pts,
+                                  unsigned char *__restrict__ end_state) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 6 * n_rows; idx += gridDim.x * blockDim.x) {
+    const int r = idx / 6, k = idx % 6;
+    const RowDev R = rows[r];
+    const bool from_start = k < 3;
+    const double2 p = cast_ray_from_endpoint_dev(g, K, from_start ? R.sx : R.ex, from_start ? R.sy : R.ey,
+                                                 from_start ? R.ex : R.sx, from_start ? R.ey : R.sy, k % 3, 1.0);
+    const double minx = g.ox, maxx = g.ox + K.gw, miny = g.oy, maxy = g.oy + K.gh;
+    bool valid = isfinite(p.x) && isfinite(p.y) && (p.x >= minx && p.x <= maxx && p.y >= miny && p.y <= maxy);
+    if (valid && P.n_poly > 0 && in_polygon_dev(P, p.x, p.y)) valid = false;
+    ray_pts[idx] = p;
+    ray_state[idx] = valid ? kSeedUndecided : kSeedReject;
+    if (k < 2) {  // endpoint seeds: start, end of every row
+      end_pts[2 * r + k] = k == 0 ? make_double2(R.sx, R.sy) : make_double2(R.ex, R.ey);
+      end_state[2 * r + k] = kSeedUndecided;
+    }
+  }
+}
+
+// ---- first-come de-duplication: "an earlier accepted point is closer than r" (sqrt distance, strict <) ----
+__global__ void seed_grid_build_kernel(const double2 *__restrict__ pts, const unsigned char *__restrict__ state, int n,
+                                       PointGrid g) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (state[i] == kSeedReject) continue;  // filtered candidates never enter the reference's lists
+    double2 p = pts[i];
+    int slot = hash_insert(g.h, cell_key(cell_coord(p.x, g.inv), cell_coord(p.y, g.inv)));
+    g.next[i] = atomicExch(&g.h.val[slot], i);
+  }
+}
+
+__global__ void seed_dedup_round_kernel(const double2 *__restrict__ pts, int n, PointGrid g, volatile unsigned char *state,
+                                        double radius, int *pending_flag) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    if (state[v] != kSeedUndecided) continue;
+    const double2 p = pts[v];
+    const long long cx = cell_coord(p.x, g.inv), cy = cell_coord(p.y, g.inv);
+    bool reject = false, pending = false;
+    for (int oy = -1; oy <= 1 && !reject; ++oy)
+      for (int ox = -1; ox <= 1 && !reject; ++ox) {
+        int slot = hash_find(g.h, cell_key(cx + ox, cy + oy));
+        if (slot < 0) continue;
+        for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
+          if (u >= v) continue;
+          unsigned char su = state[u];
+          if (su == kSeedReject) continue;
+          double ex = pts[u].x - p.x, ey = pts[u].y - p.y;
+          if (!(sqrt(ex * ex + ey * ey) < radius)) continue;
+          if (su == kSeedAccept) {
+            reject = true;
+            break;
+          }
+          pending = true;
+        }
+      }
+    if (reject) state[v] = kSeedReject;
+    else if (!pending) state[v] = kSeedAccept;
+    else *pending_flag = 1;
+  }
+}
+
+__global__ void seed_flags_kernel(const unsigned char *__restrict__ state, int n, uint32_t *__restrict__ flags) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flags[i] = state[i] == kSeedAccept;
+}
+__global__ void seed_emit_kernel(const double2 *__restrict__ pts, const unsigned char *__restrict__ state,
+                                 const uint32_t *__restrict__ pos, int n, double2 *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (state[i] == kSeedAccept) out[pos[i]] = pts[i];
+}
+
+namespace {
+inline int blocks_for(size_t n, int threads = 256) {
+  size_t b = (n + threads - 1) / threads;
+  b = std::min<size_t>(std::max<size_t>(b, 1), (size_t)kNumSMs * 16);
+  return (int)b;
+}
+inline unsigned pow2_at_least(size_t n) {
+  unsigned c = 64;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// De-duplicates pts[0..n) in place of the reference's FirstComeSet; appends survivors (in order) to `out`.
+aos_status dedup_and_fetch(Ctx *c, double2 *d_pts, unsigned char *d_state, int n, PointGrid g, unsigned cap, uint32_t *d_scan,
+                           double2 *d_out, int *d_flag, uint32_t *d_tot, int *n_out) {
+  cudaStream_t st = c->stream;
+  *n_out = 0;
+  if (n == 0) return AOS_OK;
+  AOS_CUDA_OK(c, cudaMemsetAsync(g.h.keys, 0xff, sizeof(unsigned long long) * cap, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(g.h.val, 0xff, sizeof(int) * cap, st));
+  seed_grid_build_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, d_state, n, g);
+  ++c->launches;
+  for (int round = 0; round < 100000; ++round) {
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_flag, 0, 4, st));
+    seed_dedup_round_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, d_flag);
+    ++c->launches;
+    AOS_CUDA_OK(c, cudaGetLastError());
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    if (!c->h_flag[0]) break;
+  }
+  seed_flags_kernel<<<blocks_for(n), 256, 0, st>>>(d_state, n, d_scan);
+  ++c->launches;
+  aos_status s = exclusive_scan_u32(c, d_scan, (size_t)n, c->cc_blocksum, d_tot);
+  if (s != AOS_OK) return s;
+  seed_emit_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, d_state, d_scan, n, d_out);
+  ++c->launches;
+  AOS_CUDA_OK(c, cudaGetLastError());
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  *n_out = c->h_flag[0];
+  return AOS_OK;
+}
+}  // namespace
+
+// rows: all_tree_rows in cluster order (c->h_rows).  Fills c->h_seeds / c->seed_counts like host_select_seeds.
+aos_status device_select_seeds(Ctx *c) {
+  cudaStream_t st = c->stream;
+  const SeedDeviceParams &P = c->P;
+  const int n_rows = (int)c->h_rows.size();
+  c->h_seeds.clear();
+  c->seed_counts[0] = c->seed_counts[1] = c->seed_counts[2] = 0;
+  if (n_rows == 0) return AOS_OK;
+  std::vector<RowDev> hr(n_rows);
+  for (int i = 0; i < n_rows; ++i) {
+    const aos_tree_row &r = c->h_rows[i];
+    hr[i] = RowDev{r.center_x, r.center_y, r.start_x, r.start_y, r.end_x, r.end_y};
+  }
+  // device memory, part 1: rows + counts
+  AOS_CUDA_OK(c, c->seed_buf.reserve(sizeof(RowDev) * (size_t)n_rows + sizeof(uint32_t) * ((size_t)n_rows + 8) + 4096));
+  RowDev *d_rows = c->seed_buf.as<RowDev>();
+  uint32_t *d_offs = reinterpret_cast<uint32_t *>(d_rows + n_rows);
+  uint32_t *d_tot = d_offs + n_rows + 2;  // [0..3] totals, [4] pending flag
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_rows, hr.data(), sizeof(RowDev) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+  vs_count_kernel<<<blocks_for((size_t)n_rows + 1), 256, 0, st>>>(P, d_rows, n_rows, d_offs);
+  ++c->launches;
+  aos_status s = exclusive_scan_u32(c, d_offs, (size_t)n_rows + 1, c->cc_blocksum, d_tot);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  const int n_virt = c->h_flag[0], n_ray = 6 * n_rows, n_end = 2 * n_rows;
+  const int n_max = std::max(n_virt, n_ray);
+
+  // part 2: candidates
+  const unsigned cap = pow2_at_least((size_t)n_max * 2);
+  size_t need = (sizeof(double2) * 2 + 1 + sizeof(int) + sizeof(uint32_t)) * ((size_t)n_virt + n_ray + n_end + 64) +
+                (sizeof(unsigned long long) + sizeof(int)) * (size_t)cap + 8192;
+  AOS_CUDA_OK(c, c->seed_buf2.reserve(need));
+  char *base = c->seed_buf2.as<char>();
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    char *p = base + off;
+    off += bytes;
+    return p;
+  };
+  const size_t n_all = (size_t)n_virt + n_ray + n_end;
+  double2 *d_pts = reinterpret_cast<double2 *>(take(sizeof(double2) * (n_all + 1)));
+  double2 *d_out = reinterpret_cast<double2 *>(take(sizeof(double2) * (n_all + 1)));
+  unsigned char *d_state = reinterpret_cast<unsigned char *>(take(n_all + 1));
+  uint32_t *d_scan = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)n_max + 1)));
+  PointGrid g;
+  g.h.keys = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * cap));
+  g.h.val = reinterpret_cast<int *>(take(sizeof(int) * cap));
+  g.h.mask = cap - 1;
+  g.next = reinterpret_cast<int *>(take(sizeof(int) * ((size_t)n_max + 1)));
+  g.inv = 1.0 / (0.5 * (1.0 + 1e-9));
+
+  SeedGrid sg{c->g_skel.as<uint32_t>(), P.w, P.h, P.pitch, P.ox, P.oy, P.res};
+  RayConsts K;
+  const double ang[3] = {0.0, -90.0, 90.0};
+  for (int k = 0; k < 3; ++k) {  // castRayFromEndpoint: cos(a), sin(a) for a > 0, cos(-a), sin(-a) otherwise
+    double a = ang[k] * M_PI / 180.0;
+    K.c[k] = ang[k] > 0 ? cos(a) : cos(-a);
+    K.s[k] = ang[k] > 0 ? sin(a) : sin(-a);
+  }
+  K.gw = (double)(float)((float)(unsigned)P.w * P.res);  // info.width * info.resolution is uint32 * float -> float
+  K.gh = (double)(float)((float)(unsigned)P.h * P.res);
+
+  double2 *d_vpts = d_pts, *d_rpts = d_pts + n_virt, *d_epts = d_rpts + n_ray;
+  unsigned char *d_vst = d_state, *d_rst = d_state + n_virt, *d_est = d_rst + n_ray;
+  if (n_virt > 0) {
+    vs_generate_kernel<<<blocks_for(n_virt, 128), 128, 0, st>>>(P, sg, d_rows, n_rows, d_offs, n_virt, d_vpts, d_vst);
+    ++c->launches;
+  }
+  ray_points_kernel<<<blocks_for(n_ray, 64), 64, 0, st>>>(P, sg, K, d_rows, n_rows, d_rpts, d_rst, d_epts, d_est);
+  ++c->launches;
+  AOS_CUDA_OK(c, cudaGetLastError());
+
+  int counts[3] = {0, 0, 0};
+  int *d_flag = reinterpret_cast<int *>(d_tot + 4);
+  s = dedup_and_fetch(c, d_vpts, d_vst, n_virt, g, cap, d_scan, d_out, d_flag, d_tot + 1, &counts[0]);
+  if (s != AOS_OK) return s;
+  s = dedup_and_fetch(c, d_rpts, d_rst, n_ray, g, cap, d_scan, d_out + counts[0], d_flag, d_tot + 2, &counts[1]);
+  if (s != AOS_OK) return s;
+  s = dedup_and_fetch(c, d_epts, d_est, n_end, g, cap, d_scan, d_out + counts[0] + counts[1], d_flag, d_tot + 3, &counts[2]);
+  if (s != AOS_OK) return s;
+  const int total = counts[0] + counts[1] + counts[2];
+  c->h_seeds.resize(2 * (size_t)total);
+  if (total > 0)
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_seeds.data(), d_out, sizeof(double2) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  for (int k = 0; k < 3; ++k) c->seed_counts[k] = counts[k];
+  return AOS_OK;
+}
+
+}  // namespace aos

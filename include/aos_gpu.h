@@ -153,9 +153,10 @@ AOS_API aos_status aos_get_tree_rows(aos_ctx *ctx, aos_tree_row *dst, int32_t ca
 
 /* ---- seed selection: generateVirtualSeeds / raycastToOccupiedCell / generateRayPointsFromEndpoints /
  *      castRayFromEndpoint / endpoint seeds (seed_gen:1434-1511, 1730-1891, 1894-1982, 1987-2268) and the
- *      sorted /exploration_tree_rows_info (seed_gen:2546-2582).  Stays on the HOST (north star); the ray casts
- *      read the un-framed skeleton bit grid, fetched once from the device (W*H/8 bytes).  Seeds come out in
- *      /voronoi_seeds publish order: virtual, ray, endpoint (seed_gen:1670-1710); counts[3] = those sizes. -- */
+ *      sorted /exploration_tree_rows_info (seed_gen:2546-2582).  The ray casts walk the un-framed skeleton bit
+ *      grid on the device (one thread per ray) and the first-come 0.5 m filters are resolved there as well
+ *      (k_seeds.cu); only the row sort is host code.  Seeds come out in /voronoi_seeds publish order: virtual,
+ *      ray, endpoint (seed_gen:1670-1710); counts[3] = those sizes. ------------------------------------------ */
 AOS_API aos_status aos_select_seeds(aos_ctx *ctx, int32_t *n_seeds, int32_t counts[3]);
 AOS_API aos_status aos_get_seeds(aos_ctx *ctx, double *dst_xy, int32_t capacity, int32_t *n_out);
 /* 4 doubles per row: start x, y, end x, y; rows sorted by centre (y, then x). */
