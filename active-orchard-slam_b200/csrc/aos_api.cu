@@ -93,6 +93,14 @@ aos_status aos_create(int device, aos_ctx **out) {
     return AOS_ERR_CUDA;
   }
   c->own_stream = true;
+  bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < 3 && ok; ++k)
+    ok = cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    aos_destroy(c);
+    return AOS_ERR_CUDA;
+  }
   *out = c;
   return AOS_OK;
 }
@@ -106,7 +114,16 @@ void aos_destroy(aos_ctx *c) {
                     &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf,
                     &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2};
   for (DevBuf *b : bufs) b->release();
+  c->graph.release();
+  c->pin_facet_xy.release();
+  c->pin_enext.release();
+  c->pin_rows.release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  for (int k = 0; k < 3; ++k) {
+    if (c->aux[k]) cudaStreamDestroy(c->aux[k]);
+    if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

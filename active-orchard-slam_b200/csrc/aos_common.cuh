@@ -82,6 +82,37 @@ struct DevBuf {
   T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Pinned (page-locked) host array that only ever grows: staging for the small host<->device transfers of the gvd
+// half, so they run as true asynchronous DMA instead of pageable copies.
+template <typename T>
+struct PinVec {
+  T *p = nullptr;
+  size_t n = 0, cap = 0;
+  bool resize(size_t count) {  // contents are NOT preserved when growing
+    if (count > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      size_t want = count + count / 4 + 64;
+      if (cudaHostAlloc(reinterpret_cast<void **>(&p), want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) {
+        n = 0;
+        return false;
+      }
+      cap = want;
+    }
+    n = count;
+    return true;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = cap = 0;
+  }
+  T *data() { return p; }
+  const T *data() const { return p; }
+  size_t size() const { return n; }
+};
+
 // ---- TMA (cp.async.bulk.tensor) helpers --------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -188,8 +219,9 @@ bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x,
                          std::vector<float> *facet_xy, std::vector<int32_t> *facet_off);
 
 struct GraphInputs {
-  std::vector<float> facet_xy;  // one x,y per facet-vertex slot; slot e also is Voronoi edge e (vd:97-114)
-  std::vector<int> enext;       // slot of the edge's end point (next vertex of the same facet)
+  const float *facet_xy = nullptr;  // pinned host: one x,y per facet-vertex slot; slot e also is Voronoi edge e (vd:97-114)
+  const int *enext = nullptr;       // pinned host: slot of the edge's end point (next vertex of the same facet)
+  int n_slots = 0;
   const double *rows_info = nullptr;  // host, 4 per row
   int n_rows = 0;
   const uint32_t *skel_bits = nullptr;  // device, framed skeleton
@@ -201,16 +233,21 @@ struct GraphInputs {
 struct GraphHost {  // GvdGraph.msg arrays, host side
   float resolution = 0;
   double origin_x = 0, origin_y = 0;
-  std::vector<double> nodes_xyz;
-  std::vector<int32_t> node_labels, node_cluster_indices, node_label_counts, node_label_clusters, node_label_types, edges;
-  std::vector<float> edge_lengths, edge_clearances;
-  std::vector<double> corner_points;
+  PinVec<double> nodes_xyz;
+  PinVec<int32_t> node_labels, node_cluster_indices, node_label_counts, node_label_clusters, node_label_types, edges;
+  PinVec<float> edge_lengths, edge_clearances;
+  PinVec<double> corner_points;
   int n_merged_seeds = 0, n_voronoi_edges = 0, n_boundary_points = 0, n_rows = 0;
   void clear() {
-    nodes_xyz.clear(); node_labels.clear(); node_cluster_indices.clear(); node_label_counts.clear();
-    node_label_clusters.clear(); node_label_types.clear(); edges.clear(); edge_lengths.clear();
-    edge_clearances.clear(); corner_points.clear();
+    PinVec<int32_t> *iv[] = {&node_labels, &node_cluster_indices, &node_label_counts, &node_label_clusters, &node_label_types, &edges};
+    for (auto *v : iv) v->n = 0;
+    nodes_xyz.n = edge_lengths.n = edge_clearances.n = corner_points.n = 0;
     n_voronoi_edges = n_boundary_points = n_rows = 0;
+  }
+  void release() {
+    PinVec<int32_t> *iv[] = {&node_labels, &node_cluster_indices, &node_label_counts, &node_label_clusters, &node_label_types, &edges};
+    for (auto *v : iv) v->release();
+    nodes_xyz.release(); edge_lengths.release(); edge_clearances.release(); corner_points.release();
   }
 };
 aos_status run_graph(Ctx *c, const GraphInputs &in);
@@ -236,6 +273,8 @@ struct Ctx {
   }
 
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // side streams: independent launches run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool own_stream = false;
   std::string err;
 
@@ -267,6 +306,9 @@ struct Ctx {
   GraphHost graph;
   DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel, seed_buf, seed_buf2;
   std::vector<double> h_merged;
+  PinVec<float> pin_facet_xy;
+  PinVec<int> pin_enext;
+  PinVec<double> pin_rows;
 
   // host seed selection (host_seeds.cu)
   bool have_seeds = false;

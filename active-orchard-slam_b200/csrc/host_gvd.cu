@@ -38,6 +38,7 @@ bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x,
   // cv::Subdiv2D(Rect): the Rect2f converts to the int Rect through saturate_cast<int> == cvRound
   // (round-half-even), OpenCV 4.5.4 as shipped with ROS 2 Humble (package.xml:48)
   Subdiv sd;
+  sd.reserve((size_t)n);
   sd.init((int)lrint((double)rx), (int)lrint((double)ry), (int)lrint((double)rw), (int)lrint((double)rh));
   const float margin = 0.1f;
   for (int i = 0; i < n; ++i) {
@@ -152,19 +153,26 @@ aos_status aos_gvd_stage(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, co
   c->mark("gvd_host_voronoi");
   // facets -> edge slots (vd:97-114); facets with fewer than 2 vertices contribute nothing
   const int nf = (int)foff.size() - 1;
-  in.facet_xy.reserve(fxy.size());
-  in.enext.reserve(fxy.size() / 2);
+  if (!c->pin_facet_xy.resize(fxy.size()) || !c->pin_enext.resize(fxy.size() / 2) || !c->pin_rows.resize(4 * (size_t)n_rows)) {
+    set_error(c, "cudaHostAlloc failed for the facet staging buffers");
+    return AOS_ERR_CUDA;
+  }
+  int slots = 0;
   for (int f = 0; f < nf; ++f) {
     const int b = foff[f], k = foff[f + 1] - b;
     if (k < 2) continue;
-    const int base = (int)in.enext.size();
-    for (int j = 0; j < k; ++j) {
-      in.facet_xy.push_back(fxy[2 * (size_t)(b + j)]);
-      in.facet_xy.push_back(fxy[2 * (size_t)(b + j) + 1]);
-      in.enext.push_back(base + (j + 1) % k);
-    }
+    const int base = slots;
+    memcpy(c->pin_facet_xy.data() + 2 * (size_t)base, fxy.data() + 2 * (size_t)b, sizeof(float) * 2 * (size_t)k);
+    int *en = c->pin_enext.data() + base;
+    for (int j = 0; j < k; ++j) en[j] = base + j + 1;
+    en[k - 1] = base;
+    slots += k;
   }
-  in.rows_info = rows_info;
+  if (n_rows) memcpy(c->pin_rows.data(), rows_info, sizeof(double) * 4 * (size_t)n_rows);
+  in.facet_xy = c->pin_facet_xy.data();
+  in.enext = c->pin_enext.data();
+  in.n_slots = slots;
+  in.rows_info = c->pin_rows.data();
   in.n_rows = n_rows;
   aos_status s = run_graph(c, in);
   if (s != AOS_OK) return s;

@@ -12,6 +12,10 @@ class Subdiv {
  public:
   // integer rectangle, as cv::Subdiv2D(Rect) receives it
   void init(int rx, int ry, int rw, int rh);
+  void reserve(size_t n_points) {
+    q_.reserve(3 * n_points + 16);
+    vtx_.reserve(3 * n_points + 16);  // real vertices + one Voronoi vertex per triangle
+  }
   // vertex id, or -1 where cv::Subdiv2D::insert would throw (point outside the rectangle / walk failure)
   int insert(float x, float y);
   // getVoronoiFacetList(idx = {}): one polygon per inserted vertex in insertion order, flat x,y + offsets

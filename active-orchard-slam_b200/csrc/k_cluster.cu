@@ -726,24 +726,22 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
       q[slot] = (ry + by0) * w + rx + bx0;
       atomicAnd(word_ptr(rx, ry), ~(1u << (rx & 31)));
     }
-    // float32 running sums in FIFO order (seed_gen:1053-1057); every lane keeps the same copy
-    sum_x = __fadd_rn(sum_x, (float)((int)(c0 & 0xfffffu) + bx0));
-    sum_y = __fadd_rn(sum_y, (float)((int)(c0 >> 20) + by0));
-    if (avail > 1) {
-      sum_x = __fadd_rn(sum_x, (float)((int)(c1 & 0xfffffu) + bx0));
-      sum_y = __fadd_rn(sum_y, (float)((int)(c1 >> 20) + by0));
-    }
-    if (avail > 2) {
-      sum_x = __fadd_rn(sum_x, (float)((int)(c2 & 0xfffffu) + bx0));
-      sum_y = __fadd_rn(sum_y, (float)((int)(c2 >> 20) + by0));
-    }
-    if (avail > 3) {
-      sum_x = __fadd_rn(sum_x, (float)((int)(c3 & 0xfffffu) + bx0));
-      sum_y = __fadd_rn(sum_y, (float)((int)(c3 >> 20) + by0));
-    }
     head += avail;
     tail += __popc(m);
     __syncwarp();
+  }
+  // float32 running sums in FIFO order (seed_gen:1053-1057): the queue now holds the BFS order; lanes fetch 32
+  // cells at a time, the additions themselves stay strictly sequential (every lane keeps the same copy)
+  __syncwarp();
+  for (int base = 0; base < n; base += 32) {
+    int pos = base + lane < n ? __ldcg(q + base + lane) : 0;
+    int y = pos / w;
+    float xf = (float)(pos - y * w), yf = (float)y;
+    const int cnt = min(32, n - base);
+    for (int j = 0; j < cnt; ++j) {
+      sum_x = __fadd_rn(sum_x, __shfl_sync(0xffffffffu, xf, j));
+      sum_y = __fadd_rn(sum_y, __shfl_sync(0xffffffffu, yf, j));
+    }
   }
   if (lane == 0) {
     centre_out[2 * c] = __fdiv_rn(sum_x, (float)(unsigned long long)n);
@@ -894,6 +892,10 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
       }
       jobs[cls].push_back(j);
     }
+    for (int k = 0; k < 4; ++k)  // longest first: CTAs are dispatched in index order
+      std::sort(jobs[k].begin(), jobs[k].end(), [&](const ReplayJob &a, const ReplayJob &b) {
+        return h_acc[a.cluster].size > h_acc[b.cluster].size;
+      });
     size_t total_jobs = need.size();
     if (getenv("AOS_DEBUG")) {
       size_t mx[4] = {0, 0, 0, 0};
@@ -917,24 +919,39 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     uint32_t *gvisited = prefix;  // compact indices are no longer needed: reuse as the global "unvisited" bitmap
     if (!jobs[3].empty()) AOS_CUDA_OK(c, cudaMemcpyAsync(gvisited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
     c->mark("replay_prep");
+    // the size classes are independent launches: class 0 stays on the context stream, the others fork onto side
+    // streams so that a few very long rows do not serialise behind the many short ones
+    AOS_CUDA_OK(c, cudaEventRecord(c->ev_fork, st));
     size_t done = 0;
+    int side = 0;
+    bool forked[3] = {false, false, false};
     for (int k = 0; k < 4; ++k) {
       if (jobs[k].empty()) continue;
       size_t smem = kRingN * 4 + (k < 3 ? class_words[k] * 4 : 0);
+      cudaStream_t ls = st;
+      if (k > 0 && side < 3) {
+        ls = c->aux[side];
+        AOS_CUDA_OK(c, cudaStreamWaitEvent(ls, c->ev_fork, 0));
+        forked[side++] = true;
+      }
       if (k < 3) {
         if (smem > 48 * 1024)
           AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, smem, st>>>(P, d_jobs + done, acc, offsets, root_cellpos,
+        bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, smem, ls>>>(P, d_jobs + done, acc, offsets, root_cellpos,
                                                                             mask, gvisited, queue, centre);
-  ++c->launches;
       } else {
-        bfs_replay_kernel<false><<<(unsigned)jobs[k].size(), 32, smem, st>>>(P, d_jobs + done, acc, offsets, root_cellpos,
+        bfs_replay_kernel<false><<<(unsigned)jobs[k].size(), 32, smem, ls>>>(P, d_jobs + done, acc, offsets, root_cellpos,
                                                                              mask, gvisited, queue, centre);
-  ++c->launches;
       }
+      ++c->launches;
       done += jobs[k].size();
     }
     AOS_CUDA_OK(c, cudaGetLastError());
+    for (int k = 0; k < 3; ++k)
+      if (forked[k]) {
+        AOS_CUDA_OK(c, cudaEventRecord(c->ev_join[k], c->aux[k]));
+        AOS_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join[k], 0));
+      }
     c->mark("replay_bfs");
     cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length,
                                                                          d_flagged, queue, centre, d_clusters, d_rows);

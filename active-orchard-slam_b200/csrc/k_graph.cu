@@ -654,7 +654,7 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   G.origin_x = in.ox;
   G.origin_y = in.oy;
   G.n_rows = in.n_rows;
-  const int K = (int)(in.facet_xy.size() / 2);  // facet-vertex slots == Voronoi edges (vd:97-114)
+  const int K = in.n_slots;  // facet-vertex slots == Voronoi edges (vd:97-114)
   G.n_voronoi_edges = K;
   const int n_rows = in.n_rows;
   // bounds, gvd:278-281 / :422-431: origin + float(width * resolution)
@@ -662,7 +662,8 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   const Bounds B{in.ox, in.ox + gw, in.oy, in.oy + gh};
   GridView gv{in.skel_bits, in.w, in.h, in.pitch, in.ox, in.oy, in.res};
   if (K == 0) {
-    G.corner_points.assign((size_t)8 * n_rows, 0.0);
+    if (!G.corner_points.resize((size_t)8 * n_rows)) return AOS_ERR_CUDA;
+    memset(G.corner_points.data(), 0, sizeof(double) * 8 * (size_t)n_rows);
     return AOS_OK;
   }
 
@@ -733,8 +734,8 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   uint32_t *d_loff = A.take<uint32_t>(K + 1), *d_lcur = A.take<uint32_t>(K + 1);
   uint32_t *d_tot = reinterpret_cast<uint32_t *>(d_cnt + 8);  // scan totals
 
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_fxy, in.facet_xy.data(), sizeof(float2) * K, cudaMemcpyHostToDevice, st));
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_enext, in.enext.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_fxy, in.facet_xy, sizeof(float2) * K, cudaMemcpyHostToDevice, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_enext, in.enext, sizeof(int) * K, cudaMemcpyHostToDevice, st));
   if (n_rows) AOS_CUDA_OK(c, cudaMemcpyAsync(d_rows, in.rows_info, sizeof(double) * 4 * n_rows, cudaMemcpyHostToDevice, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(d_state, 0, K, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(g5.h.keys, 0xff, sizeof(unsigned long long) * cap_pts, st));
@@ -877,7 +878,8 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   c->mark("gvd_crop");
 
   // ---- TL/TR/BL/BR corner nodes + labels ---------------------------------------------------------------
-  G.corner_points.assign((size_t)8 * n_rows, 0.0);
+  if (!G.corner_points.resize((size_t)8 * n_rows)) return AOS_ERR_CUDA;
+  if (n_rows) memset(G.corner_points.data(), 0, sizeof(double) * 8 * (size_t)n_rows);
   int n_label_entries = 0;
   int *d_codes = nullptr, *d_lcl = nullptr, *d_lty = nullptr;
   AOS_CUDA_OK(c, cudaMemsetAsync(d_loff, 0, sizeof(uint32_t) * ((size_t)N + 1), st));
@@ -932,15 +934,13 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   c->mark("gvd_corners_labels");
 
   // ---- results to the host (GvdGraph.msg arrays) -------------------------------------------------------
-  G.nodes_xyz.resize(3 * (size_t)N);
-  G.node_labels.resize(N);
-  G.node_cluster_indices.resize(N);
-  G.node_label_counts.resize(N);
-  G.node_label_clusters.resize(n_label_entries);
-  G.node_label_types.resize(n_label_entries);
-  G.edges.resize(2 * (size_t)NE);
-  G.edge_lengths.resize(NE);
-  G.edge_clearances.resize(NE);
+  if (!G.nodes_xyz.resize(3 * (size_t)N) || !G.node_labels.resize(N) || !G.node_cluster_indices.resize(N) ||
+      !G.node_label_counts.resize(N) || !G.node_label_clusters.resize(n_label_entries) ||
+      !G.node_label_types.resize(n_label_entries) || !G.edges.resize(2 * (size_t)NE) || !G.edge_lengths.resize(NE) ||
+      !G.edge_clearances.resize(NE)) {
+    set_error(c, "cudaHostAlloc failed for the graph result buffers");
+    return AOS_ERR_CUDA;
+  }
   if (N > 0) {
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.nodes_xyz.data(), d_xyz, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.node_labels.data(), d_labels, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));

@@ -93,9 +93,13 @@ struct RayConsts {
   double gw, gh;      // float(width * resolution), float(height * resolution)
 };
 
-// castRayFromEndpoint, seed_gen:1774-1891
-__device__ double2 cast_ray_from_endpoint_dev(const SeedGrid &g, const RayConsts &K, double spx, double spy, double opx,
-                                              double opy, int ang /* 0: 0 deg, 1: -90, 2: +90 */, double min_distance) {
+// castRayFromEndpoint, seed_gen:1774-1891, one WARP per ray.  The reference advances `cur += 0.1` step by step
+// (a sequential floating-point accumulation) until the sample leaves the grid or lands on a skeleton cell; rays
+// along a row can run for 10^4 steps.  Every lane replays 32 of those additions (bit-identical values of `cur`),
+// keeps the one of its own step, evaluates that step, and the first lane whose step terminates the loop wins.
+__device__ double2 cast_ray_from_endpoint_warp(const SeedGrid &g, const RayConsts &K, double spx, double spy, double opx,
+                                               double opy, int ang /* 0: 0 deg, 1: -90, 2: +90 */, double min_distance,
+                                               int lane) {
   double ex = opx - spx, ey = opy - spy;
   if (sqrt(ex * ex + ey * ey) < 1e-6) {
     ex = 1.0;
@@ -117,13 +121,39 @@ __device__ double2 cast_ray_from_endpoint_dev(const SeedGrid &g, const RayConsts
   const double resolution = (double)g.res;
   const double abs_max = sqrt(K.gw * K.gw + K.gh * K.gh) * 3.0;
   double cur = min_distance;
-  while (cur <= abs_max) {
-    double px = spx + rdx * cur, py = spy + rdy * cur;
-    if (!(px >= minx && px <= maxx && py >= miny && py <= maxy))
-      return make_double2(fmax(minx, fmin(maxx, px)), fmax(miny, fmin(maxy, py)));
-    int mx = (int)((px - g.ox) / resolution), my = (int)((py - g.oy) / resolution);
-    if (mx >= 0 && mx < g.w && my >= 0 && my < g.h && sg_occ(g, mx, my)) return make_double2(px, py);
-    cur += 0.1;
+  for (;;) {
+    double c = cur, mine = cur;
+#pragma unroll 1
+    for (int j = 1; j < 32; ++j) {
+      c += 0.1;
+      if (j == lane) mine = c;
+    }
+    // status of this lane's step: 0 continue, 1 left the grid, 2 hit a cell, 3 past abs_max (loop condition fails)
+    int status = 0;
+    double px = 0.0, py = 0.0;
+    if (!(mine <= abs_max)) {
+      status = 3;
+    } else {
+      px = spx + rdx * mine;
+      py = spy + rdy * mine;
+      if (!(px >= minx && px <= maxx && py >= miny && py <= maxy)) {
+        status = 1;
+      } else {
+        int mx = (int)((px - g.ox) / resolution), my = (int)((py - g.oy) / resolution);
+        if (mx >= 0 && mx < g.w && my >= 0 && my < g.h && sg_occ(g, mx, my)) status = 2;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, status != 0);
+    if (m) {
+      const int f = __ffs(m) - 1;
+      const int st = __shfl_sync(0xffffffffu, status, f);
+      px = __shfl_sync(0xffffffffu, px, f);
+      py = __shfl_sync(0xffffffffu, py, f);
+      if (st == 1) return make_double2(fmax(minx, fmin(maxx, px)), fmax(miny, fmin(maxy, py)));
+      if (st == 2) return make_double2(px, py);
+      break;
+    }
+    cur = c + 0.1;
   }
   double fx = spx + rdx * abs_max, fy = spy + rdy * abs_max;
   if (!(fx >= minx && fx <= maxx && fy >= miny && fy <= maxy)) {
@@ -196,12 +226,15 @@ __global__ void ray_points_kernel(const __grid_constant__ SeedDeviceParams P, Se
                                   const RowDev *__restrict__ rows, int n_rows, double2 *__restrict__ ray_pts,
                                   unsigned char *__restrict__ ray_state, double2 *__restrict__ end_pts,
                                   unsigned char *__restrict__ end_state) {
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 6 * n_rows; idx += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < 6 * n_rows; idx += warps) {
     const int r = idx / 6, k = idx % 6;
     const RowDev R = rows[r];
     const bool from_start = k < 3;
-    const double2 p = cast_ray_from_endpoint_dev(g, K, from_start ? R.sx : R.ex, from_start ? R.sy : R.ey,
-                                                 from_start ? R.ex : R.sx, from_start ? R.ey : R.sy, k % 3, 1.0);
+    const double2 p = cast_ray_from_endpoint_warp(g, K, from_start ? R.sx : R.ex, from_start ? R.sy : R.ey,
+                                                  from_start ? R.ex : R.sx, from_start ? R.ey : R.sy, k % 3, 1.0, lane);
+    if (lane != 0) continue;
     const double minx = g.ox, maxx = g.ox + K.gw, miny = g.oy, maxy = g.oy + K.gh;
     bool valid = isfinite(p.x) && isfinite(p.y) && (p.x >= minx && p.x <= maxx && p.y >= miny && p.y <= maxy);
     if (valid && P.n_poly > 0 && in_polygon_dev(P, p.x, p.y)) valid = false;
@@ -379,7 +412,7 @@ aos_status device_select_seeds(Ctx *c) {
     vs_generate_kernel<<<blocks_for(n_virt, 128), 128, 0, st>>>(P, sg, d_rows, n_rows, d_offs, n_virt, d_vpts, d_vst);
     ++c->launches;
   }
-  ray_points_kernel<<<blocks_for(n_ray, 64), 64, 0, st>>>(P, sg, K, d_rows, n_rows, d_rpts, d_rst, d_epts, d_est);
+  ray_points_kernel<<<blocks_for((size_t)n_ray * 32, 128), 128, 0, st>>>(P, sg, K, d_rows, n_rows, d_rpts, d_rst, d_epts, d_est);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
 

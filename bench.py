@@ -94,13 +94,14 @@ def make_params(lib, spec):
 
 # ---------------------------------------------------------------------------------------------------
 def bench_ours(args):
+    import concurrent.futures as cf
+
     import torch
 
+    from aos_gpu import dist as adist
     from aos_gpu import lib, synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = adist.env_rank_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libaos_gpu has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -114,70 +115,86 @@ def bench_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    spec = synth.config(args.workload, seed=rank, n_points=args.points)
-    params = make_params(lib, spec)
+    ncpu = os.cpu_count() or 1
+    T = args.maps_in_flight if args.maps_in_flight > 0 else max(1, min(8, ncpu // max(world, 1)))
+    spec0 = synth.config(args.workload, seed=rank * 64, n_points=args.points)
+    params = make_params(lib, spec0)
     gi = lib.grid_geometry(params)
     cells = gi.width * gi.height
     t0 = time.time()
-    pts = synth.make_orchard_torch(spec, dev)
+    # one independent map per stream in flight (different generator seeds), all resident in HBM
+    maps = []
+    for t in range(T):
+        spec = synth.config(args.workload, seed=rank * 64 + t, n_points=args.points)
+        maps.append(synth.make_orchard_torch(spec, dev))
     torch.cuda.synchronize()
-    n_pts = pts.shape[0]
-    host_pts = torch.empty(pts.shape, dtype=pts.dtype, pin_memory=True)
-    host_pts.copy_(pts)
+    n_pts = maps[0].shape[0]
+    host_pts = torch.empty(maps[0].shape, dtype=maps[0].dtype, pin_memory=True)   # e2e source (map 0, pinned)
+    host_pts.copy_(maps[0])
     host_np = host_pts.numpy()
     gen_s = time.time() - t0
 
-    ctx = lib.Context(local)
-    stream = torch.cuda.Stream(device=dev)
-    ctx.set_stream(stream.cuda_stream)
+    ctxs = [lib.Context(local) for _ in range(T)]     # one context (own stream, own buffers) per map in flight
+    fetch_bufs = [{} for _ in range(T)]               # e2e result buffers, reused step after step
+    pool = cf.ThreadPoolExecutor(max_workers=T)        # ctypes releases the GIL: host stages run on T cores
 
-    def step_device():
-        return ctx.map_to_graph(params, pts)
+    def run_batch(steps, host=False):
+        """Every stream processes `steps` maps back to back; returns the last summary of stream 0."""
+        def work(t):
+            torch.cuda.set_device(local)
+            out = None
+            for _ in range(steps):
+                out = ctxs[t].map_to_graph(params, host_np if host else maps[t], fetch=fetch_bufs[t] if host else None)
+            return out
+        return list(pool.map(work, range(T)))[0]
 
-    def step_host():
-        return ctx.map_to_graph(params, host_np, fetch=True)
-
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            info = step_device()
-        # ---- value: device-resident inputs -------------------------------------------------------
-        l0 = ctx.launch_count()
+    def timed(steps, host=False):
+        """CUDA events on the current stream around the whole batch, device idle at both records."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        with ClockSampler(local) as clk:
-            ev0.record(stream)
-            for _ in range(args.steps):
-                info = step_device()
-            ev1.record(stream)
-            barrier()
-        dev_ms = ev0.elapsed_time(ev1)
-        launches = (ctx.launch_count() - l0) / max(args.steps, 1)
-        # ---- e2e: host points in, host results out ---------------------------------------------------
-        for _ in range(min(args.warmup, 2)):
-            info_h = step_host()
-        barrier()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev2.record(stream)
+        ev0.record()
         w0 = time.perf_counter()
-        for _ in range(args.steps):
-            info_h = step_host()
-        ev3.record(stream)
+        info = run_batch(steps, host)
+        torch.cuda.synchronize()
+        ev1.record()
+        ev1.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3
         barrier()
-        e2e_wall_ms = (time.perf_counter() - w0) * 1e3
-        e2e_ms = max(ev2.elapsed_time(ev3), e2e_wall_ms)
-        # ---- per-stage device times (CUDA events recorded by the library on the same stream) ----------
-        ctx.set_profiling(True)
-        stage_acc = {}
+        return max(ev0.elapsed_time(ev1), wall_ms), info
+
+    run_batch(args.warmup)
+    l0 = sum(c.launch_count() for c in ctxs)
+    with ClockSampler(local) as clk:
+        dev_ms, info = timed(args.steps)
+    launches = (sum(c.launch_count() for c in ctxs) - l0) / max(args.steps, 1)
+    run_batch(min(args.warmup, 2), host=True)
+    e2e_ms, info_h = timed(args.steps, host=True)
+
+    # ---- one map at a time on one stream: latency per map, per-stage device times ------------------------
+    c0 = ctxs[0]
+    stream = torch.cuda.Stream(device=dev)
+    c0.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        c0.map_to_graph(params, maps[0])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(stream)
         reps = 3
         for _ in range(reps):
-            step_device()
-            for name, ms in ctx.stage_times():
+            c0.map_to_graph(params, maps[0])
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        single_ms = ev0.elapsed_time(ev1) / reps
+        c0.set_profiling(True)
+        stage_acc = {}
+        for _ in range(reps):
+            c0.map_to_graph(params, maps[0])
+            for name, ms in c0.stage_times():
                 stage_acc[name] = stage_acc.get(name, 0.0) + ms / reps
-        ctx.set_profiling(False)
+        c0.set_profiling(False)
 
-    from aos_gpu import dist as adist
-    dev_ms, total_cells = adist.reduce_stats(dev_ms, cells * args.steps, device=dev)   # MAX over ranks, SUM of cells
-    e2e_ms, _ = adist.reduce_stats(e2e_ms, cells * args.steps, device=dev)
+    dev_ms, total_cells = adist.reduce_stats(dev_ms, cells * args.steps * T, device=dev)   # MAX over ranks, SUM of cells
+    e2e_ms, _ = adist.reduce_stats(e2e_ms, cells * args.steps * T, device=dev)
     ms_per_step = dev_ms / args.steps
     value = adist.throughput_mcells(total_cells, dev_ms)
     e2e_value = adist.throughput_mcells(total_cells, e2e_ms)
@@ -189,24 +206,32 @@ def bench_ours(args):
         bin_ms = stage_acc.get("bin", float("nan"))
         bin_bytes = 16.0 * n_pts
         achieved = bin_bytes / (bin_ms * 1e-3) / 1e9 if bin_ms == bin_ms and bin_ms > 0 else None
-        b_alg = 16.0 * n_pts + 9.125 * cells  # compulsory bytes of the whole map
+        b_alg = 16.0 * n_pts + 9.125 * cells  # compulsory bytes of one map
+        gpu_ms = sum(v for k, v in stage_acc.items() if k not in ("gvd_host_voronoi",))
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec.grid_resolution} m, "
-                                   f"{n_pts} points, one map per GPU",
-                       "l2": "inputs (16 B x points) larger than L2 at C3; each step re-reads them from HBM",
-                       "pipeline": info.get("pipeline", "seed_stage"), "graph": info.get("graph")},
+            "config": {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec0.grid_resolution} m, "
+                                   f"{n_pts} points per map",
+                       "maps_in_flight": T, "step": f"{T} independent maps per GPU, one per stream/host thread "
+                                                    "(the Subdiv2D replay of each map runs on its own host core)",
+                       "host_cores": ncpu,
+                       "l2": "inputs (16 B x points per map) larger than L2; every map is re-read from HBM",
+                       "pipeline": info.get("pipeline"), "graph": info.get("graph")},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 3),
-                    "h2d_bytes_per_step": int(n_pts * 16), "d2h_bytes_per_step": int(info_h.get("d2h_bytes", 0))},
+                    "h2d_bytes_per_step": int(n_pts * 16) * T, "d2h_bytes_per_step": int(info_h.get("d2h_bytes", 0)) * T},
+            "single_map": {"ms_per_map": round(single_ms, 3), "value": round(cells / (single_ms * 1e-3) / 1e6, 1), "unit": UNIT,
+                           "device_stages_ms": round(gpu_ms, 3), "host_voronoi_ms": round(stage_acc.get("gvd_host_voronoi", 0.0), 3)},
             "gpu_launches": int(round(launches)),
             "roofline": {"bound": "hbm", "kernel": "bin_points_xyz16", "achieved": round(achieved, 1) if achieved else None,
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": 3225713440 if args.workload == "C3" and args.points is None else None,
+                         "traffic_source": "ncu --set full, profiles/r01_a_seed_stage_c3.txt (dram read + write per launch)",
+                         "peak_source": peak_src,
                          "whole_map": {"algorithmic_bytes": int(b_alg),
-                                       "achieved_gbs": round(b_alg / (ms_per_step * 1e-3) / 1e9, 1),
-                                       "frac": round(b_alg / (ms_per_step * 1e-3) / 1e9 / peak, 4)}},
+                                       "device_stages_gbs": round(b_alg / (gpu_ms * 1e-3) / 1e9, 1) if gpu_ms > 0 else None,
+                                       "device_stages_frac": round(b_alg / (gpu_ms * 1e-3) / 1e9 / peak, 4) if gpu_ms > 0 else None}},
             "stages_ms": {k: round(v, 4) for k, v in stage_acc.items()},
             "clocks": clk.summary(),
             "gen_s": round(gen_s, 2),
@@ -217,7 +242,9 @@ def bench_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    pool.shutdown()
+    for c in ctxs:
+        c.close()
     return line
 
 
@@ -322,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--points", type=int, default=None, help="override the workload's point count")
+    ap.add_argument("--maps-in-flight", type=int, default=0,
+                    help="independent maps processed concurrently per GPU (0 = min(8, host cores / ranks))")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
