@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
     "aos_gvd_stage", "aos_get_graph", "aos_map_to_graph", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
+    "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
 
 
@@ -76,6 +77,10 @@ class CGvdGraph(C.Structure):
                 ("edge_clearances", C.POINTER(C.c_float)), ("n_merged_seeds", C.c_int32),
                 ("n_voronoi_edges", C.c_int32), ("n_boundary_points", C.c_int32),
                 ("corner_points", C.POINTER(C.c_double)), ("n_rows", C.c_int32)]
+
+
+class CBand(C.Structure):
+    _fields_ = [("row0", C.c_int32), ("rows", C.c_int32), ("halo_lo", C.c_int32), ("halo_hi", C.c_int32)]
 
 
 class CSeedSummary(C.Structure):
@@ -133,6 +138,12 @@ def load() -> C.CDLL:
     L.aos_get_graph.argtypes = [vp, C.POINTER(CGvdGraph)]
     L.aos_map_to_graph.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.aos_set_subdiv_outer_factor.argtypes = [C.c_float]
+    L.aos_band_halo_rows.argtypes = [C.POINTER(CSeedParams)]
+    L.aos_band_raster.argtypes = [vp, C.POINTER(CSeedParams), C.POINTER(CBand), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, C.c_int]
+    L.aos_band_thin_launch.argtypes = [vp, C.POINTER(i32)]
+    L.aos_band_grid_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
+    L.aos_seed_stage_tail.argtypes = [vp, C.POINTER(CSeedParams), vp, vp]
     L.aos_merge_seeds.argtypes = [vp, i32, vp, C.POINTER(i32)]
     L.aos_voronoi_facets.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, vp, i32, vp, i32,
                                      C.POINTER(i32), C.POINTER(i32)]
@@ -325,6 +336,36 @@ class Context:
             info["fetched"] = fetch
             info["graph_arrays"] = graph
         return info
+
+    # ---- row-band sharding (see bands.py) ------------------------------------------------------
+    def band_halo_rows(self, params: SeedParams) -> int:
+        return int(self.L.aos_band_halo_rows(C.byref(params.to_c())))
+
+    def band_raster(self, params: SeedParams, band, points, n_points=None, point_step=None, offsets=(0, 4, 8)):
+        cp = params.to_c()
+        cb = CBand(band.row0, band.rows, band.halo_lo, band.halo_hi)
+        ptr, mem, n, step = self._points_args(points, n_points, point_step)
+        self._check(self.L.aos_band_raster(self.h, C.byref(cp), C.byref(cb), C.c_void_p(ptr), n, step, offsets[0],
+                                           offsets[1], offsets[2], mem), "aos_band_raster")
+
+    def band_thin_launch(self) -> bool:
+        d = C.c_int32()
+        self._check(self.L.aos_band_thin_launch(self.h, C.byref(d)), "aos_band_thin_launch")
+        return bool(d.value)
+
+    def band_grid_device(self, which: int):
+        p, pitch, rows = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._check(self.L.aos_band_grid_device(self.h, which, C.byref(p), C.byref(pitch), C.byref(rows)), "aos_band_grid_device")
+        return p.value, pitch.value, rows.value
+
+    def seed_stage_tail(self, params: SeedParams, skeleton_bits, occupancy_bits=None):
+        """skeleton_bits / occupancy_bits: full-size device bit grids (objects with data_ptr(), e.g. torch tensors)."""
+        cp = params.to_c()
+        self._keep_grids = (skeleton_bits, occupancy_bits)
+        rc = self.L.aos_seed_stage_tail(self.h, C.byref(cp), C.c_void_p(skeleton_bits.data_ptr()),
+                                        C.c_void_p(occupancy_bits.data_ptr()) if occupancy_bits is not None else None)
+        self._check(rc, "aos_seed_stage_tail")
+        return self.seed_summary()
 
     # ---- gvd stage ---------------------------------------------------------------------------
     def gvd_stage(self, seeds, rows_info, skeleton=None, info=None) -> dict:

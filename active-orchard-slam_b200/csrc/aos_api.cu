@@ -190,37 +190,109 @@ aos_status aos_grid_geometry(const aos_seed_params *p, aos_grid_info *info) {
   return AOS_OK;
 }
 
-aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points,
-                          uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
-  if (!c) return AOS_ERR_INVALID;
-  aos_status s = check_params(c, p);
-  if (s != AOS_OK) return s;
-  AOS_REQUIRE(c, n_points == 0 || points != nullptr, "points is null");
-  AOS_REQUIRE(c, n_points == 0 || (point_step >= 12 && off_x + 4 <= point_step && off_y + 4 <= point_step &&
-                                   off_z + 4 <= point_step),
-              "point_step / field offsets do not describe float32 x,y,z inside a record");
-  AOS_CUDA_OK(c, cudaSetDevice(c->device));
-  c->have_seed = false;
-  c->have_seeds = false;
+}  // extern "C"
 
-  aos_grid_info gi;
-  aos_grid_geometry(p, &gi);
-  AOS_REQUIRE(c, (double)gi.width * (double)gi.height < 2.0e9, "grid has more than 2^31 cells");
-  SeedDeviceParams &P = c->P;
+namespace {
+
+// grid geometry + device parameter block of the FULL grid (generateOccupancyGrid header, seed_gen:587-600)
+aos_status fill_device_params(aos_ctx *c, const aos_seed_params *p, aos_grid_info *gi, SeedDeviceParams *Pp) {
+  aos_grid_geometry(p, gi);
+  AOS_REQUIRE(c, (double)gi->width * (double)gi->height < 2.0e9, "grid has more than 2^31 cells");
+  SeedDeviceParams &P = *Pp;
   memset(&P, 0, sizeof(P));
   active_bounds(p, &P.minx, &P.maxx, &P.miny, &P.maxy);
   P.minz = p->clipping_minz;
   P.maxz = p->clipping_maxz;
   P.res = p->grid_resolution;
-  P.ox = gi.origin_x;
-  P.oy = gi.origin_y;
-  P.w = gi.width;
-  P.h = gi.height;
-  P.pitch = pitch_words_for(gi.width);
+  P.ox = gi->origin_x;
+  P.oy = gi->origin_y;
+  P.w = gi->width;
+  P.h = gi->height;
+  P.pitch = pitch_words_for(gi->width);
+  P.y_off = 0;
+  P.gh = gi->height;
   P.n_excl = p->n_exclusion;
   for (int i = 0; i < 3 * p->n_exclusion; ++i) P.excl[i] = p->exclusion[i];
   P.n_poly = p->n_polygon;
   for (int i = 0; i < 2 * p->n_polygon; ++i) P.poly[i] = p->polygon[i];
+  return AOS_OK;
+}
+
+// markPolygonBoundaryAsOccupied (seed_gen:772-825) + clusterOccupiedCells / rows on the full-size skeleton in
+// c->g_skel; fills the summary.  Shared by aos_seed_stage and aos_seed_stage_tail.
+aos_status seed_tail(aos_ctx *c, const aos_seed_params *p, const aos_grid_info &gi, int launches, int subiters,
+                     const unsigned long long *d_kept) {
+  const SeedDeviceParams &P = c->P;
+  cudaStream_t st = c->stream;
+  aos_status s;
+  if (p->n_polygon > 0) {
+    double bx0 = p->polygon[0], bx1 = bx0, by0 = p->polygon[1], by1 = by0;
+    for (int i = 0; i < p->n_polygon; ++i) {
+      bx0 = std::min(bx0, p->polygon[2 * i]);
+      bx1 = std::max(bx1, p->polygon[2 * i]);
+      by0 = std::min(by0, p->polygon[2 * i + 1]);
+      by1 = std::max(by1, p->polygon[2 * i + 1]);
+    }
+    const double margin = 2.5;
+    int gx0, gy0, gx1, gy1;
+    world_to_grid(P.ox, P.oy, P.res, P.w, P.h, static_cast<float>(bx0 - margin), static_cast<float>(by0 - margin), &gx0, &gy0);
+    world_to_grid(P.ox, P.oy, P.res, P.w, P.h, static_cast<float>(bx1 + margin), static_cast<float>(by1 + margin), &gx1, &gy1);
+    s = launch_frame(c, c->g_skel.as<uint32_t>(), c->g_framed.as<uint32_t>(), P.w, P.h, std::min(gx0, gx1),
+                     std::min(gy0, gy1), std::max(gx0, gx1), std::max(gy0, gy1), 1);
+  } else {
+    s = launch_frame(c, c->g_skel.as<uint32_t>(), c->g_framed.as<uint32_t>(), P.w, P.h, 0, 0, P.w - 1, P.h - 1, 5);
+  }
+  if (s != AOS_OK) return s;
+
+  c->mark("frame");
+  s = run_clusters(c, P, c->g_skel.as<uint32_t>(), static_cast<float>(p->cluster_min_length));
+  if (s != AOS_OK) return s;
+  c->mark("cluster_tail");
+
+  if (d_kept) AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag + 32, d_kept, 8, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  c->summary.info = gi;
+  c->summary.n_clusters = c->n_clusters;
+  c->summary.n_rows = static_cast<int32_t>(c->h_rows.size());
+  c->summary.thinning_launches = launches;
+  c->summary.thinning_subiters = subiters;
+  c->summary.n_points_in = 0;
+  if (d_kept) memcpy(&c->summary.n_points_in, c->h_flag + 32, 8);
+  c->have_seed = true;
+  return AOS_OK;
+}
+
+aos_status check_points(aos_ctx *c, const void *points, size_t n_points, uint32_t point_step, uint32_t off_x,
+                        uint32_t off_y, uint32_t off_z) {
+  AOS_REQUIRE(c, n_points == 0 || points != nullptr, "points is null");
+  AOS_REQUIRE(c, n_points == 0 || (point_step >= 12 && off_x + 4 <= point_step && off_y + 4 <= point_step &&
+                                   off_z + 4 <= point_step),
+              "point_step / field offsets do not describe float32 x,y,z inside a record");
+  return AOS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points,
+                          uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  if (!c) return AOS_ERR_INVALID;
+  aos_status s = check_params(c, p);
+  if (s != AOS_OK) return s;
+  s = check_points(c, points, n_points, point_step, off_x, off_y, off_z);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->have_seed = false;
+  c->have_seeds = false;
+  c->have_band = false;
+  c->band_gh = 0;
+  c->partial_grids = false;
+
+  aos_grid_info gi;
+  SeedDeviceParams &P = c->P;
+  s = fill_device_params(c, p, &gi, &P);
+  if (s != AOS_OK) return s;
 
   const size_t gbytes = (size_t)P.pitch * P.h * 4;
   DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch};
@@ -261,41 +333,154 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   if (s != AOS_OK) return s;
 
   c->mark("thin");
-  // markPolygonBoundaryAsOccupied (seed_gen:772-825)
-  if (p->n_polygon > 0) {
-    double bx0 = p->polygon[0], bx1 = bx0, by0 = p->polygon[1], by1 = by0;
-    for (int i = 0; i < p->n_polygon; ++i) {
-      bx0 = std::min(bx0, p->polygon[2 * i]);
-      bx1 = std::max(bx1, p->polygon[2 * i]);
-      by0 = std::min(by0, p->polygon[2 * i + 1]);
-      by1 = std::max(by1, p->polygon[2 * i + 1]);
-    }
-    const double margin = 2.5;
-    int gx0, gy0, gx1, gy1;
-    world_to_grid(P.ox, P.oy, P.res, P.w, P.h, static_cast<float>(bx0 - margin), static_cast<float>(by0 - margin), &gx0, &gy0);
-    world_to_grid(P.ox, P.oy, P.res, P.w, P.h, static_cast<float>(bx1 + margin), static_cast<float>(by1 + margin), &gx1, &gy1);
-    s = launch_frame(c, c->g_skel.as<uint32_t>(), c->g_framed.as<uint32_t>(), P.w, P.h, std::min(gx0, gx1),
-                     std::min(gy0, gy1), std::max(gx0, gx1), std::max(gy0, gy1), 1);
-  } else {
-    s = launch_frame(c, c->g_skel.as<uint32_t>(), c->g_framed.as<uint32_t>(), P.w, P.h, 0, 0, P.w - 1, P.h - 1, 5);
+  return seed_tail(c, p, gi, launches, subiters, d_kept);
+}
+
+// ---- row-band sharding ------------------------------------------------------------------------------------
+int32_t aos_band_halo_rows(const aos_seed_params *p) {
+  if (!p || !(p->grid_resolution > 0.f)) return -1;
+  // inflation reaches R rows, the opening 2, one thinning launch kThinSubIters
+  return static_cast<int>(p->inflation_radius / p->grid_resolution) + 2 + kThinSubIters;
+}
+
+aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band *band, const void *points, size_t n_points,
+                           uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  if (!c) return AOS_ERR_INVALID;
+  aos_status s = check_params(c, p);
+  if (s != AOS_OK) return s;
+  s = check_points(c, points, n_points, point_step, off_x, off_y, off_z);
+  if (s != AOS_OK) return s;
+  AOS_REQUIRE(c, band != nullptr, "band is null");
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->have_seed = false;
+  c->have_seeds = false;
+  c->have_band = false;
+
+  aos_grid_info gi;
+  SeedDeviceParams P;
+  s = fill_device_params(c, p, &gi, &P);
+  if (s != AOS_OK) return s;
+  const int need = aos_band_halo_rows(p);
+  AOS_REQUIRE(c, band->rows > 0 && band->row0 >= 0 && band->row0 + band->rows <= gi.height, "band outside the grid");
+  AOS_REQUIRE(c, band->halo_lo >= 0 && band->halo_hi >= 0 && band->halo_lo <= band->row0 &&
+                     band->row0 + band->rows + band->halo_hi <= gi.height,
+              "band halo outside the grid");
+  AOS_REQUIRE(c, (band->halo_lo >= need || band->halo_lo == band->row0) &&
+                     (band->halo_hi >= need || band->row0 + band->rows + band->halo_hi == gi.height),
+              "band halo smaller than aos_band_halo_rows() away from the global border");
+  // local grid = halo_lo + rows + halo_hi rows; local row r is global row y_off + r
+  P.y_off = band->row0 - band->halo_lo;
+  P.h = band->halo_lo + band->rows + band->halo_hi;
+  c->band = *band;
+  c->band_y_off = P.y_off;
+  c->band_gh = gi.height;
+  c->band_cnt_r0 = band->halo_lo;
+  c->band_cnt_r1 = band->halo_lo + band->rows;
+  c->band_P = P;
+  c->band_gi = gi;
+
+  const size_t gbytes = (size_t)P.pitch * P.h * 4;
+  DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_scratch};
+  for (DevBuf *g : grids) AOS_CUDA_OK(c, g->reserve(gbytes));
+  AOS_CUDA_OK(c, c->misc.reserve(4096));
+  cudaStream_t st = c->stream;
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->g_raw.p, 0, gbytes, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->g_scratch.p, 0, gbytes, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(c->misc.p, 0, 4096, st));
+  c->marks.clear();
+  c->mark("start");
+  const void *dpoints = points;
+  if (points_mem == AOS_MEM_HOST && n_points) {
+    AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, st));
+    dpoints = c->points_stage.p;
   }
+  c->mark("h2d_points");
+  unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->misc.as<char>() + 1024);
+  s = launch_bin(c, P, dpoints, n_points, point_step, off_x, off_y, off_z, c->g_raw.as<uint32_t>(), d_kept);
+  c->mark("bin");
+  const int R = static_cast<int>(p->inflation_radius / p->grid_resolution);
+  if (s == AOS_OK) s = launch_inflate(c, c->g_raw.as<uint32_t>(), c->g_infl.as<uint32_t>(), c->g_occ.as<uint32_t>(), P.w, P.h, R);
+  c->mark("inflate");
+  if (s == AOS_OK) s = launch_open(c, c->g_infl.as<uint32_t>(), c->g_open.as<uint32_t>(), P.w, P.h);
+  c->band_gh = 0;  // the launchers read the band geometry only while a band call is running
   if (s != AOS_OK) return s;
-
-  c->mark("frame");
-  s = run_clusters(c, P, c->g_skel.as<uint32_t>(), static_cast<float>(p->cluster_min_length));
-  if (s != AOS_OK) return s;
-  c->mark("cluster_tail");
-
-  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag + 32, d_kept, 8, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_open.p, gbytes, cudaMemcpyDeviceToDevice, st));
+  c->mark("open");
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-  c->summary.info = gi;
-  c->summary.n_clusters = c->n_clusters;
-  c->summary.n_rows = static_cast<int32_t>(c->h_rows.size());
-  c->summary.thinning_launches = launches;
-  c->summary.thinning_subiters = subiters;
-  memcpy(&c->summary.n_points_in, c->h_flag + 32, 8);
-  c->have_seed = true;
+  c->band_thin_launches = 0;
+  c->have_band = true;
   return AOS_OK;
+}
+
+aos_status aos_band_thin_launch(aos_ctx *c, int32_t *deleted) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_band) {
+    set_error(c, "aos_band_raster has not completed");
+    return AOS_ERR_STATE;
+  }
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  const SeedDeviceParams &P = c->band_P;
+  int *d_count = c->misc.as<int>() + 64;
+  aos_status s = launch_thin_once(c, c->g_skel.as<uint32_t>(), c->g_scratch.as<uint32_t>(), P.w, P.h, c->band_y_off,
+                                  c->band_gi.height, c->band_cnt_r0, c->band_cnt_r1, d_count);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_scratch.p, (size_t)P.pitch * P.h * 4, cudaMemcpyDeviceToDevice, c->stream));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  ++c->band_thin_launches;
+  if (deleted) *deleted = c->h_flag[0] != 0;
+  return AOS_OK;
+}
+
+aos_status aos_band_grid_device(aos_ctx *c, aos_grid_id which, uint32_t **bits, int32_t *pitch_words, int32_t *local_rows) {
+  if (!c || !bits) return AOS_ERR_INVALID;
+  if (!c->have_band) return AOS_ERR_STATE;
+  AOS_REQUIRE(c, which >= AOS_GRID_RAW && which <= AOS_GRID_SKELETON, "grid not available in band mode");
+  *bits = grid_buf(c, which)->as<uint32_t>();
+  if (pitch_words) *pitch_words = c->band_P.pitch;
+  if (local_rows) *local_rows = c->band_P.h;
+  return AOS_OK;
+}
+
+aos_status aos_seed_stage_tail(aos_ctx *c, const aos_seed_params *p, const uint32_t *skeleton_bits, const uint32_t *occupancy_bits) {
+  if (!c || !skeleton_bits) return AOS_ERR_INVALID;
+  aos_status s = check_params(c, p);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->have_seed = false;
+  c->have_seeds = false;
+  const int launches = c->have_band ? c->band_thin_launches : 0;
+  c->have_band = false;
+  c->band_gh = 0;
+  aos_grid_info gi;
+  s = fill_device_params(c, p, &gi, &c->P);
+  if (s != AOS_OK) return s;
+  const SeedDeviceParams &P = c->P;
+  const size_t gbytes = (size_t)P.pitch * P.h * 4;
+  // the inputs may alias this context's own (smaller, local) buffers: stage them before the buffers are regrown
+  DevBuf *outs[] = {&c->g_framed, &c->g_scratch, &c->cc_mask};
+  for (DevBuf *g : outs) AOS_CUDA_OK(c, g->reserve(gbytes));
+  AOS_CUDA_OK(c, c->misc.reserve(4096));
+  cudaStream_t st = c->stream;
+  c->marks.clear();
+  c->mark("start");
+  if (skeleton_bits != c->g_skel.as<uint32_t>()) {
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_scratch.p, skeleton_bits, gbytes, cudaMemcpyDeviceToDevice, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    AOS_CUDA_OK(c, c->g_skel.reserve(gbytes));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_scratch.p, gbytes, cudaMemcpyDeviceToDevice, st));
+  }
+  if (occupancy_bits && occupancy_bits != c->g_occ.as<uint32_t>()) {
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_scratch.p, occupancy_bits, gbytes, cudaMemcpyDeviceToDevice, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    AOS_CUDA_OK(c, c->g_occ.reserve(gbytes));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_occ.p, c->g_scratch.p, gbytes, cudaMemcpyDeviceToDevice, st));
+  }
+  c->partial_grids = true;
+  c->have_occ = occupancy_bits != nullptr;
+  c->mark("grids_in");
+  return seed_tail(c, p, gi, launches, launches * kThinSubIters, nullptr);
 }
 
 aos_status aos_seed_summary_get(aos_ctx *c, aos_seed_summary *out) {
@@ -316,6 +501,11 @@ aos_status aos_get_grid(aos_ctx *c, aos_grid_id which, aos_grid_fmt fmt, void *d
   }
   DevBuf *g = grid_buf(c, which);
   AOS_REQUIRE(c, g != nullptr, "unknown grid id");
+  if (c->partial_grids && !(which == AOS_GRID_SKELETON || which == AOS_GRID_SKELETON_FRAMED ||
+                            (which == AOS_GRID_OCCUPANCY && c->have_occ))) {
+    set_error(c, "this grid was not produced on this context (aos_seed_stage_tail)");
+    return AOS_ERR_STATE;
+  }
   const SeedDeviceParams &P = c->P;
   cudaStream_t st = c->stream;
   if (fmt == AOS_FMT_BITS) {

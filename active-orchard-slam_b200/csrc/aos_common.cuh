@@ -26,6 +26,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr int kTileBoxW = 36;
 constexpr int kTileOwnW = 28;
 constexpr int kTileLane0 = 2;
+constexpr int kThinSubIters = 8;  // sub-iterations per thinning launch == halo rows a row band refreshes per launch
 
 // ---- error plumbing: nothing throws across the C boundary -------------------------------------
 struct Ctx;
@@ -185,6 +186,7 @@ struct SeedDeviceParams {
   float res;
   double ox, oy;  // origin = (double)minx, (double)miny
   int w, h, pitch;
+  int y_off, gh;  // row-band mode: global row of local row 0 and global height (0, h otherwise)
   int n_excl;
   float excl[kMaxExcl * 3];
   int n_poly;
@@ -198,6 +200,8 @@ aos_status launch_bin(Ctx *c, const SeedDeviceParams &P, const void *points, siz
 aos_status launch_inflate(Ctx *c, const uint32_t *in, uint32_t *out, uint32_t *out_border, int w, int h, int R);
 aos_status launch_open(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h);
 aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters);
+aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, int h, int y_off, int gh, int cnt_r0,
+                            int cnt_r1, int *d_count);
 aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h, int gx0, int gy0, int gx1, int gy1,
                         int thickness);
 aos_status launch_pack(Ctx *c, const int8_t *src, uint32_t *dst, int w, int h);
@@ -277,6 +281,15 @@ struct Ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool own_stream = false;
   std::string err;
+
+  // row-band mode (aos_band_*): global row of local row 0 / global height; band_gh == 0 means not banded
+  int band_y_off = 0, band_gh = 0, band_cnt_r0 = 0, band_cnt_r1 = 0;
+  aos_band band{};
+  bool have_band = false;
+  SeedDeviceParams band_P{};
+  aos_grid_info band_gi{};
+  int band_thin_launches = 0;
+  bool partial_grids = false, have_occ = false;  // after aos_seed_stage_tail only some grids exist
 
   // seed stage state
   bool have_seed = false;

@@ -261,22 +261,46 @@ void host_rows_info(const std::vector<aos_tree_row> &rows, std::vector<double> *
 }
 
 // voronoiSeedsCallback, gvd:84-128: greedy leader clustering at 0.5 m (<=), centroid in index order.
+// Same answers as the reference's O(S^2) scan; the neighbour candidates come from a flat open-addressing grid
+// (cell = merge distance) instead.
 void host_merge_seeds(const double *seeds, int n, std::vector<double> *out) {
   const double merge_distance = 0.5;
   out->clear();
-  std::vector<char> used((size_t)n, 0);
-  // uniform hash over all raw seeds (cell = merge distance)
-  std::unordered_map<unsigned long long, std::vector<int>> cells;
+  if (n <= 0) return;
+  size_t cap = 64;
+  while (cap < (size_t)n * 2) cap <<= 1;
+  const size_t mask = cap - 1;
+  std::vector<unsigned long long> keys(cap, ~0ull);
+  std::vector<int> head(cap, -1), next((size_t)n, -1);
+  std::vector<char> used((size_t)n, 0), finite((size_t)n, 1);
+  auto cell = [&](double v) { return (long long)floor(v / merge_distance); };
   auto key = [](long long cx, long long cy) {
     return ((unsigned long long)(cx + (1ll << 30)) << 32) ^ (unsigned long long)(cy + (1ll << 30));
   };
-  std::vector<char> finite((size_t)n, 1);
+  auto slot_of = [&](unsigned long long k, bool insert) -> long long {
+    unsigned long long h = k;
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    size_t i = (size_t)h & mask;
+    for (;;) {
+      if (keys[i] == k) return (long long)i;
+      if (keys[i] == ~0ull) {
+        if (!insert) return -1;
+        keys[i] = k;
+        return (long long)i;
+      }
+      i = (i + 1) & mask;
+    }
+  };
   for (int i = 0; i < n; ++i) {
     if (!std::isfinite(seeds[2 * i]) || !std::isfinite(seeds[2 * i + 1])) {
       finite[i] = 0;  // a non-finite seed never merges with anything (norm is NaN/inf) and is dropped at gvd:266
       continue;
     }
-    cells[key((long long)floor(seeds[2 * i] / merge_distance), (long long)floor(seeds[2 * i + 1] / merge_distance))].push_back(i);
+    long long s = slot_of(key(cell(seeds[2 * i]), cell(seeds[2 * i + 1])), true);
+    next[i] = head[s];
+    head[s] = i;
   }
   std::vector<int> members;
   for (int i = 0; i < n; ++i) {
@@ -284,12 +308,12 @@ void host_merge_seeds(const double *seeds, int n, std::vector<double> *out) {
     used[i] = 1;
     if (!finite[i]) continue;  // its own cluster, filtered out by processGraph (gvd:266-270)
     members.clear();
-    long long cx = (long long)floor(seeds[2 * i] / merge_distance), cy = (long long)floor(seeds[2 * i + 1] / merge_distance);
+    const long long cx = cell(seeds[2 * i]), cy = cell(seeds[2 * i + 1]);
     for (long long dy = -1; dy <= 1; ++dy)
       for (long long dx = -1; dx <= 1; ++dx) {
-        auto it = cells.find(key(cx + dx, cy + dy));
-        if (it == cells.end()) continue;
-        for (int j : it->second) {
+        long long s = slot_of(key(cx + dx, cy + dy), false);
+        if (s < 0) continue;
+        for (int j = head[s]; j >= 0; j = next[j]) {
           if (j <= i || used[j]) continue;
           double ex = seeds[2 * i] - seeds[2 * j], ey = seeds[2 * i + 1] - seeds[2 * j + 1];
           if (sqrt(ex * ex + ey * ey) <= merge_distance) members.push_back(j);

@@ -36,7 +36,9 @@ __device__ __forceinline__ int cell_index(double q, double res, double inv_res) 
 __device__ __forceinline__ void scatter_point(const SeedDeviceParams &P, double inv_res, float x, float y, uint32_t *bits) {
   int gx = cell_index((double)x - P.ox, (double)P.res, inv_res);
   int gy = cell_index((double)y - P.oy, (double)P.res, inv_res);
-  if (gx >= 0 && gx < P.w && gy >= 0 && gy < P.h) {
+  if (gx >= 0 && gx < P.w && gy >= 0 && gy < P.gh) {
+    gy -= P.y_off;  // row-band mode: rows outside this band's local grid belong to another GPU
+    if (gy < 0 || gy >= P.h) return;
     uint32_t *wp = bits + (size_t)gy * P.pitch + (gx >> 5);
     uint32_t m = 1u << (gx & 31);
     // fire-and-forget reduction at the L2 (SASS RED.OR): no dependent read on the warp's critical path; with a

@@ -19,6 +19,7 @@ constexpr int kMaxR = 64;
 
 struct InflateParams {
   int w, h, pitch, R;
+  int y_off, gh;  // global row of local row 0, global height (frame of markBoundariesAsOccupied)
   unsigned char delta[kMaxR + 1];  // delta[d] = hw[d-1]-hw[d] for d>=1
 };
 
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kInfThreads) inflate_kernel(const __grid_const
       acc &= vmask;
       size_t o = (size_t)y * P.pitch + cw;
       out[o] = acc;
-      if (out_border) out_border[o] = (acc | frame_mask(cw, y, P.w, P.h, 5)) & vmask;
+      if (out_border) out_border[o] = (acc | frame_mask(cw, y + P.y_off, P.w, P.gh, 5)) & vmask;
     }
   }
 }
@@ -110,6 +111,8 @@ aos_status launch_inflate(Ctx *c, const uint32_t *in, uint32_t *out, uint32_t *o
   P.h = h;
   P.pitch = pitch_words_for(w);
   P.R = R;
+  P.y_off = c->band_gh ? c->band_y_off : 0;
+  P.gh = c->band_gh ? c->band_gh : h;
   int prev = R;  // hw[0] = R
   for (int d = 1; d <= R; ++d) {
     int k = 0;
@@ -139,7 +142,7 @@ constexpr int kOpenRows = 64;
 constexpr int kOpenThreads = 256;
 
 __global__ void __launch_bounds__(kOpenThreads) open_kernel(const __grid_constant__ CUtensorMap tmap, int w, int h,
-                                                            int pitch, uint32_t *__restrict__ out) {
+                                                            int pitch, int y_off, int gh, uint32_t *__restrict__ out) {
   __shared__ __align__(128) uint32_t tile[(kOpenRows + 4) * kTileBoxW];
   __shared__ __align__(8) uint64_t bar;
   const int own0 = blockIdx.x * kTileOwnW;
@@ -167,11 +170,12 @@ __global__ void __launch_bounds__(kOpenThreads) open_kernel(const __grid_constan
 
   // eroded row at image row y (tile row ty = y - y0 + 2)
   auto eroded = [&](int y) -> uint32_t {
-    if (y < 0 || y >= h) return 0u;  // eroded image does not exist outside: adds nothing to the dilation
+    // eroded image does not exist outside the (global) image: adds nothing to the dilation
+    if (y < 0 || y >= h || y + y_off < 0 || y + y_off >= gh) return 0u;
     int ty = y - y0 + 2;
     uint32_t C = tl[ty * kTileBoxW];
-    uint32_t N = (y - 1 < 0) ? 0xffffffffu : tl[(ty - 1) * kTileBoxW];
-    uint32_t S = (y + 1 >= h) ? 0xffffffffu : tl[(ty + 1) * kTileBoxW];
+    uint32_t N = (y + y_off - 1 < 0) ? 0xffffffffu : tl[(ty - 1) * kTileBoxW];
+    uint32_t S = (y + y_off + 1 >= gh) ? 0xffffffffu : tl[(ty + 1) * kTileBoxW];
     uint32_t l = __shfl_up_sync(0xffffffffu, C, 1), r = __shfl_down_sync(0xffffffffu, C, 1);
     uint32_t Wn = __funnelshift_l(l, C, 1) | first_bit;  // value of the x-1 neighbour at x
     uint32_t En = __funnelshift_r(C, r, 1) | last_bit;   // value of the x+1 neighbour at x
@@ -198,7 +202,8 @@ aos_status launch_open(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h) 
   }
   int words_used = (w + 31) >> 5;
   dim3 grid((words_used + kTileOwnW - 1) / kTileOwnW, (h + kOpenRows - 1) / kOpenRows);
-  open_kernel<<<grid, kOpenThreads, 0, c->stream>>>(tmap, w, h, pitch, out);
+  open_kernel<<<grid, kOpenThreads, 0, c->stream>>>(tmap, w, h, pitch, c->band_gh ? c->band_y_off : 0, c->band_gh ? c->band_gh : h,
+                                                     out);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;

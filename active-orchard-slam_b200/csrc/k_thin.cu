@@ -19,7 +19,7 @@
 
 namespace aos {
 
-constexpr int kSub = 8;                       // sub-iterations per launch (even)
+constexpr int kSub = kThinSubIters;           // sub-iterations per launch (even)
 constexpr int kThinOwn = 112;                 // owned rows per CTA
 constexpr int kThinBox = kThinOwn + 2 * kSub; // 128 tile rows
 constexpr int kThinThreads = 256;
@@ -52,6 +52,8 @@ __device__ __forceinline__ uint32_t zs_delete_mask(uint32_t C, uint32_t p2, uint
 
 struct ThinParams {
   int w, h, pitch;
+  int y_off, gh;       // row-band mode: global row of local row 0, global height
+  int cnt_r0, cnt_r1;  // local rows whose deletions count towards convergence (the band without its halo)
 };
 
 __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -115,9 +117,9 @@ __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constan
           const int y = y0 + r;
           uint32_t del = zs_delete_mask(cC, nC, nE, cE, sE, sC, sW, cW, nW, iter);
           del &= xmask;
-          if (y <= 0 || y >= P.h - 1) del = 0;
+          if (y + P.y_off <= 0 || y + P.y_off >= P.gh - 1) del = 0;
           res = cC & ~del;
-          if (lane_owned && r >= kSub && r < kSub + kThinOwn) deleted_owned |= (del != 0);
+          if (lane_owned && r >= kSub && r < kSub + kThinOwn && y >= P.cnt_r0 && y < P.cnt_r1) deleted_owned |= (del != 0);
         }
       }
       out[r * kTileBoxW + sl] = res;
@@ -139,9 +141,29 @@ __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constan
   if (threadIdx.x == 0 && s_deleted) atomicAdd(my_count, 1);
 }
 
+// One launch (kSub sub-iterations) src -> dst on a LOCAL grid of a row band (aos_band_thin_launch): the caller
+// refreshes the kSub halo rows next to the band from the neighbouring GPUs between launches.  d_count receives the
+// number of CTAs that deleted something inside rows [cnt_r0, cnt_r1).
+aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, int h, int y_off, int gh, int cnt_r0,
+                            int cnt_r1, int *d_count) {
+  ThinParams P{w, h, pitch_words_for(w), y_off, gh, cnt_r0, cnt_r1};
+  CUtensorMap map_src;
+  if (!make_bitgrid_tmap(&map_src, src, P.pitch, h, kTileBoxW, kThinBox)) {
+    set_error(c, "cuTensorMapEncodeTiled failed (thin)");
+    return AOS_ERR_CUDA;
+  }
+  int words_used = (w + 31) >> 5;
+  dim3 grid((words_used + kTileOwnW - 1) / kTileOwnW, (h + kThinOwn - 1) / kThinOwn);
+  AOS_CUDA_OK(c, cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
+  thin_kernel<<<grid, kThinThreads, 0, c->stream>>>(map_src, P, dst, nullptr, d_count);
+  ++c->launches;
+  AOS_CUDA_OK(c, cudaGetLastError());
+  return AOS_OK;
+}
+
 // img holds the input; on return *result_in_scratch says which of (img, scratch) holds the skeleton.
 aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters) {
-  ThinParams P{w, h, pitch_words_for(w)};
+  ThinParams P{w, h, pitch_words_for(w), 0, h, 0, h};
   CUtensorMap map_img, map_scr;
   if (!make_bitgrid_tmap(&map_img, img, P.pitch, h, kTileBoxW, kThinBox) ||
       !make_bitgrid_tmap(&map_scr, scratch, P.pitch, h, kTileBoxW, kThinBox)) {

@@ -224,6 +224,36 @@ AOS_API aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, d
                                       int32_t *facet_off, int32_t off_capacity, int32_t *n_facets,
                                       int32_t *n_points);
 
+/* ---- row-band sharding of the raster stages (BASELINE.json config 4: one huge grid over several GPUs) --------
+ * Each GPU (one process, one context) owns the image rows [row0, row0 + rows) of the global grid and keeps
+ * halo_lo / halo_hi extra rows below / above them (0 at the global border).  The halo must cover the stencil
+ * reach of inflation + opening + one thinning launch: aos_band_halo_rows(params).  The caller buckets the cloud so
+ * that every point whose cell row lies inside the local rows is given to this GPU (points outside are ignored, so
+ * handing over a superset -- even the whole cloud -- is correct), runs aos_band_raster, then loops
+ *     exchange the AOS_BAND_THIN_HALO rows next to each band edge with the neighbour (NVLink P2P / NCCL send-recv)
+ *     aos_band_thin_launch  -> all-reduce(OR) of `deleted`
+ * until no band deleted anything; the bands of AOS_GRID_SKELETON / AOS_GRID_OCCUPANCY are then gathered on one
+ * GPU and aos_seed_stage_tail finishes the seed stage there (clusters, rows; then seeds and graph as usual).
+ * Results are bit-identical to aos_seed_stage on one GPU (tests/test_bands_*.py). */
+typedef struct {
+  int32_t row0, rows;        /* owned rows of the global grid */
+  int32_t halo_lo, halo_hi;  /* extra rows kept below row0 / above row0+rows */
+} aos_band;
+#define AOS_BAND_THIN_HALO 8  /* rows refreshed from the neighbour before every aos_band_thin_launch */
+AOS_API int32_t aos_band_halo_rows(const aos_seed_params *p);
+AOS_API aos_status aos_band_raster(aos_ctx *ctx, const aos_seed_params *p, const aos_band *band, const void *points,
+                                   size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y,
+                                   uint32_t off_z, aos_mem points_mem);
+AOS_API aos_status aos_band_thin_launch(aos_ctx *ctx, int32_t *deleted);
+/* Device pointer of a LOCAL grid (AOS_GRID_RAW .. AOS_GRID_SKELETON): local row r is global row row0 - halo_lo + r. */
+AOS_API aos_status aos_band_grid_device(aos_ctx *ctx, aos_grid_id which, uint32_t **bits, int32_t *pitch_words,
+                                        int32_t *local_rows);
+/* Finish the seed stage from gathered full-size bit grids in device memory (pitch aos_bits_pitch_words(width)):
+ * skeleton = thinned image (un-framed); occupancy = inflated + frame (may be NULL).  Afterwards the context
+ * behaves as after aos_seed_stage, except that AOS_GRID_RAW / INFLATED / OPENED are not available. */
+AOS_API aos_status aos_seed_stage_tail(aos_ctx *ctx, const aos_seed_params *p, const uint32_t *skeleton_bits,
+                                       const uint32_t *occupancy_bits);
+
 /* Kernels launched by this context since aos_create (bench.py's gpu_launches). */
 AOS_API aos_status aos_get_launch_count(aos_ctx *ctx, int64_t *out);
 
