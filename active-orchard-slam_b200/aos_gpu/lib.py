@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
     "aos_gvd_stage", "aos_get_graph", "aos_map_to_graph", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
-    "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
+    "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
 
 
@@ -138,6 +138,9 @@ def load() -> C.CDLL:
     L.aos_get_graph.argtypes = [vp, C.POINTER(CGvdGraph)]
     L.aos_map_to_graph.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.aos_set_subdiv_outer_factor.argtypes = [C.c_float]
+    L.aos_set_clearance.argtypes = [vp, C.c_int]
+    L.aos_edt_bits.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.aos_inflate_bits_edt.argtypes = [vp, vp, vp, i32, i32, i32]
     L.aos_band_halo_rows.argtypes = [C.POINTER(CSeedParams)]
     L.aos_band_raster.argtypes = [vp, C.POINTER(CSeedParams), C.POINTER(CBand), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_uint32, C.c_int]
@@ -408,6 +411,9 @@ class Context:
                     corner_points=arr(g.corner_points, 8 * g.n_rows, np.float64).reshape(-1, 4, 2),
                     n_merged_seeds=g.n_merged_seeds, n_voronoi_edges=g.n_voronoi_edges,
                     n_boundary_points=g.n_boundary_points)
+
+    def set_clearance(self, on: bool):
+        self._check(self.L.aos_set_clearance(self.h, int(on)), "aos_set_clearance")
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -114,19 +114,33 @@ def make_orchard(spec: OrchardSpec) -> np.ndarray:
     return pts
 
 
-def make_orchard_torch(spec: OrchardSpec, device, chunk: int = 1 << 24):
+def make_orchard_torch(spec: OrchardSpec, device, chunk: int = 1 << 24, y_range=None):
     """Same recipe generated on `device` with torch (for the 200 M-point C3/C4 clouds).
-    Not bit-identical to make_orchard(); full-size parity goes through size-independent properties."""
+    Not bit-identical to make_orchard(); full-size parity goes through size-independent properties.
+    y_range=(lo, hi): only the share of the cloud whose trees / clutter fall into that strip (row-band sharding:
+    every GPU generates the points of its own rows; the tree layout is the same global one)."""
     import torch
 
     g = torch.Generator(device=device)
-    g.manual_seed(spec.seed)
+    g.manual_seed(spec.seed if y_range is None else spec.seed * 1000003 + int(y_range[0] * 16))
     rng = np.random.default_rng(spec.seed)
-    centres = torch.from_numpy(tree_centres(spec, rng)).to(device=device, dtype=torch.float32)
+    all_centres = tree_centres(spec, rng)
     n = spec.n_points
-    out = torch.empty((n, 4), dtype=torch.float32, device=device)
     n_clutter = int(n * spec.clutter_frac)
     n_tree_pts = n - n_clutter
+    cy0, cy1 = spec.origin_y - 1.0, spec.origin_y + spec.extent_y + 1.0
+    if y_range is not None:
+        lo, hi = y_range
+        sel = (all_centres[:, 1] >= lo - spec.tree_radius) & (all_centres[:, 1] <= hi + spec.tree_radius)
+        n_tree_pts = int(round(n_tree_pts * sel.sum() / max(len(all_centres), 1)))
+        all_centres = all_centres[sel]
+        cy0, cy1 = max(cy0, lo), min(cy1, hi)
+        n_clutter = int(round(n_clutter * max(cy1 - cy0, 0.0) / (spec.extent_y + 2.0)))
+        n = n_tree_pts + n_clutter
+    if len(all_centres) == 0:
+        n_tree_pts, n = 0, n_clutter
+    centres = torch.from_numpy(all_centres).to(device=device, dtype=torch.float32)
+    out = torch.empty((n, 4), dtype=torch.float32, device=device)
     for s in range(0, n_tree_pts, chunk):
         m = min(chunk, n_tree_pts - s)
         idx = torch.randint(0, centres.shape[0], (m,), generator=g, device=device)
@@ -138,7 +152,7 @@ def make_orchard_torch(spec: OrchardSpec, device, chunk: int = 1 << 24):
     for s in range(n_tree_pts, n, chunk):
         m = min(chunk, n - s)
         out[s:s + m, 0] = spec.origin_x - 1.0 + (spec.extent_x + 2.0) * torch.rand(m, generator=g, device=device)
-        out[s:s + m, 1] = spec.origin_y - 1.0 + (spec.extent_y + 2.0) * torch.rand(m, generator=g, device=device)
+        out[s:s + m, 1] = cy0 + (cy1 - cy0) * torch.rand(m, generator=g, device=device)
         zc = torch.rand(m, generator=g, device=device)
         out[s:s + m, 2] = torch.where(zc < 0.5, -1.5 + 2.0 * zc, 0.6 + 4.8 * (zc - 0.5))
     out[:, 3] = 1.0

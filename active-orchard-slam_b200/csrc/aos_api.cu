@@ -112,7 +112,7 @@ void aos_destroy(aos_ctx *c) {
   DevBuf *bufs[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch,
                     &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
                     &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf,
-                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2};
+                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2, &c->edt_buf, &c->edt_out};
   for (DevBuf *b : bufs) b->release();
   c->graph.release();
   c->pin_facet_xy.release();
@@ -660,6 +660,36 @@ aos_status aos_thin_bits(aos_ctx *c, uint32_t *inout, int32_t w, int32_t h, int3
   aos_status r = launch_thin(c, inout, c->g_scratch.as<uint32_t>(), w, h, &l, &s);
   if (launches) *launches = l;
   if (subiters) *subiters = s;
+  if (r != AOS_OK) return r;
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_set_clearance(aos_ctx *c, int enabled) {
+  if (!c) return AOS_ERR_INVALID;
+  c->clearance = enabled != 0;
+  return AOS_OK;
+}
+
+aos_status aos_edt_bits(aos_ctx *c, const uint32_t *bits, int32_t w, int32_t h, uint32_t *nearest_xy, int32_t *dist2) {
+  if (!c || !bits || !nearest_xy) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  aos_status r = launch_edt(c, bits, w, h, nearest_xy, dist2);
+  if (r != AOS_OK) return r;
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_inflate_bits_edt(aos_ctx *c, const uint32_t *in, uint32_t *out, int32_t w, int32_t h, int32_t radius_cells) {
+  if (!c || !in || !out || radius_cells < 0) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  const size_t cells = (size_t)w * h;
+  AOS_CUDA_OK(c, c->edt_out.reserve(cells * 8 + 1024));
+  uint32_t *nearest = c->edt_out.as<uint32_t>();
+  int32_t *d2 = reinterpret_cast<int32_t *>(nearest + cells);
+  aos_status r = launch_edt(c, in, w, h, nearest, d2);
+  if (r != AOS_OK) return r;
+  r = launch_edt_threshold(c, d2, w, h, radius_cells * radius_cells, out);
   if (r != AOS_OK) return r;
   AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return AOS_OK;

@@ -239,6 +239,38 @@ __device__ bool warp_segment_hits(const GridView &g, double2 s, double2 e, int l
   return false;
 }
 
+// Opt-in edge clearance (the reference publishes 0.0f, gvd:856,890): minimum over the same
+// samples of the exact distance to the nearest skeleton cell (k_edt.cu), in metres.  Samples outside the grid
+// are skipped; an edge without any sample inside the grid gets FLT_MAX.
+__global__ void edge_clearance_kernel(const int32_t *__restrict__ edges, int n_edges, const double2 *__restrict__ nodes,
+                                      GridView g, const int32_t *__restrict__ dist2, float *__restrict__ clearances) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_edges; e += warps) {
+    const double2 s = nodes[edges[2 * (size_t)e]], t = nodes[edges[2 * (size_t)e + 1]];
+    const double resolution = (double)g.res;
+    const double ex = t.x - s.x, ey = t.y - s.y;
+    const double z = ex * ex + ey * ey;
+    const double edge_length = sqrt(z);
+    int best = 0x7fffffff;
+    if (edge_length >= 1e-6 && edge_length / (resolution * 0.5) < 2147483648.0) {
+      const int num_samples = (int)(edge_length / (resolution * 0.5)) + 1;
+      const double q = sqrt(z), dx = ex / q, dy = ey / q;
+      for (int i = lane; i <= num_samples; i += 32) {
+        double tt = (i == num_samples) ? 1.0 : ((double)i / (double)num_samples);
+        double px = s.x + (tt * dx) * edge_length, py = s.y + (tt * dy) * edge_length;
+        double fx = (px - g.ox) / resolution, fy = (py - g.oy) / resolution;
+        if (fx > -1.0 && fx < (double)g.w && fy > -1.0 && fy < (double)g.h) {
+          int mx = (int)fx, my = (int)fy;
+          if (mx >= 0 && mx < g.w && my >= 0 && my < g.h) best = min(best, dist2[(size_t)my * g.w + mx]);
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) clearances[e] = best == 0x7fffffff ? FLT_MAX : (float)(sqrt((double)best) * resolution);
+  }
+}
+
 // buildGraphFromBoundaryPoints part 1 (gvd:806-859): every Voronoi edge -> (nearest node of start, of end)
 __global__ void edge_key_kernel(const int *__restrict__ nn, const int *__restrict__ enext, int n_edges, DevHash H) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
@@ -874,6 +906,17 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
     N = c->h_flag[0];
     NE = n_rec > 0 ? c->h_flag[1] : 0;
+  }
+  if (c->clearance && NE > 0) {  // opt-in: exact EDT of the framed skeleton, then one warp per published edge
+    const size_t cells = (size_t)in.w * in.h;
+    AOS_CUDA_OK(c, c->edt_out.reserve(cells * 8 + 1024));
+    uint32_t *d_near = c->edt_out.as<uint32_t>();
+    int32_t *d_d2 = reinterpret_cast<int32_t *>(d_near + cells);
+    s = launch_edt(c, in.skel_bits, in.w, in.h, d_near, d_d2);
+    if (s != AOS_OK) return s;
+    edge_clearance_kernel<<<blocks_for((size_t)NE * 32), 256, 0, st>>>(d_edges, NE, d_cnodes, gv, d_d2, d_clr);
+    ++c->launches;
+    AOS_CUDA_OK(c, cudaGetLastError());
   }
   c->mark("gvd_crop");
 

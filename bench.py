@@ -248,6 +248,105 @@ def bench_ours(args):
     return line
 
 
+def bench_bands(args):
+    """BASELINE config 4: ONE grid row-band sharded over the ranks (strong scaling of the raster stages; clusters,
+    seeds and graph finish on rank 0).  Not the default: `--shard bands`, normally with --workload C4."""
+    import torch
+    import torch.distributed as dist
+
+    from aos_gpu import bands
+    from aos_gpu import dist as adist
+    from aos_gpu import lib, synth
+
+    rank, world, local = adist.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spec = synth.config(args.workload, seed=0, n_points=args.points)
+    params = make_params(lib, spec)
+    gi = lib.grid_geometry(params)
+    ctx = lib.Context(local)
+    band = bands.band_for(gi.height, world, rank, ctx.band_halo_rows(params))
+    res = float(np.float32(spec.grid_resolution))
+    ylo = gi.origin_y + band.first_global_row * res - 2 * res
+    yhi = gi.origin_y + (band.first_global_row + band.local_rows) * res + 2 * res
+    pts = synth.make_orchard_torch(spec, dev, y_range=(ylo, yhi)) if world > 1 else synth.make_orchard_torch(spec, dev)
+    torch.cuda.synchronize()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one():
+        t = {}
+        t0 = time.perf_counter()
+        ctx.band_raster(params, band, pts)
+        torch.cuda.synchronize()
+        t["raster"] = time.perf_counter() - t0
+        be = bands.LibBackend(ctx)
+        t0 = time.perf_counter()
+        launches = bands.run_thinning(be, band, rank, world, dist)
+        torch.cuda.synchronize()
+        t["thin+halo"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        skel = bands.gather_rows(be.skeleton(), band, gi.height, rank, world, dist)
+        occ = bands.gather_rows(be.grid(lib.GRID_OCCUPANCY), band, gi.height, rank, world, dist)
+        torch.cuda.synchronize()
+        t["gather"] = time.perf_counter() - t0
+        g = None
+        if rank == 0:
+            t0 = time.perf_counter()
+            ctx.seed_stage_tail(params, skel, occ)
+            seeds, counts, rows_info = ctx.select_seeds()
+            g = ctx.gvd_stage(seeds, rows_info) if len(seeds) else None
+            t["tail_rank0"] = time.perf_counter() - t0
+        return t, launches, g
+
+    for _ in range(args.warmup):
+        one()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = {}
+    with ClockSampler(local) as clk:
+        ev0.record()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            t, launches, g = one()
+            for k, v in t.items():
+                acc[k] = acc.get(k, 0.0) + v * 1e3 / args.steps
+        sync_all()
+        ev1.record()
+        ev1.synchronize()
+    ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3)
+    ms, _ = adist.reduce_stats(ms, 0, device=dev)
+    n_local = torch.tensor([pts.shape[0]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_local)
+    cells = gi.width * gi.height
+    if rank == 0:
+        raster_ms = acc.get("raster", 0) + acc.get("thin+halo", 0) + acc.get("gather", 0)
+        line = {"metric": METRIC, "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: ONE {gi.width}x{gi.height} grid @ {spec.grid_resolution} m row-band "
+                                       f"sharded over {world} GPU(s), {int(n_local.item())} points in total (halo overlap "
+                                       f"included), halo {ctx.band_halo_rows(params)} rows, NCCL send/recv of 8 rows per "
+                                       "neighbour and thinning launch",
+                           "shard": "bands", "thin_launches": launches,
+                           "graph": None if g is None else {"nodes": int(g["n_nodes"]), "edges": int(g["n_edges"])}},
+                "stages_ms_rank0": {k: round(v, 3) for k, v in acc.items()},
+                "raster_stages": {"ms": round(raster_ms, 3), "value": round(cells / (raster_ms * 1e-3) / 1e6, 1), "unit": UNIT},
+                "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's algorithms) on a bounded crop of the workload
 # ---------------------------------------------------------------------------------------------------
@@ -351,11 +450,15 @@ def main():
     ap.add_argument("--points", type=int, default=None, help="override the workload's point count")
     ap.add_argument("--maps-in-flight", type=int, default=0,
                     help="independent maps processed concurrently per GPU (0 = min(8, host cores / ranks))")
+    ap.add_argument("--shard", default="maps", choices=["maps", "bands"],
+                    help="maps: independent maps per GPU (default, weak scaling); bands: one grid row-band sharded")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
+    elif args.shard == "bands":
+        bench_bands(args)
     else:
         bench_ours(args)
 

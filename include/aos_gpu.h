@@ -202,6 +202,12 @@ AOS_API aos_status aos_gvd_stage(aos_ctx *ctx, const double *seeds_xy, int32_t n
                                  int32_t n_rows, const int8_t *skeleton, const aos_grid_info *info);
 AOS_API aos_status aos_get_graph(aos_ctx *ctx, aos_gvd_graph *out);
 
+/* Opt-in (default off): fill GvdGraph.edge_clearances with the minimum, over the samples of
+ * edgePassesThroughOccupiedPixels (gvd:320-359), of the exact Euclidean distance to the nearest occupied cell of
+ * the framed skeleton, in metres.  The reference declares the field (msg/GvdGraph.msg:58) but publishes 0.0f
+ * (gvd:856,890), so with this switched on the array is no longer bit-identical to the reference's. */
+AOS_API aos_status aos_set_clearance(aos_ctx *ctx, int enabled);
+
 /* The whole path in one call: aos_seed_stage, aos_select_seeds, aos_gvd_stage on the context's own grids. */
 AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, const void *points, size_t n_points,
                                     uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
@@ -264,6 +270,15 @@ AOS_API aos_status aos_inflate_bits(aos_ctx *ctx, const uint32_t *in, uint32_t *
 AOS_API aos_status aos_open_bits(aos_ctx *ctx, const uint32_t *in, uint32_t *out, int32_t width, int32_t height);
 AOS_API aos_status aos_thin_bits(aos_ctx *ctx, uint32_t *inout, int32_t width, int32_t height,
                                  int32_t *launches, int32_t *subiters);
+/* Exact Euclidean distance transform of a device bit grid (k_edt.cu): for every cell the nearest set cell as
+ * x | y << 16 (0xFFFFFFFF when the grid is empty) and, if dist2 != NULL, the exact squared distance in cells.
+ * nearest_xy / dist2: device, width*height entries, row-major.  Width and height below 65535. */
+AOS_API aos_status aos_edt_bits(aos_ctx *ctx, const uint32_t *bits, int32_t width, int32_t height, uint32_t *nearest_xy,
+                                int32_t *dist2);
+/* applyInflation (seed_gen:933-967) as the threshold d^2 <= R^2 of that EDT: same result as aos_inflate_bits for
+ * any radius (no 64-cell limit), cost independent of the radius. */
+AOS_API aos_status aos_inflate_bits_edt(aos_ctx *ctx, const uint32_t *in, uint32_t *out, int32_t width, int32_t height,
+                                        int32_t radius_cells);
 AOS_API aos_status aos_pack_int8(aos_ctx *ctx, const int8_t *src, aos_mem src_mem, uint32_t *dst_bits,
                                  int32_t width, int32_t height);
 AOS_API aos_status aos_unpack_int8(aos_ctx *ctx, const uint32_t *src_bits, int8_t *dst, aos_mem dst_mem,
