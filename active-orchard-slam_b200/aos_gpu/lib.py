@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
-    "aos_gvd_stage", "aos_get_graph", "aos_map_to_graph", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
+    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
     "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
 
@@ -135,6 +135,7 @@ def load() -> C.CDLL:
     L.aos_get_rows_info.argtypes = [vp, vp, i32, C.POINTER(i32)]
     L.aos_get_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     L.aos_gvd_stage.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(CGridInfo)]
+    L.aos_gvd_stage_bits.argtypes = [vp, vp, i32, vp, i32, vp, C.c_int, C.POINTER(CGridInfo)]
     L.aos_get_graph.argtypes = [vp, C.POINTER(CGvdGraph)]
     L.aos_map_to_graph.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.aos_set_subdiv_outer_factor.argtypes = [C.c_float]
@@ -376,7 +377,12 @@ class Context:
         /skeletonized_occupancy_grid with info=(resolution, origin_x, origin_y), or None to use this context's."""
         sd = np.ascontiguousarray(seeds, np.float64).reshape(-1, 2)
         rw = np.ascontiguousarray(rows_info, np.float64).reshape(-1, 4)
-        if skeleton is not None:
+        if skeleton is not None and np.asarray(skeleton).dtype == np.uint32:   # AOS_FMT_BITS grid [H, pitch], host
+            sk = np.ascontiguousarray(skeleton, np.uint32)
+            gi = CGridInfo(int(info[3]), sk.shape[0], float(info[0]), float(info[1]), float(info[2]))
+            rc = self.L.aos_gvd_stage_bits(self.h, sd.ctypes.data_as(C.c_void_p), len(sd), rw.ctypes.data_as(C.c_void_p), len(rw),
+                                           sk.ctypes.data_as(C.c_void_p), AOS_MEM_HOST, C.byref(gi))
+        elif skeleton is not None:
             sk = np.ascontiguousarray(skeleton, np.int8)
             gi = CGridInfo(sk.shape[1], sk.shape[0], float(info[0]), float(info[1]), float(info[2]))
             rc = self.L.aos_gvd_stage(self.h, sd.ctypes.data_as(C.c_void_p), len(sd), rw.ctypes.data_as(C.c_void_p), len(rw),

@@ -674,6 +674,8 @@ aos_status aos_set_clearance(aos_ctx *c, int enabled) {
 aos_status aos_edt_bits(aos_ctx *c, const uint32_t *bits, int32_t w, int32_t h, uint32_t *nearest_xy, int32_t *dist2) {
   if (!c || !bits || !nearest_xy) return AOS_ERR_INVALID;
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->marks.clear();
+  c->mark("start");
   aos_status r = launch_edt(c, bits, w, h, nearest_xy, dist2);
   if (r != AOS_OK) return r;
   AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));

@@ -92,8 +92,22 @@ aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, double mi
   return AOS_OK;
 }
 
+static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
+                                 const void *skeleton, bool skeleton_is_bits, aos_mem skeleton_mem, const aos_grid_info *info);
+
 aos_status aos_gvd_stage(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
                          const int8_t *skeleton, const aos_grid_info *info) {
+  return gvd_stage_impl(c, seeds_xy, n_seeds, rows_info, n_rows, skeleton, false, AOS_MEM_HOST, info);
+}
+
+aos_status aos_gvd_stage_bits(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
+                              const uint32_t *skeleton_bits, aos_mem skeleton_mem, const aos_grid_info *info) {
+  if (!skeleton_bits || !info) return AOS_ERR_INVALID;
+  return gvd_stage_impl(c, seeds_xy, n_seeds, rows_info, n_rows, skeleton_bits, true, skeleton_mem, info);
+}
+
+static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
+                                 const void *skeleton, bool skeleton_is_bits, aos_mem skeleton_mem, const aos_grid_info *info) {
   if (!c) return AOS_ERR_INVALID;
   AOS_REQUIRE(c, n_seeds >= 0 && n_rows >= 0, "negative count");
   AOS_REQUIRE(c, n_seeds == 0 || seeds_xy != nullptr, "seeds pointer is null");
@@ -115,13 +129,21 @@ aos_status aos_gvd_stage(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, co
     in.ox = info->origin_x;
     in.oy = info->origin_y;
     in.res = info->resolution;
-    const size_t cells = (size_t)in.w * in.h;
-    AOS_CUDA_OK(c, c->gvd_skel.reserve((size_t)in.pitch * in.h * 4));
-    AOS_CUDA_OK(c, c->points_stage.reserve(cells));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, skeleton, cells, cudaMemcpyHostToDevice, c->stream));
-    aos_status s = launch_pack(c, c->points_stage.as<int8_t>(), c->gvd_skel.as<uint32_t>(), in.w, in.h);
-    if (s != AOS_OK) return s;
-    in.skel_bits = c->gvd_skel.as<uint32_t>();
+    const size_t cells = (size_t)in.w * in.h, bit_bytes = (size_t)in.pitch * in.h * 4;
+    if (skeleton_is_bits && skeleton_mem == AOS_MEM_DEVICE) {
+      in.skel_bits = static_cast<const uint32_t *>(skeleton);  // shared device handle: no copy at all
+    } else {
+      AOS_CUDA_OK(c, c->gvd_skel.reserve(bit_bytes));
+      if (skeleton_is_bits) {  // bit-packed side channel: W*H/8 bytes instead of W*H
+        AOS_CUDA_OK(c, cudaMemcpyAsync(c->gvd_skel.p, skeleton, bit_bytes, cudaMemcpyHostToDevice, c->stream));
+      } else {
+        AOS_CUDA_OK(c, c->points_stage.reserve(cells));
+        AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, skeleton, cells, cudaMemcpyHostToDevice, c->stream));
+        aos_status s = launch_pack(c, c->points_stage.as<int8_t>(), c->gvd_skel.as<uint32_t>(), in.w, in.h);
+        if (s != AOS_OK) return s;
+      }
+      in.skel_bits = c->gvd_skel.as<uint32_t>();
+    }
   } else {
     if (!c->have_seed) {  // gvd:257: no skeleton yet
       set_error(c, "no skeleton: pass one or run aos_seed_stage on this context first");

@@ -7,12 +7,12 @@
 // (aos_set_clearance), default off so the published arrays stay bit-identical to the reference.
 // aos_gvd_node's Voronoi diagram itself is cv::Subdiv2D's point-site diagram (host_subdiv.cu), not a raster.
 //
-// Exact, integer-only, separable (the structure of the parallel banding algorithm with one band per line):
+// Exact, integer-only, the parallel banding algorithm (Cao et al., I3D 2010):
 //   phase 1  per row   : nearest set cell of the same row for every cell (bit tricks inside a word, block-wide
 //                        max/min scans across the words of the row)                      -> uint16 x of that cell
-//   phase 2  per column: lower envelope of the parabolas (x - sx(y))^2 + (u - y)^2 by the stack sweep with exact
-//                        integer separators (floor division), one thread per column, coalesced across columns
-//   phase 3  per column: backward sweep over the stack writes the nearest site (x | y << 16) and d^2
+//   phase 2  per column: lower envelope of the parabolas (x - sx(y))^2 + (u - y)^2 by stack sweeps with exact
+//                        integer separators (floor division): per band, then merged per column
+//   phase 3  per band  : backward sweep over the merged stack writes the nearest site (x | y << 16) and d^2
 // No approximation (this is not jump flooding); ties go to the site met first by the sweeps (lowest row, then
 // lowest x), which tests/test_edt_gpu.py checks only through the distances, which are unique.
 #include "aos_common.cuh"
@@ -79,68 +79,121 @@ __global__ void __launch_bounds__(kEdtRowThreads) edt_rows_kernel(const uint32_t
   }
 }
 
-// ---- phases 2 + 3: one thread per column -------------------------------------------------------------------
+// ---- phases 2 + 3: parallel banding over the columns ----------------------------------------------------------
+// Every column is cut into bands of kEdtBandRows rows.  (2a) one thread per (column, band) sweeps its rows and keeps
+// the sites of the band's own lower envelope on a stack; (2b) one thread per column merges the band stacks in row
+// order into the column's envelope (only survivors are visited: a site dominated inside its band is dominated
+// globally); (3) one thread per (column, band) locates its last row in the merged stack by binary search and fills
+// nearest site and d^2 downwards.  Threads of a warp work on adjacent columns, so every plane access is coalesced.
+constexpr int kEdtBandRows = 512;
+
 __device__ __forceinline__ long long floor_div(long long a, long long b) {  // b > 0
   long long q = a / b;
   return (a % b != 0 && a < 0) ? q - 1 : q;
 }
 
-__global__ void edt_columns_kernel(const uint16_t *__restrict__ sx, int w, int h, uint16_t *__restrict__ stack_s,
-                                   uint16_t *__restrict__ stack_t, uint32_t *__restrict__ nearest, int32_t *__restrict__ dist2) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= w) return;
-  // forward sweep: s[q] = row of the q-th envelope site, t[q] = first row where it wins
-  int q = -1;
-  long long top_s = 0, top_t = 0, top_g = 0;  // cached top of the stack
-  for (int u = 0; u < h; ++u) {
-    const uint16_t sxu = sx[(size_t)u * w + x];
-    if (sxu == kNoSite16) continue;
-    const long long dx = (long long)x - sxu, gu = dx * dx;
-    while (q >= 0) {
-      const long long a = top_t - top_s, b = top_t - u;
-      if (a * a + top_g > b * b + gu) {  // the new parabola already wins where the top one starts: pop
-        --q;
-        if (q >= 0) {
-          top_s = stack_s[(size_t)q * w + x];
-          top_t = stack_t[(size_t)q * w + x];
-          const long long d = (long long)x - sx[(size_t)top_s * w + x];
-          top_g = d * d;
-        }
-      } else {
-        break;
+struct EnvTop {
+  int q;                      // index of the top entry, -1 = empty
+  long long s, t, g;          // its row, first row where it wins, squared x-distance
+};
+
+// push site (row u, squared x-distance gu) onto the envelope stack stored at plane rows base + q
+__device__ __forceinline__ void env_push(uint16_t *__restrict__ S, uint16_t *__restrict__ T, const uint16_t *__restrict__ sx,
+                                         size_t base, int w, int h, int x, EnvTop &e, int u, long long gu) {
+  while (e.q >= 0) {
+    const long long a = e.t - e.s, b = e.t - u;
+    if (a * a + e.g > b * b + gu) {  // the new parabola already wins where the top one starts: pop
+      --e.q;
+      if (e.q >= 0) {
+        e.s = S[(base + e.q) * w + x];
+        e.t = T[(base + e.q) * w + x];
+        const long long d = (long long)x - sx[(size_t)e.s * w + x];
+        e.g = d * d;
       }
-    }
-    if (q < 0) {
-      q = 0;
-      top_s = u;
-      top_t = 0;
-      top_g = gu;
-      stack_s[x] = (uint16_t)u;
-      stack_t[x] = 0;
     } else {
-      // first row where u beats top_s: 1 + floor((u^2 - s^2 + g(u) - g(s)) / (2 (u - s)))
-      const long long num = (long long)u * u - top_s * top_s + gu - top_g;
-      const long long wrow = 1 + floor_div(num, 2 * ((long long)u - top_s));
-      if (wrow < h) {
-        ++q;
-        top_s = u;
-        top_t = wrow;
-        top_g = gu;
-        stack_s[(size_t)q * w + x] = (uint16_t)u;
-        stack_t[(size_t)q * w + x] = (uint16_t)wrow;
-      }
+      break;
     }
   }
-  // backward sweep
-  if (q < 0) {
-    for (int u = 0; u < h; ++u) {
+  if (e.q < 0) {
+    e.q = 0;
+    e.s = u;
+    e.t = 0;
+    e.g = gu;
+    S[base * w + x] = (uint16_t)u;
+    T[base * w + x] = 0;
+  } else {
+    // first row where u beats the top: 1 + floor((u^2 - s^2 + g(u) - g(s)) / (2 (u - s)))
+    const long long num = (long long)u * u - e.s * e.s + gu - e.g;
+    const long long wrow = 1 + floor_div(num, 2 * ((long long)u - e.s));
+    if (wrow < h) {
+      ++e.q;
+      e.s = u;
+      e.t = wrow;
+      e.g = gu;
+      S[(base + e.q) * w + x] = (uint16_t)u;
+      T[(base + e.q) * w + x] = (uint16_t)wrow;
+    }
+  }
+}
+
+__global__ void edt_band_sweep_kernel(const uint16_t *__restrict__ sx, int w, int h, uint16_t *__restrict__ S,
+                                      uint16_t *__restrict__ T, uint16_t *__restrict__ counts) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, band = blockIdx.y;
+  if (x >= w) return;
+  const int r0 = band * kEdtBandRows, r1 = min(h, r0 + kEdtBandRows);
+  EnvTop e{-1, 0, 0, 0};
+  for (int u = r0; u < r1; ++u) {
+    const uint16_t sxu = sx[(size_t)u * w + x];
+    if (sxu == kNoSite16) continue;
+    const long long dx = (long long)x - sxu;
+    env_push(S, T, sx, (size_t)r0, w, h, x, e, u, dx * dx);
+  }
+  counts[(size_t)band * w + x] = (uint16_t)(e.q + 1);
+}
+
+// merged stack of column x lives in plane rows 0 .. total-1 (in place: entry q is written after entry >= q was read)
+__global__ void edt_merge_kernel(const uint16_t *__restrict__ sx, int w, int h, int n_bands, uint16_t *__restrict__ S,
+                                 uint16_t *__restrict__ T, const uint16_t *__restrict__ counts, int *__restrict__ totals) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  EnvTop e{-1, 0, 0, 0};
+  for (int band = 0; band < n_bands; ++band) {
+    const int cnt = counts[(size_t)band * w + x];
+    const size_t r0 = (size_t)band * kEdtBandRows;
+    for (int j = 0; j < cnt; ++j) {
+      const int u = S[(r0 + j) * w + x];
+      const long long dx = (long long)x - sx[(size_t)u * w + x];
+      env_push(S, T, sx, 0, w, h, x, e, u, dx * dx);
+    }
+  }
+  totals[x] = e.q + 1;
+}
+
+__global__ void edt_fill_kernel(const uint16_t *__restrict__ sx, int w, int h, const uint16_t *__restrict__ S,
+                                const uint16_t *__restrict__ T, const int *__restrict__ totals, uint32_t *__restrict__ nearest,
+                                int32_t *__restrict__ dist2) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, band = blockIdx.y;
+  if (x >= w) return;
+  const int r0 = band * kEdtBandRows, r1 = min(h, r0 + kEdtBandRows);
+  const int total = totals[x];
+  if (total == 0) {
+    for (int u = r0; u < r1; ++u) {
       nearest[(size_t)u * w + x] = 0xffffffffu;
       if (dist2) dist2[(size_t)u * w + x] = 0x7fffffff;
     }
     return;
   }
+  // largest q with t[q] <= r1 - 1 (t is increasing, t[0] = 0)
+  int lo = 0, hi = total - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)T[(size_t)mid * w + x] <= r1 - 1) lo = mid;
+    else hi = mid - 1;
+  }
+  int q = lo;
+  long long top_s = S[(size_t)q * w + x], top_t = T[(size_t)q * w + x];
   long long site_x = sx[(size_t)top_s * w + x];
-  for (int u = h - 1; u >= 0; --u) {
+  for (int u = r1 - 1; u >= r0; --u) {
     nearest[(size_t)u * w + x] = (uint32_t)site_x | ((uint32_t)top_s << 16);
     if (dist2) {
       const long long dx = (long long)x - site_x, dy = (long long)u - top_s;
@@ -148,8 +201,8 @@ __global__ void edt_columns_kernel(const uint16_t *__restrict__ sx, int w, int h
     }
     if (u == top_t && q > 0) {
       --q;
-      top_s = stack_s[(size_t)q * w + x];
-      top_t = stack_t[(size_t)q * w + x];
+      top_s = S[(size_t)q * w + x];
+      top_t = T[(size_t)q * w + x];
       site_x = sx[(size_t)top_s * w + x];
     }
   }
@@ -172,15 +225,30 @@ aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *near
   AOS_REQUIRE(c, w > 0 && h > 0 && w < 65535 && h < 65535, "EDT grid must be smaller than 65535 x 65535");
   const int pitch = pitch_words_for(w);
   const size_t cells = (size_t)w * h;
-  AOS_CUDA_OK(c, c->edt_buf.reserve(cells * 2 * 3 + 1024));
-  uint16_t *sx = c->edt_buf.as<uint16_t>();
-  uint16_t *ss = sx + cells, *st = ss + cells;
+  const int n_bands = (h + kEdtBandRows - 1) / kEdtBandRows;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t plane = up(cells * 2), cnt_bytes = up((size_t)n_bands * w * 2);
+  AOS_CUDA_OK(c, c->edt_buf.reserve(3 * plane + cnt_bytes + up((size_t)w * 4) + 1024));
+  char *base = c->edt_buf.as<char>();
+  uint16_t *sx = reinterpret_cast<uint16_t *>(base);
+  uint16_t *ss = reinterpret_cast<uint16_t *>(base + plane), *st = reinterpret_cast<uint16_t *>(base + 2 * plane);
+  uint16_t *counts = reinterpret_cast<uint16_t *>(base + 3 * plane);
+  int *totals = reinterpret_cast<int *>(base + 3 * plane + cnt_bytes);
   const int nw = (w + 31) >> 5;
   AOS_REQUIRE(c, nw <= 8 * kEdtRowThreads, "row too wide for the EDT row kernel");
   edt_rows_kernel<<<h, kEdtRowThreads, sizeof(int) * 2 * nw, c->stream>>>(bits, w, h, pitch, sx);
   ++c->launches;
-  edt_columns_kernel<<<(w + 63) / 64, 64, 0, c->stream>>>(sx, w, h, ss, st, nearest, dist2);
+  c->mark("edt_rows");
+  dim3 gband((w + 127) / 128, n_bands);
+  edt_band_sweep_kernel<<<gband, 128, 0, c->stream>>>(sx, w, h, ss, st, counts);
   ++c->launches;
+  c->mark("edt_band_sweep");
+  edt_merge_kernel<<<(w + 63) / 64, 64, 0, c->stream>>>(sx, w, h, n_bands, ss, st, counts, totals);
+  ++c->launches;
+  c->mark("edt_merge");
+  edt_fill_kernel<<<gband, 128, 0, c->stream>>>(sx, w, h, ss, st, totals, nearest, dist2);
+  ++c->launches;
+  c->mark("edt_fill");
   AOS_CUDA_OK(c, cudaGetLastError());
   return AOS_OK;
 }

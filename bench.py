@@ -116,7 +116,7 @@ def bench_ours(args):
         torch.cuda.synchronize()
 
     ncpu = os.cpu_count() or 1
-    T = args.maps_in_flight if args.maps_in_flight > 0 else max(1, min(8, ncpu // max(world, 1)))
+    T = args.maps_in_flight if args.maps_in_flight > 0 else max(1, min(16, ncpu // max(world, 1)))
     spec0 = synth.config(args.workload, seed=rank * 64, n_points=args.points)
     params = make_params(lib, spec0)
     gi = lib.grid_geometry(params)
@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--points", type=int, default=None, help="override the workload's point count")
     ap.add_argument("--maps-in-flight", type=int, default=0,
-                    help="independent maps processed concurrently per GPU (0 = min(8, host cores / ranks))")
+                    help="independent maps processed concurrently per GPU (0 = min(16, host cores / ranks))")
     ap.add_argument("--shard", default="maps", choices=["maps", "bands"],
                     help="maps: independent maps per GPU (default, weak scaling); bands: one grid row-band sharded")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")

@@ -200,6 +200,12 @@ typedef struct {
 
 AOS_API aos_status aos_gvd_stage(aos_ctx *ctx, const double *seeds_xy, int32_t n_seeds, const double *rows_info,
                                  int32_t n_rows, const int8_t *skeleton, const aos_grid_info *info);
+/* Same, with the skeleton as an AOS_FMT_BITS grid (the 1 byte/cell OccupancyGrid is 400 MB at
+ * 20000^2 cells; the bit-packed grid is 50 MB in host memory, or a device pointer shared by the seed-gen side --
+ * e.g. aos_grid_device_bits(AOS_GRID_SKELETON_FRAMED) in the same process, a CUDA IPC handle across processes). */
+AOS_API aos_status aos_gvd_stage_bits(aos_ctx *ctx, const double *seeds_xy, int32_t n_seeds, const double *rows_info,
+                                      int32_t n_rows, const uint32_t *skeleton_bits, aos_mem skeleton_mem,
+                                      const aos_grid_info *info);
 AOS_API aos_status aos_get_graph(aos_ctx *ctx, aos_gvd_graph *out);
 
 /* Opt-in (default off): fill GvdGraph.edge_clearances with the minimum, over the samples of

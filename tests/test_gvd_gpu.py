@@ -37,6 +37,10 @@ def test_gvd_stage_from_messages(gpu_ctx, oracle):
     ctx = lib.Context(0)
     got = ctx.gvd_stage(r["seeds"], r["rows_info"], skeleton=r["skel_framed"], info=(r["res"], r["origin_x"], r["origin_y"]))
     assert_graph_parity(got, ref)
+    # bit-packed side channel (row F4): same graph from the 8x smaller AOS_FMT_BITS grid
+    bits = lib.pack_bits(r["skel_framed"] == 100)
+    got2 = ctx.gvd_stage(r["seeds"], r["rows_info"], skeleton=bits, info=(r["res"], r["origin_x"], r["origin_y"], r["w"]))
+    assert_graph_parity(got2, ref)
     ctx.close()
 
 
