@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
-    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
+    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
     "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
 
@@ -81,6 +81,12 @@ class CGvdGraph(C.Structure):
 
 class CBand(C.Structure):
     _fields_ = [("row0", C.c_int32), ("rows", C.c_int32), ("halo_lo", C.c_int32), ("halo_hi", C.c_int32)]
+
+
+class CBatchItem(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("params", C.POINTER(CSeedParams)), ("points", C.c_void_p), ("n_points", C.c_size_t),
+                ("point_step", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32), ("off_z", C.c_uint32),
+                ("points_mem", C.c_int), ("status", C.c_int)]
 
 
 class CSeedSummary(C.Structure):
@@ -148,6 +154,7 @@ def load() -> C.CDLL:
     L.aos_band_thin_launch.argtypes = [vp, C.POINTER(i32)]
     L.aos_band_grid_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.aos_seed_stage_tail.argtypes = [vp, C.POINTER(CSeedParams), vp, vp]
+    L.aos_map_to_graph_batch.argtypes = [C.POINTER(CBatchItem), i32, i32]
     L.aos_merge_seeds.argtypes = [vp, i32, vp, C.POINTER(i32)]
     L.aos_voronoi_facets.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, vp, i32, vp, i32,
                                      C.POINTER(i32), C.POINTER(i32)]
@@ -450,6 +457,23 @@ class Context:
         if n.value:
             self._check(self.L.aos_get_tree_rows(self.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_tree_rows")
         return out
+
+
+def map_to_graph_batch(contexts, params_list, points_list, max_threads: int = 0):
+    """aos_map_to_graph_batch: map i on contexts[i] (one host thread each).  Returns the per-map status codes;
+    results are read from each context with the usual getters."""
+    n = len(contexts)
+    items = (CBatchItem * n)()
+    keep = []
+    for i, (ctx, prm, pts) in enumerate(zip(contexts, params_list, points_list)):
+        cp = prm.to_c()
+        ptr, mem, cnt, step = ctx._points_args(pts, None, None)
+        keep.append((cp, pts))
+        items[i] = CBatchItem(ctx.h, C.pointer(cp), ptr, cnt, step, 0, 4, 8, mem, 0)
+    rc = load().aos_map_to_graph_batch(items, n, max_threads)
+    if rc != 0:
+        raise AosError(f"aos_map_to_graph_batch -> {rc}")
+    return [items[i].status for i in range(n)]
 
 
 def merge_seeds(seeds) -> np.ndarray:

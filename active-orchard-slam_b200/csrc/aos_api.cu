@@ -320,7 +320,19 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   // applyInflation: int(inflation_radius / grid_resolution) in float (seed_gen:936)
   const int R = static_cast<int>(p->inflation_radius / p->grid_resolution);
   AOS_REQUIRE(c, R >= 0, "negative inflation radius");
-  s = launch_inflate(c, c->g_raw.as<uint32_t>(), c->g_infl.as<uint32_t>(), c->g_occ.as<uint32_t>(), P.w, P.h, R);
+  if (R <= kMaxStencilRadius) {
+    s = launch_inflate(c, c->g_raw.as<uint32_t>(), c->g_infl.as<uint32_t>(), c->g_occ.as<uint32_t>(), P.w, P.h, R);
+  } else {
+    // beyond the stencil's reach: the same set as the threshold d^2 <= R^2 of the exact EDT (k_edt.cu), whose cost
+    // does not depend on R; the 5-cell frame of markBoundariesAsOccupied is OR-ed in separately
+    const size_t cells = (size_t)P.w * P.h;
+    AOS_CUDA_OK(c, c->edt_out.reserve(cells * 8 + 1024));
+    uint32_t *nearest = c->edt_out.as<uint32_t>();
+    int32_t *d2 = reinterpret_cast<int32_t *>(nearest + cells);
+    s = launch_edt(c, c->g_raw.as<uint32_t>(), P.w, P.h, nearest, d2);
+    if (s == AOS_OK) s = launch_edt_threshold(c, d2, P.w, P.h, R * R, c->g_infl.as<uint32_t>());
+    if (s == AOS_OK) s = launch_frame(c, c->g_infl.as<uint32_t>(), c->g_occ.as<uint32_t>(), P.w, P.h, 0, 0, P.w - 1, P.h - 1, 5);
+  }
   if (s != AOS_OK) return s;
   c->mark("inflate");
   // skeletonizeOccupancyGrid runs on the inflated grid WITHOUT the frame (seed_gen:560)

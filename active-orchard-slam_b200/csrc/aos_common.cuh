@@ -26,6 +26,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr int kTileBoxW = 36;
 constexpr int kTileOwnW = 28;
 constexpr int kTileLane0 = 2;
+constexpr int kMaxStencilRadius = 64;  // inflate_kernel's disc radius limit (cells); larger radii go through the EDT
 constexpr int kThinSubIters = 8;  // sub-iterations per thinning launch == halo rows a row band refreshes per launch
 
 // ---- error plumbing: nothing throws across the C boundary -------------------------------------

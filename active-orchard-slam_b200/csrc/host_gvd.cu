@@ -5,6 +5,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 #include "aos_common.cuh"
 #include "host_subdiv.h"
@@ -245,6 +247,38 @@ aos_status aos_map_to_graph(aos_ctx *c, const aos_seed_params *p, const void *po
                       (int32_t)(c->h_rows_info.size() / 4), nullptr, nullptr);
   c->composite = false;
   return s;
+}
+
+
+// BASELINE config 5 (sweeps of independent maps): one host thread per map in flight, each on its own context --
+// the GPU stages of one map overlap the host stages (Subdiv2D replay) of the others.
+aos_status aos_map_to_graph_batch(aos_batch_item *items, int32_t n_items, int32_t max_threads) {
+  if (n_items < 0 || (n_items > 0 && !items)) return AOS_ERR_INVALID;
+  for (int i = 0; i < n_items; ++i) {
+    if (!items[i].ctx) return AOS_ERR_INVALID;
+    for (int j = 0; j < i; ++j)
+      if (items[j].ctx == items[i].ctx && max_threads != 1) return AOS_ERR_INVALID;  // a context is not thread-safe
+  }
+  int nt = max_threads > 0 ? std::min(max_threads, n_items) : n_items;
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (int i = next.fetch_add(1); i < n_items; i = next.fetch_add(1)) {
+      aos_batch_item &it = items[i];
+      it.status = aos_map_to_graph(it.ctx, it.params, it.points, it.n_points, it.point_step, it.off_x, it.off_y, it.off_z,
+                                   it.points_mem);
+    }
+  };
+  if (nt <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+  }
+  for (int i = 0; i < n_items; ++i)
+    if (items[i].status != AOS_OK && items[i].status != AOS_ERR_STATE) return items[i].status;
+  return AOS_OK;
 }
 
 }  // extern "C"

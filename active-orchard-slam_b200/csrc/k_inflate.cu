@@ -15,7 +15,7 @@ namespace aos {
 
 constexpr int kInfRows = 64;   // output rows per CTA
 constexpr int kInfThreads = 256;
-constexpr int kMaxR = 64;
+constexpr int kMaxR = kMaxStencilRadius;
 
 struct InflateParams {
   int w, h, pitch, R;

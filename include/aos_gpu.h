@@ -226,6 +226,21 @@ AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, cons
  * Process-wide; default 6. */
 AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
 
+/* Independent maps in flight (BASELINE.json config 5: sweeps over maps / parameters): item i runs aos_map_to_graph on
+ * its own context (contexts may sit on different devices) from a pool of at most max_threads host threads
+ * (0 = one per item).  Two items may share a context only with max_threads == 1.  items[i].status receives each
+ * map's status (AOS_ERR_STATE = a map without rows, as in aos_map_to_graph); the call returns the first real error. */
+typedef struct {
+  aos_ctx *ctx;
+  const aos_seed_params *params;
+  const void *points;
+  size_t n_points;
+  uint32_t point_step, off_x, off_y, off_z;
+  aos_mem points_mem;
+  aos_status status;
+} aos_batch_item;
+AOS_API aos_status aos_map_to_graph_batch(aos_batch_item *items, int32_t n_items, int32_t max_threads);
+
 /* Stand-alone host steps of the gvd half (unit tests; no device needed). */
 /* voronoiSeedsCallback's merge; out_xy must hold 2*n doubles; *n_out = merged count. */
 AOS_API aos_status aos_merge_seeds(const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out);

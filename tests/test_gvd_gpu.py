@@ -95,3 +95,39 @@ def test_gvd_stage_needs_inputs(oracle):
     with pytest.raises(lib.AosError):   # no valid seeds (gvd:273)
         ctx.gvd_stage(np.full((2, 2), np.nan), np.zeros((0, 4)), skeleton=np.zeros((8, 8), np.int8), info=(0.05, 0.0, 0.0))
     ctx.close()
+
+
+def test_sweep_of_maps_in_flight(oracle):
+    """BASELINE config 5 in miniature: a sweep over row pitch / inflation radius / resolution, all maps in flight at
+    once through aos_map_to_graph_batch (one context and host thread per map), each bit-exact against the oracle."""
+    sweep = [(3.5, 0.6, 0.05), (4.0, 0.8, 0.05), (5.0, 1.0, 0.05), (6.0, 0.8, 0.1), (4.5, 0.7, 0.1), (8.0, 1.0, 0.05)]
+    ctxs, prms, clouds, refs = [], [], [], []
+    for i, (pitch, infl, res) in enumerate(sweep):
+        spec = synth.OrchardSpec(extent_x=30.0, extent_y=24.0, row_pitch=pitch, n_points=90_000, outlier_count=4, seed=20 + i,
+                                 grid_resolution=res, inflation_radius=infl)
+        pts = synth.make_orchard(spec)
+        po, pl = params_pair(spec, oracle)
+        r = oracle.seed_stage(po, pts)
+        refs.append((r, _oracle_graph(oracle, r)))
+        ctxs.append(lib.Context(0))
+        prms.append(pl)
+        clouds.append(pts)
+    status = lib.map_to_graph_batch(ctxs, prms, clouds)
+    from helpers import assert_seed_parity
+    for ctx, st, (r, g) in zip(ctxs, status, refs):
+        assert st == 0
+        assert_seed_parity(ctx, r)
+        assert_graph_parity(ctx.graph(), g)
+        ctx.close()
+
+
+def test_inflation_radius_beyond_the_stencil(gpu_ctx, oracle):
+    """R = 80 cells (> 64): the seed stage switches to the EDT threshold for applyInflation; still bit-exact."""
+    spec = synth.OrchardSpec(extent_x=30.0, extent_y=20.0, row_pitch=7.0, tree_spacing=4.0, n_points=60_000, outlier_count=2,
+                             seed=4, grid_resolution=0.02, inflation_radius=1.6)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    gpu_ctx.seed_stage(pl, pts)
+    from helpers import assert_seed_parity
+    assert_seed_parity(gpu_ctx, r)
