@@ -55,27 +55,31 @@ __global__ void __launch_bounds__(kEdtRowThreads) edt_rows_kernel(const uint32_t
     }
     __syncthreads();
   }
-  uint16_t *out = sx + (size_t)y * w;
-  for (int k = threadIdx.x; k < nw; k += kEdtRowThreads) {
+  // one thread per pair of cells, so a warp stores 128 contiguous bytes; the word and the two scan values it needs
+  // come from shared memory (broadcast within the 16 lanes that share a word)
+  uint32_t *out2 = reinterpret_cast<uint32_t *>(sx + (size_t)y * w);  // w * 2 bytes per row: 4-byte aligned iff w even
+  const bool pair_ok = (w & 1) == 0;
+  auto nearest_in_row = [&](int x) -> int {
+    const int k = x >> 5, b = x & 31;
     uint32_t v = row[k];
     if (k == nw - 1 && (w & 31)) v &= (1u << (w & 31)) - 1u;
-    const int left_before = k > 0 ? hi[k - 1] : -1;                // nearest set cell in earlier words
-    const int right_after = k + 1 < nw ? lo[k + 1] : 0x7fffffff;   // nearest set cell in later words
-    const int x0 = k << 5;
-    const int nb = min(32, w - x0);
-    for (int b = 0; b < nb; ++b) {
-      const uint32_t le = v & (0xffffffffu >> (31 - b));  // bits <= b
-      const uint32_t ge = v & (0xffffffffu << b);         // bits >= b
-      const int L = le ? x0 + 31 - __clz(le) : left_before;
-      const int R = ge ? x0 + __ffs(ge) - 1 : right_after;
-      const int x = x0 + b;
-      int s;
-      if (L < 0 && R == 0x7fffffff) s = kNoSite16;
-      else if (L < 0) s = R;
-      else if (R == 0x7fffffff) s = L;
-      else s = (x - L <= R - x) ? L : R;
-      out[x] = (uint16_t)s;
+    const uint32_t le = v & (0xffffffffu >> (31 - b));  // bits <= b
+    const uint32_t ge = v & (0xffffffffu << b);         // bits >= b
+    const int L = le ? (k << 5) + 31 - __clz(le) : (k > 0 ? hi[k - 1] : -1);
+    const int R = ge ? (k << 5) + __ffs(ge) - 1 : (k + 1 < nw ? lo[k + 1] : 0x7fffffff);
+    if (L < 0 && R == 0x7fffffff) return kNoSite16;
+    if (L < 0) return R;
+    if (R == 0x7fffffff) return L;
+    return (x - L <= R - x) ? L : R;  // ties go to the lower x
+  };
+  if (pair_ok) {
+    for (int p = threadIdx.x; p < (w >> 1); p += kEdtRowThreads) {
+      const int x = p << 1;
+      out2[p] = (uint32_t)nearest_in_row(x) | ((uint32_t)nearest_in_row(x + 1) << 16);
     }
+  } else {
+    uint16_t *out = sx + (size_t)y * w;
+    for (int x = threadIdx.x; x < w; x += kEdtRowThreads) out[x] = (uint16_t)nearest_in_row(x);
   }
 }
 
@@ -151,47 +155,127 @@ __global__ void edt_band_sweep_kernel(const uint16_t *__restrict__ sx, int w, in
   counts[(size_t)band * w + x] = (uint16_t)(e.q + 1);
 }
 
-// merged stack of column x lives in plane rows 0 .. total-1 (in place: entry q is written after entry >= q was read)
-__global__ void edt_merge_kernel(const uint16_t *__restrict__ sx, int w, int h, int n_bands, uint16_t *__restrict__ S,
-                                 uint16_t *__restrict__ T, const uint16_t *__restrict__ counts, int *__restrict__ totals) {
+// (2b) Junction merge.  The band stacks stay where they are; only the junction between the envelope built so far
+// and the next band is repaired: tops that the band's first site beats at their start row are popped, leading
+// sites of the band that never win against the new predecessor are dropped, and the first survivor gets its
+// global start row.  Everything behind it keeps its local start rows (same predecessor as in the band's own
+// envelope), so the cost per column is proportional to what is removed, not to what survives.  Per (band, column):
+// lo/hi = surviving index range; per column: the list of non-empty bands (for the search in phase 3).
+constexpr int kEdtMaxBands = 128;
+
+__global__ void edt_merge_kernel(const uint16_t *__restrict__ sx, int w, int h, int n_bands, const uint16_t *__restrict__ S,
+                                 uint16_t *__restrict__ T, const uint16_t *__restrict__ counts, uint16_t *__restrict__ lo_pl,
+                                 uint16_t *__restrict__ hi_pl, uint16_t *__restrict__ ne_pl, int *__restrict__ n_ne) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
-  EnvTop e{-1, 0, 0, 0};
-  for (int band = 0; band < n_bands; ++band) {
-    const int cnt = counts[(size_t)band * w + x];
-    const size_t r0 = (size_t)band * kEdtBandRows;
-    for (int j = 0; j < cnt; ++j) {
-      const int u = S[(r0 + j) * w + x];
-      const long long dx = (long long)x - sx[(size_t)u * w + x];
-      env_push(S, T, sx, 0, w, h, x, e, u, dx * dx);
+  int n_live = 0;  // non-empty bands so far: ne_pl[i * w + x], their hi in hi_pl
+  int top_band = -1, top_hi = 0, top_lo = 0;  // cached range of the last non-empty band
+  for (int k = 0; k < n_bands; ++k) {
+    const int cnt = counts[(size_t)k * w + x];
+    const size_t r0 = (size_t)k * kEdtBandRows;
+    int lo = 0;
+    bool live = cnt > 0;
+    if (cnt > 0 && top_band >= 0) {
+      int j = 0;
+      for (;;) {
+        if (j == cnt) {  // the whole band lost against the envelope below it
+          live = false;
+          break;
+        }
+        const long long u = S[(r0 + j) * w + x];
+        const long long dxu = (long long)x - sx[(size_t)u * w + x], gu = dxu * dxu;
+        // pop tops that u already beats where they start
+        long long ts = 0, tt = 0, tg = 0;
+        while (top_band >= 0) {
+          const size_t tr = (size_t)top_band * kEdtBandRows + top_hi - 1;
+          ts = S[tr * w + x];
+          tt = T[tr * w + x];
+          const long long d = (long long)x - sx[(size_t)ts * w + x];
+          tg = d * d;
+          const long long a = tt - ts, bb = tt - u;
+          if (a * a + tg > bb * bb + gu) {
+            if (--top_hi <= top_lo) {  // that band is exhausted: fall back to the previous non-empty one
+              hi_pl[(size_t)top_band * w + x] = (uint16_t)top_lo;
+              --n_live;
+              if (n_live > 0) {
+                top_band = ne_pl[(size_t)(n_live - 1) * w + x];
+                top_hi = hi_pl[(size_t)top_band * w + x];
+                top_lo = lo_pl[(size_t)top_band * w + x];
+              } else {
+                top_band = -1;
+              }
+            }
+          } else {
+            break;
+          }
+        }
+        if (top_band < 0) {  // nothing below survives: u starts the envelope
+          T[(r0 + j) * w + x] = 0;
+          lo = j;
+          break;
+        }
+        const long long num = u * u - ts * ts + gu - tg;
+        const long long wrow = 1 + floor_div(num, 2 * (u - ts));
+        const long long next_t = j + 1 < cnt ? (long long)T[(r0 + j + 1) * w + x] : (long long)h;
+        if (wrow >= next_t || wrow >= h) {  // u never wins between its new predecessor and its successor
+          ++j;
+          continue;
+        }
+        T[(r0 + j) * w + x] = (uint16_t)wrow;
+        lo = j;
+        break;
+      }
+    }
+    if (top_band >= 0) hi_pl[(size_t)top_band * w + x] = (uint16_t)top_hi;  // publish pops
+    lo_pl[(size_t)k * w + x] = (uint16_t)lo;
+    hi_pl[(size_t)k * w + x] = (uint16_t)(live ? cnt : lo);
+    if (live) {
+      ne_pl[(size_t)n_live * w + x] = (uint16_t)k;
+      ++n_live;
+      top_band = k;
+      top_hi = cnt;
+      top_lo = lo;
     }
   }
-  totals[x] = e.q + 1;
+  n_ne[x] = n_live;
 }
 
 __global__ void edt_fill_kernel(const uint16_t *__restrict__ sx, int w, int h, const uint16_t *__restrict__ S,
-                                const uint16_t *__restrict__ T, const int *__restrict__ totals, uint32_t *__restrict__ nearest,
+                                const uint16_t *__restrict__ T, const uint16_t *__restrict__ lo_pl, const uint16_t *__restrict__ hi_pl,
+                                const uint16_t *__restrict__ ne_pl, const int *__restrict__ n_ne, uint32_t *__restrict__ nearest,
                                 int32_t *__restrict__ dist2) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, band = blockIdx.y;
   if (x >= w) return;
   const int r0 = band * kEdtBandRows, r1 = min(h, r0 + kEdtBandRows);
-  const int total = totals[x];
-  if (total == 0) {
+  const int live = n_ne[x];
+  if (live == 0) {
     for (int u = r0; u < r1; ++u) {
       nearest[(size_t)u * w + x] = 0xffffffffu;
       if (dist2) dist2[(size_t)u * w + x] = 0x7fffffff;
     }
     return;
   }
-  // largest q with t[q] <= r1 - 1 (t is increasing, t[0] = 0)
-  int lo = 0, hi = total - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if ((int)T[(size_t)mid * w + x] <= r1 - 1) lo = mid;
-    else hi = mid - 1;
+  // owner of row r1 - 1: last surviving entry whose start row is <= r1 - 1.  Start rows increase along the merged
+  // sequence, so search the non-empty bands by the start row of their first survivor, then inside the band.
+  int a = 0, b = live - 1;
+  while (a < b) {
+    const int mid = (a + b + 1) >> 1;
+    const int kb = ne_pl[(size_t)mid * w + x];
+    const int t0 = T[((size_t)kb * kEdtBandRows + lo_pl[(size_t)kb * w + x]) * w + x];
+    if (t0 <= r1 - 1) a = mid;
+    else b = mid - 1;
   }
-  int q = lo;
-  long long top_s = S[(size_t)q * w + x], top_t = T[(size_t)q * w + x];
+  int li = a;                                   // index into the non-empty band list
+  int kb = ne_pl[(size_t)li * w + x];
+  int lo = lo_pl[(size_t)kb * w + x], hi = hi_pl[(size_t)kb * w + x];
+  int ja = lo, jb = hi - 1;
+  while (ja < jb) {
+    const int mid = (ja + jb + 1) >> 1;
+    if ((int)T[((size_t)kb * kEdtBandRows + mid) * w + x] <= r1 - 1) ja = mid;
+    else jb = mid - 1;
+  }
+  int j = ja;
+  long long top_s = S[((size_t)kb * kEdtBandRows + j) * w + x], top_t = T[((size_t)kb * kEdtBandRows + j) * w + x];
   long long site_x = sx[(size_t)top_s * w + x];
   for (int u = r1 - 1; u >= r0; --u) {
     nearest[(size_t)u * w + x] = (uint32_t)site_x | ((uint32_t)top_s << 16);
@@ -199,10 +283,18 @@ __global__ void edt_fill_kernel(const uint16_t *__restrict__ sx, int w, int h, c
       const long long dx = (long long)x - site_x, dy = (long long)u - top_s;
       dist2[(size_t)u * w + x] = (int32_t)(dx * dx + dy * dy);
     }
-    if (u == top_t && q > 0) {
-      --q;
-      top_s = S[(size_t)q * w + x];
-      top_t = T[(size_t)q * w + x];
+    if (u == top_t && (j > lo || li > 0)) {  // step to the previous survivor
+      if (j > lo) {
+        --j;
+      } else {
+        --li;
+        kb = ne_pl[(size_t)li * w + x];
+        lo = lo_pl[(size_t)kb * w + x];
+        hi = hi_pl[(size_t)kb * w + x];
+        j = hi - 1;
+      }
+      top_s = S[((size_t)kb * kEdtBandRows + j) * w + x];
+      top_t = T[((size_t)kb * kEdtBandRows + j) * w + x];
       site_x = sx[(size_t)top_s * w + x];
     }
   }
@@ -227,13 +319,17 @@ aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *near
   const size_t cells = (size_t)w * h;
   const int n_bands = (h + kEdtBandRows - 1) / kEdtBandRows;
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  AOS_REQUIRE(c, n_bands <= kEdtMaxBands, "EDT grid has more than 65536 rows");
   const size_t plane = up(cells * 2), cnt_bytes = up((size_t)n_bands * w * 2);
-  AOS_CUDA_OK(c, c->edt_buf.reserve(3 * plane + cnt_bytes + up((size_t)w * 4) + 1024));
+  AOS_CUDA_OK(c, c->edt_buf.reserve(3 * plane + 4 * cnt_bytes + up((size_t)w * 4) + 1024));
   char *base = c->edt_buf.as<char>();
   uint16_t *sx = reinterpret_cast<uint16_t *>(base);
   uint16_t *ss = reinterpret_cast<uint16_t *>(base + plane), *st = reinterpret_cast<uint16_t *>(base + 2 * plane);
   uint16_t *counts = reinterpret_cast<uint16_t *>(base + 3 * plane);
-  int *totals = reinterpret_cast<int *>(base + 3 * plane + cnt_bytes);
+  uint16_t *lo_pl = reinterpret_cast<uint16_t *>(base + 3 * plane + cnt_bytes);
+  uint16_t *hi_pl = reinterpret_cast<uint16_t *>(base + 3 * plane + 2 * cnt_bytes);
+  uint16_t *ne_pl = reinterpret_cast<uint16_t *>(base + 3 * plane + 3 * cnt_bytes);
+  int *totals = reinterpret_cast<int *>(base + 3 * plane + 4 * cnt_bytes);
   const int nw = (w + 31) >> 5;
   AOS_REQUIRE(c, nw <= 8 * kEdtRowThreads, "row too wide for the EDT row kernel");
   edt_rows_kernel<<<h, kEdtRowThreads, sizeof(int) * 2 * nw, c->stream>>>(bits, w, h, pitch, sx);
@@ -243,10 +339,10 @@ aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *near
   edt_band_sweep_kernel<<<gband, 128, 0, c->stream>>>(sx, w, h, ss, st, counts);
   ++c->launches;
   c->mark("edt_band_sweep");
-  edt_merge_kernel<<<(w + 63) / 64, 64, 0, c->stream>>>(sx, w, h, n_bands, ss, st, counts, totals);
+  edt_merge_kernel<<<(w + 63) / 64, 64, 0, c->stream>>>(sx, w, h, n_bands, ss, st, counts, lo_pl, hi_pl, ne_pl, totals);
   ++c->launches;
   c->mark("edt_merge");
-  edt_fill_kernel<<<gband, 128, 0, c->stream>>>(sx, w, h, ss, st, totals, nearest, dist2);
+  edt_fill_kernel<<<gband, 128, 0, c->stream>>>(sx, w, h, ss, st, lo_pl, hi_pl, ne_pl, totals, nearest, dist2);
   ++c->launches;
   c->mark("edt_fill");
   AOS_CUDA_OK(c, cudaGetLastError());

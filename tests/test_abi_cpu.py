@@ -44,3 +44,19 @@ def test_no_device_fails_loudly():
     except lib.AosError:
         return
     raise AssertionError("Context() must raise without a CUDA device (no CPU fallback)")
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/aos_gpu.h must be consumable from C (the reference's nodes are C++, but the boundary is a C-ABI):
+    compile a C99 translation unit that takes the address of every declared entry point."""
+    import subprocess
+    names = _declared_symbols()
+    src = tmp_path / "abi.c"
+    body = "\n".join(f"  p[{i}] = (void (*)(void))&{n};" for i, n in enumerate(names))
+    src.write_text('#include "aos_gpu.h"\n'
+                   f"void (*p[{len(names)}])(void);\n"
+                   "int main(void) {\n" + body + "\n  aos_seed_params sp; aos_gvd_graph g; aos_band b; aos_batch_item it;\n"
+                   "  (void)sp; (void)g; (void)b; (void)it;\n  return p[0] == 0;\n}\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        "-c", str(src), "-o", str(tmp_path / "abi.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
