@@ -303,21 +303,57 @@ __global__ void acc_init_kernel(ClusterAcc *acc, int n) {
 __global__ void cc_accumulate_kernel(const int *__restrict__ parent, const uint32_t *__restrict__ rootrank,
                                      const int *__restrict__ cellpos, int n, int w, int *__restrict__ cell_cluster,
                                      ClusterAcc *acc) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int c = (int)rootrank[parent[i]];
-    cell_cluster[i] = c;
-    int pos = cellpos[i];
-    int y = pos / w, x = pos - y * w;
-    ClusterAcc *a = acc + c;
-    atomicAdd(&a->size, 1u);
-    atomicAdd(&a->sumx, (unsigned long long)x);
-    atomicAdd(&a->sumy, (unsigned long long)y);
-    long long vals[4] = {x, y, (long long)x + y, (long long)x - y};
+  // Compact indices follow the raster, so a warp's 32 cells usually are one horizontal run of one cluster: reduce
+  // inside the warp (REDUX) and issue one set of atomics per warp instead of ten atomics per cell.
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += stride) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    int c = -1, pos = 0, x = 0, y = 0;
+    if (valid) {
+      c = (int)rootrank[parent[i]];
+      cell_cluster[i] = c;
+      pos = cellpos[i];
+      y = pos / w;
+      x = pos - y * w;
+    }
+    int uniform = 0;
+    __match_all_sync(0xffffffffu, c, &uniform);
+    const int vals[4] = {x, y, x + y, x - y};
+    if (uniform && c >= 0) {
+      const unsigned sx = __reduce_add_sync(0xffffffffu, (unsigned)x), sy = __reduce_add_sync(0xffffffffu, (unsigned)y);
+      unsigned long long kmax[4], kmin[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      unsigned long long key = ((unsigned long long)(vals[k] + kExtBias) << 32) | (unsigned int)pos;
-      atomicMax(&a->ext[k], key);
-      atomicMin(&a->ext[4 + k], key);
+      for (int k = 0; k < 4; ++k) {
+        const int vmax = __reduce_max_sync(0xffffffffu, vals[k]), vmin = __reduce_min_sync(0xffffffffu, vals[k]);
+        const unsigned pmax = __reduce_max_sync(0xffffffffu, vals[k] == vmax ? (unsigned)pos : 0u);
+        const unsigned pmin = __reduce_min_sync(0xffffffffu, vals[k] == vmin ? (unsigned)pos : 0xffffffffu);
+        kmax[k] = ((unsigned long long)((long long)vmax + kExtBias) << 32) | pmax;
+        kmin[k] = ((unsigned long long)((long long)vmin + kExtBias) << 32) | pmin;
+      }
+      if (lane == 0) {
+        ClusterAcc *a = acc + c;
+        atomicAdd(&a->size, 32u);
+        atomicAdd(&a->sumx, (unsigned long long)sx);
+        atomicAdd(&a->sumy, (unsigned long long)sy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          atomicMax(&a->ext[k], kmax[k]);
+          atomicMin(&a->ext[4 + k], kmin[k]);
+        }
+      }
+    } else if (valid) {
+      ClusterAcc *a = acc + c;
+      atomicAdd(&a->size, 1u);
+      atomicAdd(&a->sumx, (unsigned long long)x);
+      atomicAdd(&a->sumy, (unsigned long long)y);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned long long key = ((unsigned long long)((long long)vals[k] + kExtBias) << 32) | (unsigned int)pos;
+        atomicMax(&a->ext[k], key);
+        atomicMin(&a->ext[4 + k], key);
+      }
     }
   }
 }
@@ -340,6 +376,7 @@ __global__ void cc_group_kernel(const int *__restrict__ cell_cluster, const int 
 // 5. one CTA per cluster
 // ---------------------------------------------------------------------------------------------------
 constexpr int kClThreads = 128;
+constexpr int kMaxCand = 2048;  // pruned diameter candidates kept in shared memory per cluster
 enum : int { kFlagNeedsOrder = 1, kFlagRow = 2, kFlagTie = 4 };
 
 struct RowOut {  // device-side mirror of aos_tree_row + book-keeping
@@ -431,17 +468,45 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
     long long dx = max(x - bx0, bx1 - x), dy = max(y - by0, by1 - y);
     return dx * dx + dy * dy >= lb;
   };
-  long long best = lb;
+  // survivors of the pruning are few (the two tips of a row): gather them once, then all pairs among them
+  __shared__ int s_cand[kMaxCand];
+  __shared__ int s_ncand;
+  if (threadIdx.x == 0) s_ncand = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += kClThreads) {
     int pi = cells[i];
     int yi = pi / w, xi = pi - yi * w;
-    if (!is_cand(xi, yi)) continue;
-    for (int j = 0; j < n; ++j) {
-      int pj = cells[j];
-      int yj = pj / w, xj = pj - yj * w;
-      if (!is_cand(xj, yj)) continue;
-      long long d = d2ll(xi, yi, xj, yj);
-      best = d > best ? d : best;
+    if (is_cand(xi, yi)) {
+      int k = atomicAdd(&s_ncand, 1);
+      if (k < kMaxCand) s_cand[k] = pi;
+    }
+  }
+  __syncthreads();
+  const int nc = s_ncand;
+  long long best = lb;
+  if (nc <= kMaxCand) {
+    for (int i = threadIdx.x; i < nc; i += kClThreads) {
+      int pi = s_cand[i];
+      int yi = pi / w, xi = pi - yi * w;
+      for (int j = 0; j < nc; ++j) {
+        int pj = s_cand[j];
+        int yj = pj / w, xj = pj - yj * w;
+        long long d = d2ll(xi, yi, xj, yj);
+        best = d > best ? d : best;
+      }
+    }
+  } else {  // too many candidates for the shared list (a blob rather than a row): filter on the fly
+    for (int i = threadIdx.x; i < n; i += kClThreads) {
+      int pi = cells[i];
+      int yi = pi / w, xi = pi - yi * w;
+      if (!is_cand(xi, yi)) continue;
+      for (int j = 0; j < n; ++j) {
+        int pj = cells[j];
+        int yj = pj / w, xj = pj - yj * w;
+        if (!is_cand(xj, yj)) continue;
+        long long d = d2ll(xi, yi, xj, yj);
+        best = d > best ? d : best;
+      }
     }
   }
   const long long maxd2 = block_reduce_max<long long>(best, s_i64);
