@@ -22,11 +22,11 @@ class Subdiv {
   void voronoi_facets(std::vector<float> *xy, std::vector<int32_t> *off);
 
  private:
-  struct QuadEdge {
+  struct alignas(32) QuadEdge {  // 32 bytes, never straddles a cache line
     int next[4];
     int pt[4];
   };
-  struct Vertex {
+  struct alignas(16) Vertex {
     int first_edge;
     int type;  // -1 free, 0 real, 1 virtual (Voronoi vertex)
     float x, y;
