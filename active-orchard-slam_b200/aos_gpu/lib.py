@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
     "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
-    "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
+    "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
 
 
@@ -145,6 +145,8 @@ def load() -> C.CDLL:
     L.aos_get_graph.argtypes = [vp, C.POINTER(CGvdGraph)]
     L.aos_map_to_graph.argtypes = [vp, C.POINTER(CSeedParams), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.aos_set_subdiv_outer_factor.argtypes = [C.c_float]
+    L.aos_radius_outlier_removal.argtypes = [vp, vp, sz, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float,
+                                             i32, C.POINTER(vp), C.POINTER(sz)]
     L.aos_set_clearance.argtypes = [vp, C.c_int]
     L.aos_edt_bits.argtypes = [vp, vp, i32, i32, vp, vp]
     L.aos_inflate_bits_edt.argtypes = [vp, vp, vp, i32, i32, i32]
@@ -194,6 +196,22 @@ def grid_geometry(params: SeedParams) -> CGridInfo:
     if rc != 0:
         raise AosError(f"aos_grid_geometry -> {rc}")
     return gi
+
+
+class DevicePoints:
+    """A library-owned device cloud of 16-byte x,y,z,pad records (quacks like a [N,4] float32 CUDA tensor)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.ptr, self.shape = ptr, (n, 4)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def stride(self, dim):
+        return 4 if dim == 0 else 1
+
+    def element_size(self):
+        return 4
 
 
 class Context:
@@ -424,6 +442,15 @@ class Context:
                     corner_points=arr(g.corner_points, 8 * g.n_rows, np.float64).reshape(-1, 4, 2),
                     n_merged_seeds=g.n_merged_seeds, n_voronoi_edges=g.n_voronoi_edges,
                     n_boundary_points=g.n_boundary_points)
+
+    def radius_outlier_removal(self, points, radius=0.2, min_neighbors=2, n_points=None, point_step=None, offsets=(0, 4, 8)):
+        """aos_radius_outlier_removal.  Returns (device pointer of the kept x,y,z,1 records, count); pass them on
+        as seed_stage(params, DevicePoints(ptr, count))."""
+        ptr, mem, n, step = self._points_args(points, n_points, point_step)
+        out, cnt = C.c_void_p(), C.c_size_t()
+        self._check(self.L.aos_radius_outlier_removal(self.h, C.c_void_p(ptr), n, step, offsets[0], offsets[1], offsets[2], mem,
+                                                      radius, min_neighbors, C.byref(out), C.byref(cnt)), "aos_radius_outlier_removal")
+        return DevicePoints(out.value, cnt.value)
 
     def set_clearance(self, on: bool):
         self._check(self.L.aos_set_clearance(self.h, int(on)), "aos_set_clearance")

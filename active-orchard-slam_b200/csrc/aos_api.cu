@@ -112,7 +112,7 @@ void aos_destroy(aos_ctx *c) {
   DevBuf *bufs[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch,
                     &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
                     &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf,
-                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2, &c->edt_buf, &c->edt_out};
+                    &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2, &c->edt_buf, &c->edt_out, &c->ror_buf, &c->ror_out};
   for (DevBuf *b : bufs) b->release();
   c->graph.release();
   c->pin_facet_xy.release();
@@ -674,6 +674,28 @@ aos_status aos_thin_bits(aos_ctx *c, uint32_t *inout, int32_t w, int32_t h, int3
   if (subiters) *subiters = s;
   if (r != AOS_OK) return r;
   AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return AOS_OK;
+}
+
+aos_status aos_radius_outlier_removal(aos_ctx *c, const void *points, size_t n_points, uint32_t point_step, uint32_t off_x,
+                                      uint32_t off_y, uint32_t off_z, aos_mem points_mem, float radius, int32_t min_neighbors,
+                                      const void **out_points, size_t *n_out) {
+  if (!c || !out_points || !n_out) return AOS_ERR_INVALID;
+  aos_status s = check_points(c, points, n_points, point_step, off_x, off_y, off_z);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  c->marks.clear();
+  c->mark("start");
+  const void *dpoints = points;
+  if (points_mem == AOS_MEM_HOST && n_points) {
+    AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, c->stream));
+    dpoints = c->points_stage.p;
+  }
+  c->mark("h2d_points");
+  s = run_ror(c, dpoints, n_points, point_step, off_x, off_y, off_z, radius, min_neighbors, n_out);
+  if (s != AOS_OK) return s;
+  *out_points = c->ror_out.p;
   return AOS_OK;
 }
 

@@ -203,6 +203,8 @@ aos_status launch_open(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h);
 aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters);
 aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, int h, int y_off, int gh, int cnt_r0,
                             int cnt_r1, int *d_count);
+aos_status run_ror(Ctx *c, const void *dpoints, size_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, float radius,
+                   int min_neighbors, size_t *n_out);
 aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *nearest, int32_t *dist2);
 aos_status launch_edt_threshold(Ctx *c, const int32_t *dist2, int w, int h, int r2, uint32_t *out);
 aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h, int gx0, int gy0, int gx1, int gy1,
@@ -320,7 +322,7 @@ struct Ctx {
   // gvd half (host_gvd.cu, k_graph.cu)
   bool have_graph = false;
   GraphHost graph;
-  DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel, seed_buf, seed_buf2, edt_buf, edt_out;
+  DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel, seed_buf, seed_buf2, edt_buf, edt_out, ror_buf, ror_out;
   bool clearance = false;  // aos_set_clearance
   std::vector<double> h_merged;
   PinVec<float> pin_facet_xy;

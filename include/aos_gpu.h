@@ -130,6 +130,17 @@ AOS_API aos_status aos_get_stage_times(aos_ctx *ctx, aos_stage_time *dst, int32_
 /* ---- grid geometry: getActiveBounds + generateOccupancyGrid header (seed_gen:874-890, 587-600) - */
 AOS_API aos_status aos_grid_geometry(const aos_seed_params *p, aos_grid_info *info);
 
+/* ---- ahead of the seam: pcl::RadiusOutlierRemoval of globalMapCallback (seed_gen:229-248; radius 0.2 m, 2
+ *      neighbours).  A point is kept iff at least min_neighbors OTHER points lie within `radius` in 3-D (squared
+ *      distance accumulated in float32 as FLANN's L2_Simple does, compared with radius*radius in double; the dense-
+ *      cloud branch of PCL 1.12, restated -- PCL is absent here, parity unpinned).  Non-finite points are dropped.
+ *      The survivors come back compacted in input order as 16-byte x,y,z,1 records in context-owned DEVICE memory
+ *      (valid until the next call of this function), ready to be passed to aos_seed_stage with AOS_MEM_DEVICE. -- */
+AOS_API aos_status aos_radius_outlier_removal(aos_ctx *ctx, const void *points, size_t n_points, uint32_t point_step,
+                                              uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem,
+                                              float radius, int32_t min_neighbors, const void **out_points,
+                                              size_t *n_out);
+
 /* ---- the seed-gen half: replaces the body of processPointCloud (seed_gen:452-579) up to and
  *      including clusterOccupiedCells / convertClustersToTreeRows' row extraction (:1309-1406).
  *      `points` is the post-RadiusOutlierRemoval cloud as PointCloud2 bytes: n_points records of

@@ -202,3 +202,27 @@ def gvd_stage(seeds: np.ndarray, skel_framed: np.ndarray, origin_x: float, origi
     )
     lib().orc_graph_free(C.byref(gr))
     return g
+
+
+def radius_outlier_removal(points: np.ndarray, radius: float = 0.2, min_neighbors: int = 2) -> np.ndarray:
+    """pcl::RadiusOutlierRemoval as globalMapCallback uses it (src/aos_seed_gen_node.cpp:229-248), dense-cloud branch
+    of PCL 1.12 restated (PCL is absent: PARITY UNPINNED): keep a point iff the (min_neighbors + 1)-th nearest
+    neighbour -- the query point is its own nearest -- has squared distance <= radius^2, the distance being FLANN's
+    L2_Simple<float>: ((dx*dx + dy*dy) + dz*dz) in float32, compared in double.  Brute force, O(N^2): small clouds
+    only.  Returns the boolean keep mask; non-finite points are dropped."""
+    p = np.ascontiguousarray(points[:, :3], dtype=np.float32)
+    n = len(p)
+    keep = np.zeros(n, bool)
+    fin = np.isfinite(p).all(axis=1)
+    r2 = float(np.float32(radius)) ** 2 if isinstance(radius, np.floating) else float(radius) * float(radius)
+    idx = np.nonzero(fin)[0]
+    q = p[idx]
+    for a in range(0, len(q), 512):
+        blk = q[a:a + 512]
+        dx = blk[:, None, 0] - q[None, :, 0]
+        dy = blk[:, None, 1] - q[None, :, 1]
+        dz = blk[:, None, 2] - q[None, :, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz            # float32 throughout
+        cnt = (d2.astype(np.float64) <= r2).sum(axis=1) - 1   # minus the query itself
+        keep[idx[a:a + 512]] = cnt >= min_neighbors
+    return keep
