@@ -60,3 +60,18 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
                         "-c", str(src), "-o", str(tmp_path / "abi.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cpp_example_links_against_the_library(tmp_path):
+    """examples/map_to_graph.cpp is what a node-side caller looks like: it must compile as C++17 and link against
+    libaos_gpu.so (running it needs a GPU: tests/test_gvd_gpu.py::test_cpp_example_runs)."""
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    exe = tmp_path / "map_to_graph"
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "map_to_graph.cpp"), "-L", os.path.dirname(lib.LIB_PATH), "-laos_gpu",
+                        "-Wl,-rpath," + os.path.dirname(lib.LIB_PATH), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

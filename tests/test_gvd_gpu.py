@@ -131,3 +131,27 @@ def test_inflation_radius_beyond_the_stencil(gpu_ctx, oracle):
     gpu_ctx.seed_stage(pl, pts)
     from helpers import assert_seed_parity
     assert_seed_parity(gpu_ctx, r)
+
+
+def test_cpp_example_runs(tmp_path, oracle):
+    """The C++ caller of examples/ (no Python in the loop) reports the oracle's counts."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "map_to_graph"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "map_to_graph.cpp"),
+                           "-L", os.path.dirname(lib.LIB_PATH), "-laos_gpu", "-Wl,-rpath," + os.path.dirname(lib.LIB_PATH), "-o", str(exe)])
+    spec = synth.config("SMALL", seed=1)
+    pts = synth.make_orchard(spec)
+    cloud = tmp_path / "cloud.bin"
+    pts.tofile(cloud)
+    po, _ = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    ref = _oracle_graph(oracle, r)
+    x0, y0 = spec.polygon[0]
+    x1, y1 = spec.polygon[2]
+    out = subprocess.run([str(exe), str(cloud), str(x0), str(y0), str(x1), str(y1)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert f"grid {r['w']} x {r['h']}" in out.stdout
+    assert f"{r['n_clusters']} clusters, {r['n_rows']} tree rows" in out.stdout
+    assert f"GvdGraph: {len(ref['nodes'])} nodes" in out.stdout and f"{len(ref['edges'])} edges" in out.stdout
