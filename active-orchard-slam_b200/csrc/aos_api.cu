@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 #include "aos_common.cuh"
@@ -13,6 +14,24 @@ using namespace aos;
 struct aos_ctx : public aos::Ctx {};
 
 namespace {
+
+// Host -> device upload of a point cloud.  Large uploads from different contexts (maps in flight on several host
+// threads) are serialised through one process-wide gate: concurrent copies would only share the PCIe link and
+// finish together, which keeps the threads in lockstep (all uploading, then all computing); one copy at a time runs
+// at the full link rate and staggers the threads, so the upload of one map overlaps the host/GPU stages of the others.
+std::mutex g_upload_gate;
+aos_status upload_points(aos_ctx *c, const void *points, size_t bytes, const void **dpoints) {
+  AOS_CUDA_OK(c, c->points_stage.reserve(bytes));
+  if (bytes >= ((size_t)64 << 20)) {
+    std::lock_guard<std::mutex> lock(g_upload_gate);
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, bytes, cudaMemcpyHostToDevice, c->stream));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  } else {
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  *dpoints = c->points_stage.p;
+  return AOS_OK;
+}
 
 // getActiveBounds, seed_gen:874-890
 void active_bounds(const aos_seed_params *p, float *minx, float *maxx, float *miny, float *maxy) {
@@ -307,9 +326,8 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   c->mark("start");
   const void *dpoints = points;
   if (points_mem == AOS_MEM_HOST && n_points) {
-    AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, st));
-    dpoints = c->points_stage.p;
+    s = upload_points(c, points, n_points * (size_t)point_step, &dpoints);
+    if (s != AOS_OK) return s;
   }
   c->mark("h2d_points");
   unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->misc.as<char>() + 1024);
@@ -403,9 +421,8 @@ aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band 
   c->mark("start");
   const void *dpoints = points;
   if (points_mem == AOS_MEM_HOST && n_points) {
-    AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, st));
-    dpoints = c->points_stage.p;
+    s = upload_points(c, points, n_points * (size_t)point_step, &dpoints);
+    if (s != AOS_OK) return s;
   }
   c->mark("h2d_points");
   unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->misc.as<char>() + 1024);
@@ -688,9 +705,8 @@ aos_status aos_radius_outlier_removal(aos_ctx *c, const void *points, size_t n_p
   c->mark("start");
   const void *dpoints = points;
   if (points_mem == AOS_MEM_HOST && n_points) {
-    AOS_CUDA_OK(c, c->points_stage.reserve(n_points * (size_t)point_step));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, n_points * (size_t)point_step, cudaMemcpyHostToDevice, c->stream));
-    dpoints = c->points_stage.p;
+    s = upload_points(c, points, n_points * (size_t)point_step, &dpoints);
+    if (s != AOS_OK) return s;
   }
   c->mark("h2d_points");
   s = run_ror(c, dpoints, n_points, point_step, off_x, off_y, off_z, radius, min_neighbors, n_out);

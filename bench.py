@@ -145,7 +145,19 @@ def bench_ours(args):
     gen_s = time.time() - t0
 
     ctxs = [lib.Context(local) for _ in range(T)]     # one context (own stream, own buffers) per map in flight
-    fetch_bufs = [{} for _ in range(T)]               # e2e result buffers, reused step after step
+    pitch = lib.load().aos_bits_pitch_words(gi.width)
+
+    def _result_grids():                               # e2e result buffers (published grids), pinned, reused every step
+        out = {}
+        for key in ("occ_bits", "skel_bits"):
+            try:
+                t = torch.empty((gi.height, pitch), dtype=torch.int32, pin_memory=True)
+            except RuntimeError:
+                t = torch.empty((gi.height, pitch), dtype=torch.int32)
+            out[key] = t.numpy().view(np.uint32)
+            out["_keep_" + key] = t
+        return out
+    fetch_bufs = [_result_grids() for _ in range(T)]
     pool = cf.ThreadPoolExecutor(max_workers=T)        # ctypes releases the GIL: host stages run on T cores
 
     def run_batch(steps, host=False):
