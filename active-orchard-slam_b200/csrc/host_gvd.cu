@@ -3,9 +3,11 @@
 // (gvd:84-128).  Host side: seed merge, VoronoiDiagram::compute (src/utils/voronoi_diagram.cpp:16-114, the
 // Subdiv2D replay of host_subdiv.cu); device side: k_graph.cu.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 
 #include "aos_common.cuh"
@@ -39,6 +41,8 @@ bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x,
   if (rw <= 0 || rh <= 0) return false;
   // cv::Subdiv2D(Rect): the Rect2f converts to the int Rect through saturate_cast<int> == cvRound
   // (round-half-even), OpenCV 4.5.4 as shipped with ROS 2 Humble (package.xml:48)
+  const bool dbg = getenv("AOS_DEBUG") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   Subdiv sd;
   sd.reserve((size_t)n);
   sd.init((int)lrint((double)rx), (int)lrint((double)ry), (int)lrint((double)rw), (int)lrint((double)rh));
@@ -51,7 +55,13 @@ bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x,
     y = std::max(ry + margin, std::min(ry + rh - margin, y));
     sd.insert(x, y);  // -1 where cv::Subdiv2D::insert throws: the reference skips the seed (vd:83-88)
   }
+  auto t1 = std::chrono::steady_clock::now();
   sd.voronoi_facets(facet_xy, facet_off);
+  if (dbg) {
+    auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[aos] subdiv: %d seeds, insert %.1f ms, voronoi+facets %.1f ms\n", n,
+            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
   return true;
 }
 

@@ -12,8 +12,8 @@
 // opencv_contrib's loops (1..rows-2, 1..cols-2).
 //
 // Convergence: the reference stops when a full (0,1) pair changes nothing; extra sub-iterations at the
-// fixed point are no-ops, so running whole launches until one deletes nothing in its owned region gives
-// the same image.  Launches are queued in batches; each launch first reads its predecessor's deletion
+// fixed point are no-ops, so running whole launches until the last pair of one deletes nothing in the owned
+// regions gives the same image.  Launches are queued in batches; each launch first reads its predecessor's deletion
 // counter and exits at once if that was zero, so the host synchronises once per batch, not per launch.
 #include "aos_common.cuh"
 
@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constan
           del &= xmask;
           if (y + P.y_off <= 0 || y + P.y_off >= P.gh - 1) del = 0;
           res = cC & ~del;
-          if (lane_owned && r >= kSub && r < kSub + kThinOwn && y >= P.cnt_r0 && y < P.cnt_r1) deleted_owned |= (del != 0);
+          // convergence = the LAST full (0,1) pair of this launch deleted nothing in the owned rows: that is the
+          // reference's stopping rule, and it spares the extra launch that would only confirm the fixed point
+          if (s >= kSub - 2 && lane_owned && r >= kSub && r < kSub + kThinOwn && y >= P.cnt_r0 && y < P.cnt_r1)
+            deleted_owned |= (del != 0);
         }
       }
       out[r * kTileBoxW + sl] = res;

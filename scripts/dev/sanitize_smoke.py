@@ -1,7 +1,7 @@
 """Small end-to-end pass over every kernel family for compute-sanitizer (memcheck): TINY map through
 aos_map_to_graph, ROR, EDT + clearance, band API with world 1, generic point layout."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "active-orchard-slam_b200")); sys.path.insert(0, ROOT)
 import numpy as np
 from aos_gpu import lib, synth, bands
