@@ -42,14 +42,8 @@ inline double tri_area(float ax, float ay, float bx, float by, float cx, float c
   return ((double)bx - ax) * ((double)cy - ay) - ((double)by - ay) * ((double)cx - ax);
 }
 
-inline int pt_in_circle3(float px, float py, float ax, float ay, float bx, float by, float cx, float cy) {
-  const double eps = FLT_EPSILON * 0.125;
-  double val = ((double)ax * ax + (double)ay * ay) * tri_area(bx, by, cx, cy, px, py);
-  val -= ((double)bx * bx + (double)by * by) * tri_area(ax, ay, cx, cy, px, py);
-  val += ((double)cx * cx + (double)cy * cy) * tri_area(ax, ay, bx, by, px, py);
-  val -= ((double)px * px + (double)py * py) * tri_area(ax, ay, bx, by, cx, cy);
-  return val > eps ? 1 : val < -eps ? -1 : 0;
-}
+// isPtInCircle3(pt, a, b, c) = sign of  |a|^2 A(b,c,pt) - |b|^2 A(a,c,pt) + |c|^2 A(a,b,pt) - |pt|^2 A(a,b,c)  with A =
+// tri_area and a dead zone of FLT_EPSILON / 8; evaluated inline in flip_around (its only caller).
 }  // namespace
 
 float g_outer_factor = 6.f;  // see aos_set_subdiv_outer_factor
@@ -144,39 +138,30 @@ int Subdiv::connect_edges(int a, int b) {
   return edge;
 }
 
-void Subdiv::swap_edges(int edge) {
-  int sedge = edge ^ 2;
-  int a = get_edge(edge, PREV_AROUND_ORG);
-  int b = get_edge(sedge, PREV_AROUND_ORG);
-  splice(edge, a);
-  splice(sedge, b);
-  set_edge_points(edge, dst(a), dst(b));
-  splice(edge, get_edge(a, NEXT_AROUND_LEFT));
-  splice(sedge, get_edge(b, NEXT_AROUND_LEFT));
-}
-
-int Subdiv::is_right_of(float px, float py, int edge) const {
-  const Vertex &o = vtx_[org(edge)], &d = vtx_[dst(edge)];
-  double cw = tri_area(px, py, d.x, d.y, o.x, o.y);
-  return (cw > 0) - (cw < 0);
-}
-
 int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
   int vertex = 0;
   const int max_edges = (int)(q_.size() * 4);
   if (px < tlx_ || py < tly_ || px >= brx_ || py >= bry_) return LOC_ERROR;  // cv::Exception(StsOutOfRange)
   int edge = recent_;
   int location = LOC_ERROR;
-  int right_of_curr = is_right_of(px, py, edge);
+  const QuadEdge *const q = q_.data();
+  const Vertex *const vtx = vtx_.data();
+  auto right_of = [q, vtx](float x, float y, int e) {  // isRightOf
+    const Vertex &o = vtx[q[e >> 2].pt[e & 3]], &d = vtx[q[e >> 2].pt[(e + 2) & 3]];
+    const double cw = tri_area(x, y, d.x, d.y, o.x, o.y);
+    return (cw > 0) - (cw < 0);
+  };
+  int right_of_curr = right_of(px, py, edge);
   if (right_of_curr > 0) {
     edge ^= 2;
     right_of_curr = -right_of_curr;
   }
   for (int i = 0; i < max_edges; ++i) {
-    int onext = q_[edge >> 2].next[edge & 3];
-    int dprev = get_edge(edge, PREV_AROUND_DST);
-    int right_of_onext = is_right_of(px, py, onext);
-    int right_of_dprev = is_right_of(px, py, dprev);
+    const int onext = q[edge >> 2].next[edge & 3];
+    int dprev = q[edge >> 2].next[(edge + PREV_AROUND_DST) & 3];
+    dprev = (dprev & ~3) + ((dprev + (PREV_AROUND_DST >> 4)) & 3);
+    const int right_of_onext = right_of(px, py, onext);
+    const int right_of_dprev = right_of(px, py, dprev);
     if (right_of_dprev > 0) {
       if (right_of_onext > 0 || (right_of_onext == 0 && right_of_curr == 0)) {
         location = LOC_INSIDE;
@@ -192,8 +177,14 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
         }
         right_of_curr = right_of_dprev;
         edge = dprev;
-      } else if (right_of_curr == 0 && is_right_of(vtx_[dst(onext)].x, vtx_[dst(onext)].y, edge) >= 0) {
-        edge ^= 2;
+      } else if (right_of_curr == 0) {
+        const Vertex &dn = vtx[q[onext >> 2].pt[(onext + 2) & 3]];
+        if (right_of(dn.x, dn.y, edge) >= 0) {
+          edge ^= 2;
+        } else {
+          right_of_curr = right_of_onext;
+          edge = onext;
+        }
       } else {
         right_of_curr = right_of_onext;
         edge = onext;
@@ -252,24 +243,74 @@ int Subdiv::insert(float px, float py) {
     curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
   } while (dst(curr_edge) != first_point);
   curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
+  flip_around(curr_edge, first_point, px, py);
+  return curr_point;
+}
+
+// The Lawson flips around the new point (the second loop of cv::Subdiv2D::insert): same tests, same order, same
+// splices.  Hot loop of the whole gvd half (about 55 flips per seed for seeds sorted along rows), so it works on raw
+// pointers (no re-loading of the vectors' data pointers after every store) and re-uses the orientation determinant
+// that isRightOf and isPtInCircle3 share.
+void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
+  QuadEdge *const q = q_.data();
+  Vertex *const vtx = vtx_.data();
   const int max_edges = (int)(q_.size() * 4);
+  auto gedge = [q](int edge, int type) {
+    edge = q[edge >> 2].next[(edge + type) & 3];
+    return (edge & ~3) + ((edge + (type >> 4)) & 3);
+  };
+  auto splice_raw = [q](int a, int b) {
+    int &a_next = q[a >> 2].next[a & 3];
+    int &b_next = q[b >> 2].next[b & 3];
+    const int a_rot = (a_next & ~3) + ((a_next + 1) & 3);
+    const int b_rot = (b_next & ~3) + ((b_next + 1) & 3);
+    int &a_rot_next = q[a_rot >> 2].next[a_rot & 3];
+    int &b_rot_next = q[b_rot >> 2].next[b_rot & 3];
+    std::swap(a_next, b_next);
+    std::swap(a_rot_next, b_rot_next);
+  };
+  const double pxx = (double)px * px + (double)py * py;
   for (int i = 0; i < max_edges; ++i) {
-    int temp_edge = get_edge(curr_edge, PREV_AROUND_ORG);
-    int temp_dst = dst(temp_edge);
-    int curr_org = org(curr_edge);
-    int curr_dst = dst(curr_edge);
-    if (is_right_of(vtx_[temp_dst].x, vtx_[temp_dst].y, curr_edge) > 0 &&
-        pt_in_circle3(vtx_[curr_org].x, vtx_[curr_org].y, vtx_[temp_dst].x, vtx_[temp_dst].y, vtx_[curr_dst].x,
-                      vtx_[curr_dst].y, vtx_[curr_point].x, vtx_[curr_point].y) < 0) {
-      swap_edges(curr_edge);
-      curr_edge = get_edge(curr_edge, PREV_AROUND_ORG);
+    const int temp_edge = gedge(curr_edge, PREV_AROUND_ORG);
+    const QuadEdge &qc = q[curr_edge >> 2];
+    const int curr_org = qc.pt[curr_edge & 3], curr_dst = qc.pt[(curr_edge + 2) & 3];
+    const int temp_dst = q[temp_edge >> 2].pt[(temp_edge + 2) & 3];
+    const Vertex &t = vtx[temp_dst], &o = vtx[curr_org], &d = vtx[curr_dst];
+    // isRightOf(t, curr_edge) = sign of triangleArea(t, dst, org); the same determinant is the third term of
+    // isPtInCircle3(pt = org, a = t, b = dst, c = p)
+    const double area_tdo = tri_area(t.x, t.y, d.x, d.y, o.x, o.y);
+    bool flip = false;
+    if (area_tdo > 0) {
+      const double eps = FLT_EPSILON * 0.125;
+      double val = ((double)t.x * t.x + (double)t.y * t.y) * tri_area(d.x, d.y, px, py, o.x, o.y);
+      val -= ((double)d.x * d.x + (double)d.y * d.y) * tri_area(t.x, t.y, px, py, o.x, o.y);
+      val += pxx * area_tdo;
+      val -= ((double)o.x * o.x + (double)o.y * o.y) * tri_area(t.x, t.y, d.x, d.y, px, py);
+      flip = val < -eps;
+    }
+    if (flip) {
+      // swapEdges(curr_edge)
+      const int sedge = curr_edge ^ 2;
+      const int a = temp_edge;  // == getEdge(curr_edge, PREV_AROUND_ORG)
+      const int b = gedge(sedge, PREV_AROUND_ORG);
+      splice_raw(curr_edge, a);
+      splice_raw(sedge, b);
+      {  // setEdgePoints(curr_edge, edgeDst(a), edgeDst(b))
+        const int no = q[a >> 2].pt[(a + 2) & 3], nd = q[b >> 2].pt[(b + 2) & 3];
+        q[curr_edge >> 2].pt[curr_edge & 3] = no;
+        q[curr_edge >> 2].pt[(curr_edge + 2) & 3] = nd;
+        vtx[no].first_edge = curr_edge;
+        vtx[nd].first_edge = curr_edge ^ 2;
+      }
+      splice_raw(curr_edge, gedge(a, NEXT_AROUND_LEFT));
+      splice_raw(sedge, gedge(b, NEXT_AROUND_LEFT));
+      curr_edge = gedge(curr_edge, PREV_AROUND_ORG);
     } else if (curr_org == first_point) {
       break;
     } else {
-      curr_edge = get_edge(q_[curr_edge >> 2].next[curr_edge & 3], PREV_AROUND_LEFT);
+      curr_edge = gedge(q[curr_edge >> 2].next[curr_edge & 3], PREV_AROUND_LEFT);
     }
   }
-  return curr_point;
 }
 
 // intersection of the bisectors of (org0,dst0) and (org1,dst1): float differences and sums, double solve

@@ -40,8 +40,7 @@ class Subdiv {
   void splice(int a, int b);
   void set_edge_points(int edge, int org, int dst);
   int connect_edges(int a, int b);
-  void swap_edges(int edge);
-  int is_right_of(float px, float py, int edge) const;
+  void flip_around(int curr_edge, int first_point, float px, float py);
   int locate(float px, float py, int *edge, int *vertex);
   static bool voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y);
   void calc_voronoi();
