@@ -155,3 +155,20 @@ def test_cpp_example_runs(tmp_path, oracle):
     assert f"grid {r['w']} x {r['h']}" in out.stdout
     assert f"{r['n_clusters']} clusters, {r['n_rows']} tree rows" in out.stdout
     assert f"GvdGraph: {len(ref['nodes'])} nodes" in out.stdout and f"{len(ref['edges'])} edges" in out.stdout
+
+
+def test_long_rows_graph(gpu_ctx, oracle):
+    """1 km rows: endpoint rays run for thousands of 0.1 m steps (the warp-parallel replay of `cur += 0.1`), float32
+    cluster sums pass 2^24 (BFS-order replay), and the graph has a few thousand nodes -- all bit-exact."""
+    spec = synth.OrchardSpec(extent_x=1000.0, extent_y=16.0, row_pitch=4.0, n_points=500_000, gap_prob=0.01,
+                             jitter=0.05, outlier_count=4, seed=12)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    assert r["cl_sumx"].max() >= (1 << 24) and r["n_rows"] >= 4
+    ref = _oracle_graph(oracle, r)
+    gpu_ctx.map_to_graph(pl, pts)
+    from helpers import assert_seed_selection_parity
+    assert_seed_selection_parity(gpu_ctx, r)
+    assert_graph_parity(gpu_ctx.graph(), ref)
+    assert len(ref["nodes"]) > 2000
