@@ -41,6 +41,7 @@ class OrchardSpec:
     clutter_frac: float = 0.08     # ground / canopy clutter outside the z window
     outlier_count: int = 12        # isolated in-window points
     seed: int = 0
+    rotation_deg: float = 0.0      # rows rotated about the centre of the extent (0 = parallel to x)
     grid_resolution: float = 0.05
     inflation_radius: float = 0.8
     exclusion: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
@@ -85,7 +86,17 @@ def tree_centres(spec: OrchardSpec, rng: np.random.Generator) -> np.ndarray:
     c = np.stack([cx.ravel(), cy.ravel()], axis=1)
     c += rng.uniform(-spec.jitter, spec.jitter, size=c.shape)
     keep = rng.random(len(c)) >= spec.gap_prob
-    return c[keep]
+    c = c[keep]
+    if spec.rotation_deg != 0.0:   # rotate the layout, keep the trees that stay well inside the extent
+        a = np.deg2rad(spec.rotation_deg)
+        mid = np.array([spec.origin_x + 0.5 * spec.extent_x, spec.origin_y + 0.5 * spec.extent_y])
+        rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        c = (c - mid) @ rot.T + mid
+        m = 3.0
+        inside = ((c[:, 0] > spec.origin_x + m) & (c[:, 0] < spec.origin_x + spec.extent_x - m) &
+                  (c[:, 1] > spec.origin_y + m) & (c[:, 1] < spec.origin_y + spec.extent_y - m))
+        c = c[inside]
+    return c
 
 
 def make_orchard(spec: OrchardSpec) -> np.ndarray:

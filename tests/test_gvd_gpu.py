@@ -100,7 +100,8 @@ def test_gvd_stage_needs_inputs(oracle):
 def test_sweep_of_maps_in_flight(oracle):
     """BASELINE config 5 in miniature: a sweep over row pitch / inflation radius / resolution, all maps in flight at
     once through aos_map_to_graph_batch (one context and host thread per map), each bit-exact against the oracle."""
-    sweep = [(3.5, 0.6, 0.05), (4.0, 0.8, 0.05), (5.0, 1.0, 0.05), (6.0, 0.8, 0.1), (4.5, 0.7, 0.1), (8.0, 1.0, 0.05)]
+    sweep = [(3.5, 0.6, 0.05), (4.0, 0.8, 0.05), (5.0, 1.0, 0.05), (6.0, 0.8, 0.1), (4.5, 0.7, 0.1), (8.0, 1.0, 0.05),
+             (4.0, 0.8, 0.025), (6.0, 0.8, 0.2)]   # config 4's resolution (R = 32 cells) and a coarse grid (R = 4)
     ctxs, prms, clouds, refs = [], [], [], []
     for i, (pitch, infl, res) in enumerate(sweep):
         spec = synth.OrchardSpec(extent_x=30.0, extent_y=24.0, row_pitch=pitch, n_points=90_000, outlier_count=4, seed=20 + i,
@@ -172,3 +173,20 @@ def test_long_rows_graph(gpu_ctx, oracle):
     assert_seed_selection_parity(gpu_ctx, r)
     assert_graph_parity(gpu_ctx.graph(), ref)
     assert len(ref["nodes"]) > 2000
+
+
+@pytest.mark.parametrize("rot,seed", [(17.0, 0), (45.0, 1), (90.0, 2), (-63.0, 3)])
+def test_rotated_orchards(gpu_ctx, oracle, rot, seed):
+    """Rows that are not parallel to the grid: diagonal skeletons (8-connected steps, BFS order), rays and row end
+    points in arbitrary directions, Voronoi cells of slanted seed lines -- the whole path against the oracle."""
+    spec = synth.OrchardSpec(extent_x=44.0, extent_y=40.0, row_pitch=5.0, n_points=260_000, outlier_count=5, seed=seed,
+                             rotation_deg=rot)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    assert r["n_rows"] >= 3
+    ref = _oracle_graph(oracle, r)
+    gpu_ctx.map_to_graph(pl, pts)
+    from helpers import assert_seed_parity
+    assert_seed_parity(gpu_ctx, r)
+    assert_graph_parity(gpu_ctx.graph(), ref)
