@@ -1000,8 +1000,9 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
         forked[side++] = true;
       }
       if (k < 3) {
-        if (smem > 48 * 1024)
-          AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // per-function attribute shared by every context: always ask for the largest class
+        AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(kRingN * 4 + class_words[2] * 4)));
         bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, smem, ls>>>(P, d_jobs + done, acc, offsets, root_cellpos,
                                                                             mask, gvisited, queue, centre);
       } else {

@@ -129,7 +129,10 @@ aos_status launch_inflate(Ctx *c, const uint32_t *in, uint32_t *out, uint32_t *o
   int words_used = (w + 31) >> 5;
   dim3 grid((words_used + kTileOwnW - 1) / kTileOwnW, (h + kInfRows - 1) / kInfRows);
   size_t smem = (size_t)box_h * kTileBoxW * 4;
-  AOS_CUDA_OK(c, cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // always the maximum (R = kMaxR): contexts on other host threads launch this kernel with other radii, and the
+  // attribute is per function, not per launch
+  AOS_CUDA_OK(c, cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)(kInfRows + 2 * kMaxR) * kTileBoxW * 4)));
   inflate_kernel<<<grid, kInfThreads, smem, c->stream>>>(tmap, P, out, out_border);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());

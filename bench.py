@@ -270,6 +270,112 @@ def bench_ours(args):
     return line
 
 
+def bench_sweep(args):
+    """BASELINE config 5: a sweep of 256 independent C2-size maps (row pitch in [4, 8] m, inflation 0.6 / 0.8 / 1.0 m),
+    map i on rank i mod N, each rank keeping several maps in flight.  One step = the whole sweep."""
+    import concurrent.futures as cf
+    import queue
+
+    import torch
+
+    from aos_gpu import dist as adist
+    from aos_gpu import lib, synth
+
+    rank, world, local = adist.env_rank_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_maps = 256
+    mine = adist.map_assignment(n_maps, world, rank)
+    ncpu = os.cpu_count() or 1
+    T = args.maps_in_flight if args.maps_in_flight > 0 else max(1, min(16, ncpu // max(world, 1), len(mine)))
+    specs, prms, clouds, hosts = [], [], [], []
+    for i in mine:
+        r = np.random.default_rng(5000 + i)
+        spec = synth.OrchardSpec(row_pitch=float(r.uniform(4.0, 8.0)), inflation_radius=float(r.choice([0.6, 0.8, 1.0])),
+                                 n_points=args.points or 2_000_000, seed=i)
+        specs.append(spec)
+        prms.append(make_params(lib, spec))
+        clouds.append(synth.make_orchard_torch(spec, dev))
+        h = torch.empty(clouds[-1].shape, dtype=torch.float32, pin_memory=True)
+        h.copy_(clouds[-1])
+        hosts.append(h.numpy())
+    torch.cuda.synchronize()
+    gi = lib.grid_geometry(prms[0])
+    cells = gi.width * gi.height
+    ctxs = [lib.Context(local) for _ in range(T)]
+    fetch = [{} for _ in range(T)]
+    pool = cf.ThreadPoolExecutor(max_workers=T)
+
+    def sweep(host):
+        todo = queue.SimpleQueue()
+        for k in range(len(mine)):
+            todo.put(k)
+        stats = []
+
+        def work(t):
+            torch.cuda.set_device(local)
+            n_nodes = 0
+            while True:
+                try:
+                    k = todo.get_nowait()
+                except queue.Empty:
+                    return n_nodes
+                info = ctxs[t].map_to_graph(prms[k], hosts[k] if host else clouds[k], fetch=fetch[t] if host else None)
+                n_nodes += (info["graph"] or {}).get("nodes", 0)
+        stats = list(pool.map(work, range(T)))
+        return sum(stats)
+
+    def timed(steps, host):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        w0 = time.perf_counter()
+        nodes = 0
+        for _ in range(steps):
+            nodes = sweep(host)
+        torch.cuda.synchronize()
+        ev1.record()
+        ev1.synchronize()
+        ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3)
+        return ms, nodes
+
+    for _ in range(args.warmup):
+        sweep(False)
+    l0 = sum(c.launch_count() for c in ctxs)
+    with ClockSampler(local) as clk:
+        dev_ms, nodes = timed(args.steps, False)
+    launches = (sum(c.launch_count() for c in ctxs) - l0) / max(args.steps, 1)
+    sweep(True)
+    e2e_ms, _ = timed(args.steps, True)
+    dev_ms, total_cells = adist.reduce_stats(dev_ms, cells * len(mine) * args.steps, device=dev)
+    e2e_ms, _ = adist.reduce_stats(e2e_ms, 0, device=dev)
+    if rank == 0:
+        n_pts = sum(int(c.shape[0]) for c in clouds)
+        line = {"metric": METRIC, "value": round(adist.throughput_mcells(total_cells, dev_ms), 1), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
+                "config": {"workload": f"C5: sweep of {n_maps} independent {gi.width}x{gi.height} maps @ 0.05 m (row pitch 4-8 m, "
+                                       "inflation 0.6/0.8/1.0 m, 2 M points each), map i on rank i mod N",
+                           "maps_in_flight": T, "host_cores": ncpu, "maps_per_s": round(n_maps * args.steps / (dev_ms * 1e-3), 1),
+                           "graph_nodes_rank0_sweep": int(nodes)},
+                "e2e": {"value": round(adist.throughput_mcells(total_cells, e2e_ms), 1), "unit": UNIT,
+                        "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_bytes_per_step": int(n_pts * 16),
+                        "d2h_bytes_per_step": None},
+                "gpu_launches": int(round(launches)), "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    pool.shutdown()
+    for c in ctxs:
+        c.close()
+
+
 def bench_bands(args):
     """BASELINE config 4: ONE grid row-band sharded over the ranks (strong scaling of the raster stages; clusters,
     seeds and graph finish on rank 0).  Not the default: `--shard bands`, normally with --workload C4."""
@@ -487,6 +593,8 @@ def main():
         bench_reference(args)
     elif args.shard == "bands":
         bench_bands(args)
+    elif args.workload.upper() == "C5":
+        bench_sweep(args)
     else:
         bench_ours(args)
 
