@@ -186,6 +186,7 @@ aos_status aos_get_stage_times(aos_ctx *c, aos_stage_time *dst, int32_t capacity
 
 aos_status aos_synchronize(aos_ctx *c) {
   if (!c) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
   AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return AOS_OK;
 }
@@ -530,6 +531,7 @@ aos_status aos_get_grid(aos_ctx *c, aos_grid_id which, aos_grid_fmt fmt, void *d
   }
   DevBuf *g = grid_buf(c, which);
   AOS_REQUIRE(c, g != nullptr, "unknown grid id");
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
   if (c->partial_grids && !(which == AOS_GRID_SKELETON || which == AOS_GRID_SKELETON_FRAMED ||
                             (which == AOS_GRID_OCCUPANCY && c->have_occ))) {
     set_error(c, "this grid was not produced on this context (aos_seed_stage_tail)");
@@ -573,6 +575,7 @@ aos_status aos_get_labels(aos_ctx *c, int32_t *dst, size_t dst_count, aos_mem ds
   if (!c->have_seed) return AOS_ERR_STATE;
   size_t cells = (size_t)c->P.w * c->P.h;
   if (dst_count < cells) return AOS_ERR_CAPACITY;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
   if (dst_mem == AOS_MEM_DEVICE) {
     aos_status s = launch_labels(c, dst);
     if (s != AOS_OK) return s;
