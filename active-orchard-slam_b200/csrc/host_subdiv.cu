@@ -289,21 +289,54 @@ void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
       flip = val < -eps;
     }
     if (flip) {
-      // swapEdges(curr_edge)
-      const int sedge = curr_edge ^ 2;
+      // swapEdges(curr_edge): splice(e, a); splice(s, b); setEdgePoints(e, dst(a), dst(b)); splice(e, Lnext(a));
+      // splice(s, Lnext(b)) with a = Oprev(e), b = Oprev(s).  In a triangulation the four splices touch twelve
+      // `next` slots whose final values follow from the initial ones (derivation in DESIGN.md section 4, "Host hot loop"); they are
+      // read once and written once here instead of going through four dependent read-modify-write rounds.  The
+      // guards check the local structure that derivation assumes; anything else takes the literal splice sequence.
+      const int e = curr_edge, sedge = curr_edge ^ 2;
       const int a = temp_edge;  // == getEdge(curr_edge, PREV_AROUND_ORG)
       const int b = gedge(sedge, PREV_AROUND_ORG);
-      splice_raw(curr_edge, a);
-      splice_raw(sedge, b);
-      {  // setEdgePoints(curr_edge, edgeDst(a), edgeDst(b))
+      int *const nx = &q[0].next[0];  // next[edge] = nx[(edge >> 2) * (sizeof(QuadEdge) / 4) + (edge & 3)]
+      constexpr int kStride = (int)(sizeof(QuadEdge) / sizeof(int));
+      auto slot = [nx](int edge) -> int & { return nx[(edge >> 2) * kStride + (edge & 3)]; };
+      auto rot = [](int edge) { return (edge & ~3) + ((edge + 1) & 3); };
+      auto invrot = [](int edge) { return (edge & ~3) + ((edge + 3) & 3); };
+      const int c = slot(e), d = slot(sedge);
+      const int ia = invrot(a), ib = invrot(b);
+      const int U = slot(ia), U2 = slot(ib);
+      const int la = rot(U), lb = rot(U2);
+      if (slot(a) == e && slot(b) == sedge && la == (d ^ 2) && lb == (c ^ 2) && slot(la) == (a ^ 2) && slot(lb) == (b ^ 2)) {
+        const int rc = rot(c), re = rot(e), rd = rot(d), rs = rot(sedge);
+        const int P = slot(rc), Q = slot(re), P2 = slot(rd), Q2 = slot(rs);
+        slot(e) = a ^ 2;
+        slot(a) = c;
+        slot(la) = e;
+        slot(sedge) = b ^ 2;
+        slot(b) = d;
+        slot(lb) = sedge;
+        slot(rc) = Q;
+        slot(re) = U;
+        slot(ia) = P;
+        slot(rd) = Q2;
+        slot(rs) = U2;
+        slot(ib) = P2;
         const int no = q[a >> 2].pt[(a + 2) & 3], nd = q[b >> 2].pt[(b + 2) & 3];
-        q[curr_edge >> 2].pt[curr_edge & 3] = no;
-        q[curr_edge >> 2].pt[(curr_edge + 2) & 3] = nd;
-        vtx[no].first_edge = curr_edge;
-        vtx[nd].first_edge = curr_edge ^ 2;
+        q[e >> 2].pt[e & 3] = no;
+        q[e >> 2].pt[(e + 2) & 3] = nd;
+        vtx[no].first_edge = e;
+        vtx[nd].first_edge = e ^ 2;
+      } else {
+        splice_raw(e, a);
+        splice_raw(sedge, b);
+        const int no = q[a >> 2].pt[(a + 2) & 3], nd = q[b >> 2].pt[(b + 2) & 3];
+        q[e >> 2].pt[e & 3] = no;
+        q[e >> 2].pt[(e + 2) & 3] = nd;
+        vtx[no].first_edge = e;
+        vtx[nd].first_edge = e ^ 2;
+        splice_raw(e, gedge(a, NEXT_AROUND_LEFT));
+        splice_raw(sedge, gedge(b, NEXT_AROUND_LEFT));
       }
-      splice_raw(curr_edge, gedge(a, NEXT_AROUND_LEFT));
-      splice_raw(sedge, gedge(b, NEXT_AROUND_LEFT));
       curr_edge = gedge(curr_edge, PREV_AROUND_ORG);
     } else if (curr_org == first_point) {
       break;
