@@ -623,21 +623,10 @@ aos_status aos_select_seeds(aos_ctx *c, int32_t *n_seeds, int32_t counts[3]) {
     set_error(c, "aos_seed_stage has not completed");
     return AOS_ERR_STATE;
   }
-  const SeedDeviceParams &P = c->P;
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
-  static const bool on_host = getenv("AOS_SEEDS_ON_HOST") != nullptr;  // debugging aid: the plain host loops
-  if (on_host) {
-    const size_t words = (size_t)P.pitch * P.h;
-    c->h_skel_bits.resize(words);
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_skel_bits.data(), c->g_skel.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
-    AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    host_select_seeds(c->h_skel_bits.data(), P.w, P.h, P.pitch, P.ox, P.oy, P.res, c->h_rows, P.poly, P.n_poly, &c->h_seeds,
-                      c->seed_counts, &c->h_rows_info);
-  } else {
-    aos_status s = device_select_seeds(c);
-    if (s != AOS_OK) return s;
-    host_rows_info(c->h_rows, &c->h_rows_info);
-  }
+  aos_status s = device_select_seeds(c);  // ray casts + first-come filters: k_seeds.cu
+  if (s != AOS_OK) return s;
+  host_rows_info(c->h_rows, &c->h_rows_info);
   c->have_seeds = true;
   c->mark("select_seeds");
   if (n_seeds) *n_seeds = (int32_t)(c->h_seeds.size() / 2);

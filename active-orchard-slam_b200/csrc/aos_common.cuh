@@ -213,9 +213,6 @@ aos_status launch_pack(Ctx *c, const int8_t *src, uint32_t *dst, int w, int h);
 aos_status launch_unpack(Ctx *c, const uint32_t *src, int8_t *dst, int w, int h);
 aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel, float min_length);
 aos_status launch_labels(Ctx *c, int32_t *dst);
-void host_select_seeds(const uint32_t *skel_bits, int w, int h, int pitch, double ox, double oy, float res,
-                       const std::vector<aos_tree_row> &rows, const double *poly, int n_poly,
-                       std::vector<double> *seeds, int counts[3], std::vector<double> *rows_info);
 void host_rows_info(const std::vector<aos_tree_row> &rows, std::vector<double> *rows_info);
 aos_status device_select_seeds(Ctx *c);
 void host_merge_seeds(const double *seeds, int n, std::vector<double> *out);
@@ -331,7 +328,6 @@ struct Ctx {
 
   // host seed selection (host_seeds.cu)
   bool have_seeds = false;
-  std::vector<uint32_t> h_skel_bits;  // un-framed skeleton, host copy for the ray casts
   std::vector<double> h_seeds;        // /voronoi_seeds, x,y pairs in publish order
   int seed_counts[3] = {0, 0, 0};     // virtual, ray, endpoint
   std::vector<double> h_rows_info;    // /exploration_tree_rows_info: start x,y,end x,y per row, sorted

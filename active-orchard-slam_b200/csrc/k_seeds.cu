@@ -8,7 +8,6 @@
 // on the host).  The reference then filters each candidate list first-come ("is an earlier accepted seed
 // closer than 0.5 m"): that greedy rule is resolved exactly by monotone rounds over a 0.5 m hash grid, as for
 // the graph nodes (k_graph.cu), and the survivors are emitted in order by a prefix sum.
-// host_seeds.cu holds the same logic as plain host code; AOS_SEEDS_ON_HOST=1 selects it (debugging aid).
 #include <math.h>
 
 #include <algorithm>
@@ -342,7 +341,7 @@ aos_status dedup_and_fetch(Ctx *c, double2 *d_pts, unsigned char *d_state, int n
 }
 }  // namespace
 
-// rows: all_tree_rows in cluster order (c->h_rows).  Fills c->h_seeds / c->seed_counts like host_select_seeds.
+// rows: all_tree_rows in cluster order (c->h_rows).  Fills c->h_seeds / c->seed_counts.
 aos_status device_select_seeds(Ctx *c) {
   cudaStream_t st = c->stream;
   const SeedDeviceParams &P = c->P;
