@@ -258,7 +258,7 @@ def bench_ours(args):
             "clocks": clk.summary(),
             "gen_s": round(gen_s, 2),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported beside the N = 1 line only
             line["cpu_baseline"] = cpu_baseline(args, cores=1, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
     if world > 1:
