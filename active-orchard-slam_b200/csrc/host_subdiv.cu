@@ -279,15 +279,13 @@ void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
     // isRightOf(t, curr_edge) = sign of triangleArea(t, dst, org); the same determinant is the third term of
     // isPtInCircle3(pt = org, a = t, b = dst, c = p)
     const double area_tdo = tri_area(t.x, t.y, d.x, d.y, o.x, o.y);
-    bool flip = false;
-    if (area_tdo > 0) {
-      const double eps = FLT_EPSILON * 0.125;
-      double val = ((double)t.x * t.x + (double)t.y * t.y) * tri_area(d.x, d.y, px, py, o.x, o.y);
-      val -= ((double)d.x * d.x + (double)d.y * d.y) * tri_area(t.x, t.y, px, py, o.x, o.y);
-      val += pxx * area_tdo;
-      val -= ((double)o.x * o.x + (double)o.y * o.y) * tri_area(t.x, t.y, d.x, d.y, px, py);
-      flip = val < -eps;
-    }
+    // evaluated unconditionally: the two data-dependent tests collapse into one branch
+    const double eps = FLT_EPSILON * 0.125;
+    double val = ((double)t.x * t.x + (double)t.y * t.y) * tri_area(d.x, d.y, px, py, o.x, o.y);
+    val -= ((double)d.x * d.x + (double)d.y * d.y) * tri_area(t.x, t.y, px, py, o.x, o.y);
+    val += pxx * area_tdo;
+    val -= ((double)o.x * o.x + (double)o.y * o.y) * tri_area(t.x, t.y, d.x, d.y, px, py);
+    const bool flip = (area_tdo > 0) & (val < -eps);
     if (flip) {
       // swapEdges(curr_edge): splice(e, a); splice(s, b); setEdgePoints(e, dst(a), dst(b)); splice(e, Lnext(a));
       // splice(s, Lnext(b)) with a = Oprev(e), b = Oprev(s).  In a triangulation the four splices touch twelve
