@@ -94,6 +94,45 @@ def run_thinning(backend, band: Band, rank: int, world: int, dist, max_launches:
     return launches
 
 
+def run_thinning_p2p(backend, band: Band, rank: int, world: int, dist, device=None, max_launches: int = 100000) -> int:
+    """Thinning with the halo exchange FUSED into the kernel (aos_band_thin_launch_p2p): no send/recv.  Every rank
+    publishes handles of its two ping-pong buffers, maps those of its neighbours (CUDA IPC: peer memory over
+    NVLink), and each launch stores the band's edge rows straight into the neighbour's destination buffer.  The
+    only collective left is the all-reduce(MAX) of the "deleted" flags, which also orders a launch's peer stores
+    before the neighbour's next launch reads them.
+
+    Backend protocol (the numpy/shared-memory backend of tests/test_bands_cpu.py implements the same):
+        export_handle(buffer) -> bytes (64)     import_handle(side, buffer, handle, peer_first_global_row)
+        thin_launch_p2p() -> bool
+    """
+    import torch
+    if world > 1:
+        mine = torch.tensor(list(backend.export_handle(0) + backend.export_handle(1)) +
+                            list(int(band.first_global_row).to_bytes(8, "little", signed=True)),
+                            dtype=torch.uint8, device=device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        for side, peer in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= peer < world:
+                raw = bytes(allh[peer].cpu().tolist())
+                first = int.from_bytes(raw[128:136], "little", signed=True)
+                backend.import_handle(side, 0, raw[:64], first)
+                backend.import_handle(side, 1, raw[64:128], first)
+        # the all_gather doubles as the barrier this needs: a rank leaves it only after EVERY rank has entered, i.e.
+        # finished aos_band_raster, so nobody's buffers are still being written when the first peer stores arrive
+    launches = 0
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    for _ in range(max_launches):
+        deleted = bool(backend.thin_launch_p2p())   # returns after the launch (and its peer stores) completed
+        launches += 1
+        flag.fill_(1 if deleted else 0)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) == 0:
+            break
+    return launches
+
+
 def gather_rows(local, band: Band, height: int, rank: int, world: int, dist):
     """Band rows of every rank -> the full [height, pitch] grid on rank 0 (None elsewhere)."""
     import torch
@@ -139,17 +178,30 @@ class LibBackend:
     def thin_launch(self):
         return self.ctx.band_thin_launch()
 
+    def export_handle(self, buffer):
+        return self.ctx.band_ipc_export(buffer)
 
-def banded_map_to_graph(ctx, params, points, rank: int, world: int, dist, device_index: int):
+    def import_handle(self, side, buffer, handle, peer_first_global_row):
+        self.ctx.band_ipc_import(side, buffer, handle, peer_first_global_row)
+
+    def thin_launch_p2p(self):
+        return self.ctx.band_thin_launch_p2p()
+
+
+def banded_map_to_graph(ctx, params, points, rank: int, world: int, dist, device_index: int, halo: str = "nccl"):
     """The whole path with the raster stages row-band sharded; results (as after aos_map_to_graph) on rank 0's
-    context.  `points`: this rank's points (any superset of the points falling into its local rows)."""
+    context.  `points`: this rank's points (any superset of the points falling into its local rows).
+    halo: "nccl" = send/recv of the halo rows between launches, "p2p" = stores into peer memory from the kernel."""
     import torch
     from . import lib
     gi = lib.grid_geometry(params)
     band = band_for(gi.height, world, rank, ctx.band_halo_rows(params))
     ctx.band_raster(params, band, points)
     be = LibBackend(ctx)
-    launches = run_thinning(be, band, rank, world, dist)
+    if halo == "p2p":
+        launches = run_thinning_p2p(be, band, rank, world, dist, device=torch.device("cuda", device_index))
+    else:
+        launches = run_thinning(be, band, rank, world, dist)
     skel = gather_rows(be.skeleton(), band, gi.height, rank, world, dist)
     occ = gather_rows(be.grid(lib.GRID_OCCUPANCY), band, gi.height, rank, world, dist)
     info = None

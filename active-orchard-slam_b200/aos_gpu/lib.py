@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
     "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_set_subdiv_outer_factor",
-    "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_grid_device", "aos_seed_stage_tail",
+    "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_ipc_export", "aos_band_ipc_import",
+    "aos_band_thin_launch_p2p", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
 
 
@@ -154,6 +155,9 @@ def load() -> C.CDLL:
     L.aos_band_raster.argtypes = [vp, C.POINTER(CSeedParams), C.POINTER(CBand), vp, sz, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_uint32, C.c_int]
     L.aos_band_thin_launch.argtypes = [vp, C.POINTER(i32)]
+    L.aos_band_ipc_export.argtypes = [vp, i32, vp]
+    L.aos_band_ipc_import.argtypes = [vp, i32, i32, vp, i32]
+    L.aos_band_thin_launch_p2p.argtypes = [vp, C.POINTER(i32)]
     L.aos_band_grid_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.aos_seed_stage_tail.argtypes = [vp, C.POINTER(CSeedParams), vp, vp]
     L.aos_map_to_graph_batch.argtypes = [C.POINTER(CBatchItem), i32, i32]
@@ -380,6 +384,25 @@ class Context:
     def band_thin_launch(self) -> bool:
         d = C.c_int32()
         self._check(self.L.aos_band_thin_launch(self.h, C.byref(d)), "aos_band_thin_launch")
+        return bool(d.value)
+
+    def band_ipc_export(self, buffer: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._check(self.L.aos_band_ipc_export(self.h, buffer, h), "aos_band_ipc_export")
+        return bytes(h)
+
+    def band_ipc_import(self, side: int, buffer: int, handle: bytes, peer_first_global_row: int):
+        cache = self.__dict__.setdefault("_ipc_imported", {})
+        if cache.get((side, buffer)) == (handle, peer_first_global_row):
+            return          # same allocation as last map: the mapping is still open
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        cache.pop((side, buffer), None)
+        self._check(self.L.aos_band_ipc_import(self.h, side, buffer, h, peer_first_global_row), "aos_band_ipc_import")
+        cache[(side, buffer)] = (handle, peer_first_global_row)
+
+    def band_thin_launch_p2p(self) -> bool:
+        d = C.c_int32()
+        self._check(self.L.aos_band_thin_launch_p2p(self.h, C.byref(d)), "aos_band_thin_launch_p2p")
         return bool(d.value)
 
     def band_grid_device(self, which: int):

@@ -133,6 +133,11 @@ void aos_destroy(aos_ctx *c) {
                     &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf,
                     &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2, &c->edt_buf, &c->edt_out, &c->ror_buf, &c->ror_out};
   for (DevBuf *b : bufs) b->release();
+  for (int s = 0; s < 2; ++s)
+    for (int b = 0; b < 2; ++b)
+      if (c->band_peer[s][b]) cudaIpcCloseMemHandle(c->band_peer[s][b]);
+  c->band_thin[0].release();
+  c->band_thin[1].release();
   c->graph.release();
   c->pin_facet_xy.release();
   c->pin_enext.release();
@@ -317,6 +322,8 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   const size_t gbytes = (size_t)P.pitch * P.h * 4;
   DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch};
   for (DevBuf *g : grids) AOS_CUDA_OK(c, g->reserve(gbytes));
+  AOS_CUDA_OK(c, c->band_thin[0].reserve(gbytes));
+  AOS_CUDA_OK(c, c->band_thin[1].reserve(gbytes));
   AOS_CUDA_OK(c, c->misc.reserve(4096));
   cudaStream_t st = c->stream;
   AOS_CUDA_OK(c, cudaMemsetAsync(c->g_raw.p, 0, gbytes, st));
@@ -413,6 +420,8 @@ aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band 
   const size_t gbytes = (size_t)P.pitch * P.h * 4;
   DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_scratch};
   for (DevBuf *g : grids) AOS_CUDA_OK(c, g->reserve(gbytes));
+  AOS_CUDA_OK(c, c->band_thin[0].reserve(gbytes));
+  AOS_CUDA_OK(c, c->band_thin[1].reserve(gbytes));
   AOS_CUDA_OK(c, c->misc.reserve(4096));
   cudaStream_t st = c->stream;
   AOS_CUDA_OK(c, cudaMemsetAsync(c->g_raw.p, 0, gbytes, st));
@@ -436,9 +445,12 @@ aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band 
   c->band_gh = 0;  // the launchers read the band geometry only while a band call is running
   if (s != AOS_OK) return s;
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_open.p, gbytes, cudaMemcpyDeviceToDevice, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->band_thin[0].p, c->g_open.p, gbytes, cudaMemcpyDeviceToDevice, st));
   c->mark("open");
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
   c->band_thin_launches = 0;
+  c->band_cur = 0;
+  c->band_p2p = false;
   c->have_band = true;
   return AOS_OK;
 }
@@ -449,11 +461,12 @@ aos_status aos_band_thin_launch(aos_ctx *c, int32_t *deleted) {
     set_error(c, "aos_band_raster has not completed");
     return AOS_ERR_STATE;
   }
+  AOS_REQUIRE(c, !c->band_p2p, "this band is being thinned with aos_band_thin_launch_p2p");
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
   const SeedDeviceParams &P = c->band_P;
   int *d_count = c->misc.as<int>() + 64;
   aos_status s = launch_thin_once(c, c->g_skel.as<uint32_t>(), c->g_scratch.as<uint32_t>(), P.w, P.h, c->band_y_off,
-                                  c->band_gi.height, c->band_cnt_r0, c->band_cnt_r1, d_count);
+                                  c->band_gi.height, c->band_cnt_r0, c->band_cnt_r1, d_count, nullptr);
   if (s != AOS_OK) return s;
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->g_skel.p, c->g_scratch.p, (size_t)P.pitch * P.h * 4, cudaMemcpyDeviceToDevice, c->stream));
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -463,11 +476,81 @@ aos_status aos_band_thin_launch(aos_ctx *c, int32_t *deleted) {
   return AOS_OK;
 }
 
+// ---- fused halo exchange over peer memory -------------------------------------------------------------------
+aos_status aos_band_ipc_export(aos_ctx *c, int32_t buffer, unsigned char *handle) {
+  if (!c || !handle || (buffer != 0 && buffer != 1)) return AOS_ERR_INVALID;
+  if (!c->have_band) return AOS_ERR_STATE;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == AOS_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  AOS_CUDA_OK(c, cudaIpcGetMemHandle(&h, c->band_thin[buffer].p));
+  memcpy(handle, &h, sizeof(h));
+  return AOS_OK;
+}
+
+aos_status aos_band_ipc_import(aos_ctx *c, int32_t side, int32_t buffer, const unsigned char *handle,
+                               int32_t peer_first_global_row) {
+  if (!c || !handle || (side != 0 && side != 1) || (buffer != 0 && buffer != 1)) return AOS_ERR_INVALID;
+  if (!c->have_band) return AOS_ERR_STATE;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  if (c->band_peer[side][buffer]) {
+    cudaIpcCloseMemHandle(c->band_peer[side][buffer]);
+    c->band_peer[side][buffer] = nullptr;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  AOS_CUDA_OK(c, cudaIpcOpenMemHandle(&c->band_peer[side][buffer], h, cudaIpcMemLazyEnablePeerAccess));
+  c->band_peer_first_row[side] = peer_first_global_row;
+  return AOS_OK;
+}
+
+aos_status aos_band_thin_launch_p2p(aos_ctx *c, int32_t *deleted) {
+  if (!c) return AOS_ERR_INVALID;
+  if (!c->have_band) {
+    set_error(c, "aos_band_raster has not completed");
+    return AOS_ERR_STATE;
+  }
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  const SeedDeviceParams &P = c->band_P;
+  const aos_band &B = c->band;
+  const bool has_lo = B.halo_lo > 0, has_hi = B.halo_hi > 0;
+  AOS_REQUIRE(c, c->band_p2p || c->band_thin_launches == 0, "this band is being thinned with aos_band_thin_launch");
+  const int nxt = c->band_cur ^ 1;  // every rank flips in lockstep, so the neighbours' destination has the same index
+  AOS_REQUIRE(c, (!has_lo || c->band_peer[0][nxt]) && (!has_hi || c->band_peer[1][nxt]),
+              "neighbour buffers not imported (aos_band_ipc_import)");
+  AOS_REQUIRE(c, B.rows >= kThinSubIters, "band lower than the thinning halo");
+  ThinHalo H;
+  if (has_lo) {
+    H.peer_lo = static_cast<uint32_t *>(c->band_peer[0][nxt]);
+    H.push_lo_r0 = B.halo_lo;
+    H.push_lo_shift = c->band_y_off - c->band_peer_first_row[0];
+    H.skip_lo_r0 = B.halo_lo - kThinSubIters;
+  }
+  if (has_hi) {
+    H.peer_hi = static_cast<uint32_t *>(c->band_peer[1][nxt]);
+    H.push_hi_r0 = B.halo_lo + B.rows - kThinSubIters;
+    H.push_hi_shift = c->band_y_off - c->band_peer_first_row[1];
+    H.skip_hi_r0 = B.halo_lo + B.rows;
+  }
+  uint32_t *bufs[2] = {c->band_thin[0].as<uint32_t>(), c->band_thin[1].as<uint32_t>()};
+  int *d_count = c->misc.as<int>() + 64;
+  aos_status s = launch_thin_once(c, bufs[c->band_cur], bufs[nxt], P.w, P.h, c->band_y_off, c->band_gi.height, c->band_cnt_r0,
+                                  c->band_cnt_r1, d_count, &H);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  c->band_cur = nxt;
+  c->band_p2p = true;
+  ++c->band_thin_launches;
+  if (deleted) *deleted = c->h_flag[0] != 0;
+  return AOS_OK;
+}
+
 aos_status aos_band_grid_device(aos_ctx *c, aos_grid_id which, uint32_t **bits, int32_t *pitch_words, int32_t *local_rows) {
   if (!c || !bits) return AOS_ERR_INVALID;
   if (!c->have_band) return AOS_ERR_STATE;
   AOS_REQUIRE(c, which >= AOS_GRID_RAW && which <= AOS_GRID_SKELETON, "grid not available in band mode");
-  *bits = grid_buf(c, which)->as<uint32_t>();
+  *bits = (which == AOS_GRID_SKELETON && c->band_p2p) ? c->band_thin[c->band_cur].as<uint32_t>() : grid_buf(c, which)->as<uint32_t>();
   if (pitch_words) *pitch_words = c->band_P.pitch;
   if (local_rows) *local_rows = c->band_P.h;
   return AOS_OK;

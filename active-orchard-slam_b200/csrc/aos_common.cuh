@@ -201,8 +201,13 @@ aos_status launch_bin(Ctx *c, const SeedDeviceParams &P, const void *points, siz
 aos_status launch_inflate(Ctx *c, const uint32_t *in, uint32_t *out, uint32_t *out_border, int w, int h, int R);
 aos_status launch_open(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h);
 aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters);
+struct ThinHalo {  // fused halo exchange of a row band, see ThinParams in k_thin.cu
+  uint32_t *peer_lo = nullptr, *peer_hi = nullptr;
+  int push_lo_r0 = 0, push_lo_shift = 0, push_hi_r0 = 0, push_hi_shift = 0;
+  int skip_lo_r0 = -1, skip_hi_r0 = -1;
+};
 aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, int h, int y_off, int gh, int cnt_r0,
-                            int cnt_r1, int *d_count);
+                            int cnt_r1, int *d_count, const ThinHalo *halo);
 aos_status run_ror(Ctx *c, const void *dpoints, size_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, float radius,
                    int min_neighbors, size_t *n_out);
 aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *nearest, int32_t *dist2);
@@ -291,6 +296,12 @@ struct Ctx {
   SeedDeviceParams band_P{};
   aos_grid_info band_gi{};
   int band_thin_launches = 0;
+  DevBuf band_thin[2];                    // p2p mode: dedicated ping-pong planes (exported over CUDA IPC, so no other
+                                          // stage may ever re-allocate them)
+  int band_cur = 0;                       // which of band_thin[] holds the current thinning image
+  bool band_p2p = false;                  // a p2p launch has run since aos_band_raster
+  void *band_peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [lo/hi neighbour][buffer 0/1], IPC-mapped
+  int band_peer_first_row[2] = {0, 0};    // neighbour's global row of its local row 0
   bool partial_grids = false, have_occ = false;  // after aos_seed_stage_tail only some grids exist
 
   // seed stage state

@@ -54,6 +54,13 @@ struct ThinParams {
   int w, h, pitch;
   int y_off, gh;       // row-band mode: global row of local row 0, global height
   int cnt_r0, cnt_r1;  // local rows whose deletions count towards convergence (the band without its halo)
+  // fused halo exchange (aos_band_thin_launch_p2p): the band's first / last kThinSubIters rows are ALSO stored into
+  // the neighbouring GPU's destination buffer (peer memory over NVLink: its halo rows next to its band), and the
+  // local halo rows the neighbours provide are not written here.  Null pointers / empty ranges switch it off.
+  uint32_t *peer_lo, *peer_hi;       // neighbour's destination grid (same pitch), or null
+  int push_lo_r0, push_lo_shift;     // local rows [push_lo_r0, +kSub) go to peer_lo row (local + push_lo_shift)
+  int push_hi_r0, push_hi_shift;
+  int skip_lo_r0, skip_hi_r0;        // local rows [skip_*_r0, +kSub) are provided by the neighbour (-1: none)
 };
 
 __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -137,7 +144,14 @@ __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constan
   for (int r = kSub + warp; r < kSub + kThinOwn; r += kThinThreads / 32) {
     int y = y0 + r;
     if (y >= P.h) break;
-    if (lane_owned && cw < P.pitch) dst[(size_t)y * P.pitch + cw] = fin[r * kTileBoxW + sl];
+    if (lane_owned && cw < P.pitch) {
+      const uint32_t v = fin[r * kTileBoxW + sl];
+      const bool from_lo = P.skip_lo_r0 >= 0 && y >= P.skip_lo_r0 && y < P.skip_lo_r0 + kSub;
+      const bool from_hi = P.skip_hi_r0 >= 0 && y >= P.skip_hi_r0 && y < P.skip_hi_r0 + kSub;
+      if (!from_lo && !from_hi) dst[(size_t)y * P.pitch + cw] = v;
+      if (P.peer_lo && y >= P.push_lo_r0 && y < P.push_lo_r0 + kSub) P.peer_lo[(size_t)(y + P.push_lo_shift) * P.pitch + cw] = v;
+      if (P.peer_hi && y >= P.push_hi_r0 && y < P.push_hi_r0 + kSub) P.peer_hi[(size_t)(y + P.push_hi_shift) * P.pitch + cw] = v;
+    }
   }
   if (__any_sync(0xffffffffu, deleted_owned) && lane == 0) atomicOr(&s_deleted, 1);
   __syncthreads();
@@ -148,8 +162,18 @@ __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constan
 // refreshes the kSub halo rows next to the band from the neighbouring GPUs between launches.  d_count receives the
 // number of CTAs that deleted something inside rows [cnt_r0, cnt_r1).
 aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, int h, int y_off, int gh, int cnt_r0,
-                            int cnt_r1, int *d_count) {
-  ThinParams P{w, h, pitch_words_for(w), y_off, gh, cnt_r0, cnt_r1};
+                            int cnt_r1, int *d_count, const ThinHalo *halo) {
+  ThinParams P{w, h, pitch_words_for(w), y_off, gh, cnt_r0, cnt_r1, nullptr, nullptr, 0, 0, 0, 0, -1, -1};
+  if (halo) {
+    P.peer_lo = halo->peer_lo;
+    P.peer_hi = halo->peer_hi;
+    P.push_lo_r0 = halo->push_lo_r0;
+    P.push_lo_shift = halo->push_lo_shift;
+    P.push_hi_r0 = halo->push_hi_r0;
+    P.push_hi_shift = halo->push_hi_shift;
+    P.skip_lo_r0 = halo->skip_lo_r0;
+    P.skip_hi_r0 = halo->skip_hi_r0;
+  }
   CUtensorMap map_src;
   if (!make_bitgrid_tmap(&map_src, src, P.pitch, h, kTileBoxW, kThinBox)) {
     set_error(c, "cuTensorMapEncodeTiled failed (thin)");
@@ -166,7 +190,7 @@ aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, i
 
 // img holds the input; on return *result_in_scratch says which of (img, scratch) holds the skeleton.
 aos_status launch_thin(Ctx *c, uint32_t *img, uint32_t *scratch, int w, int h, int *launches, int *subiters) {
-  ThinParams P{w, h, pitch_words_for(w), 0, h, 0, h};
+  ThinParams P{w, h, pitch_words_for(w), 0, h, 0, h, nullptr, nullptr, 0, 0, 0, 0, -1, -1};
   CUtensorMap map_img, map_scr;
   if (!make_bitgrid_tmap(&map_img, img, P.pitch, h, kTileBoxW, kThinBox) ||
       !make_bitgrid_tmap(&map_scr, scratch, P.pitch, h, kTileBoxW, kThinBox)) {

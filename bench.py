@@ -416,7 +416,10 @@ def bench_bands(args):
         t["raster"] = time.perf_counter() - t0
         be = bands.LibBackend(ctx)
         t0 = time.perf_counter()
-        launches = bands.run_thinning(be, band, rank, world, dist)
+        if args.halo == "p2p":
+            launches = bands.run_thinning_p2p(be, band, rank, world, dist, device=dev)
+        else:
+            launches = bands.run_thinning(be, band, rank, world, dist)
         torch.cuda.synchronize()
         t["thin+halo"] = time.perf_counter() - t0
         t0 = time.perf_counter()
@@ -461,9 +464,11 @@ def bench_bands(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: ONE {gi.width}x{gi.height} grid @ {spec.grid_resolution} m row-band "
                                        f"sharded over {world} GPU(s), {int(n_local.item())} points in total (halo overlap "
-                                       f"included), halo {ctx.band_halo_rows(params)} rows, NCCL send/recv of 8 rows per "
-                                       "neighbour and thinning launch",
-                           "shard": "bands", "thin_launches": launches,
+                                       f"included), halo {ctx.band_halo_rows(params)} rows, " +
+                                       ("8 edge rows per neighbour stored into its peer-mapped buffer by the thinning kernel "
+                                        "(NVLink P2P), flags all-reduced" if args.halo == "p2p" else
+                                        "NCCL send/recv of 8 rows per neighbour and thinning launch"),
+                           "shard": "bands", "halo": args.halo, "thin_launches": launches,
                            "graph": None if g is None else {"nodes": int(g["n_nodes"]), "edges": int(g["n_edges"])}},
                 "stages_ms_rank0": {k: round(v, 3) for k, v in acc.items()},
                 "raster_stages": {"ms": round(raster_ms, 3), "value": round(cells / (raster_ms * 1e-3) / 1e6, 1), "unit": UNIT},
@@ -584,6 +589,8 @@ def main():
     ap.add_argument("--points", type=int, default=None, help="override the workload's point count")
     ap.add_argument("--maps-in-flight", type=int, default=0,
                     help="independent maps processed concurrently per GPU (0 = min(16, host cores / ranks))")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="--shard bands: p2p = halo rows stored into peer memory by the thinning kernel; nccl = send/recv")
     ap.add_argument("--shard", default="maps", choices=["maps", "bands"],
                     help="maps: independent maps per GPU (default, weak scaling); bands: one grid row-band sharded")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")

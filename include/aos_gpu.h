@@ -283,7 +283,22 @@ AOS_API aos_status aos_band_raster(aos_ctx *ctx, const aos_seed_params *p, const
                                    size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y,
                                    uint32_t off_z, aos_mem points_mem);
 AOS_API aos_status aos_band_thin_launch(aos_ctx *ctx, int32_t *deleted);
-/* Device pointer of a LOCAL grid (AOS_GRID_RAW .. AOS_GRID_SKELETON): local row r is global row row0 - halo_lo + r. */
+/* Fused halo exchange over peer memory (NVLink P2P), the variant without NCCL send/recv: every rank exports its two
+ * thinning buffers as CUDA IPC handles, imports those of its lower (side 0) and upper (side 1) neighbour, and
+ * aos_band_thin_launch_p2p then runs the same launch, except that the kernel stores the band's first / last 8 rows
+ * straight into the neighbour's destination buffer (its halo rows) and leaves its own halo rows to the neighbours.
+ * The buffers alternate launch by launch on every rank in lockstep; the caller only has to all-reduce the
+ * `deleted` flags between launches (that also orders the peer stores before the next launch reads them).
+ * The two buffers are dedicated planes of the context (allocated by aos_band_raster, re-allocated only when a
+ * LARGER band is rasterised -- export and import again then; handles of an unchanged allocation stay valid from
+ * map to map).  Export after this rank's aos_band_raster, launch after EVERY rank's aos_band_raster has returned
+ * (e.g. exchange the handles with an all-gather every map).  One band uses one of the two launch calls, not both. */
+#define AOS_IPC_HANDLE_BYTES 64
+AOS_API aos_status aos_band_ipc_export(aos_ctx *ctx, int32_t buffer, unsigned char *handle /* [AOS_IPC_HANDLE_BYTES] */);
+AOS_API aos_status aos_band_ipc_import(aos_ctx *ctx, int32_t side, int32_t buffer, const unsigned char *handle,
+                                       int32_t peer_first_global_row);
+AOS_API aos_status aos_band_thin_launch_p2p(aos_ctx *ctx, int32_t *deleted);
+/* Device pointer of a LOCAL grid (AOS_GRID_RAW .. AOS_GRID_SKELETON; the skeleton is the current thinning image): local row r is global row row0 - halo_lo + r. */
 AOS_API aos_status aos_band_grid_device(aos_ctx *ctx, aos_grid_id which, uint32_t **bits, int32_t *pitch_words,
                                         int32_t *local_rows);
 /* Finish the seed stage from gathered full-size bit grids in device memory (pitch aos_bits_pitch_words(width)):

@@ -51,6 +51,65 @@ class NumpyBackend:
         return bool(deleted[b.halo_lo:b.halo_lo + b.rows].any())
 
 
+class SharedMemBackend:
+    """The p2p protocol of bands.run_thinning_p2p on CPU: the two ping-pong buffers are POSIX shared-memory blocks
+    (the "IPC handle" is the block's name), a launch writes its band's edge rows into the neighbours' destination
+    block and leaves its own halo rows next to the band to them -- what thin_kernel does through peer memory."""
+
+    def __init__(self, local, band, gh):
+        from multiprocessing import shared_memory
+        self.band, self.gh, self.shape = band, gh, local.shape
+        self.shm = [shared_memory.SharedMemory(create=True, size=local.size) for _ in range(2)]
+        self.buf = [np.ndarray(local.shape, np.uint8, buffer=m.buf) for m in self.shm]
+        self.buf[0][:] = local
+        self.buf[1][:] = 0xEE                     # never-written rows must not matter
+        self.cur = 0
+        self.peer, self.peer_shm, self.peer_first = {}, [], {}
+
+    def export_handle(self, buffer):
+        return self.shm[buffer].name.encode().ljust(64, b"\0")
+
+    def import_handle(self, side, buffer, handle, peer_first_global_row):
+        from multiprocessing import shared_memory
+        m = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
+        self.peer_shm.append(m)
+        rows = len(m.buf) // self.shape[1]
+        self.peer[(side, buffer)] = np.ndarray((rows, self.shape[1]), np.uint8, buffer=m.buf[:rows * self.shape[1]])
+        self.peer_first[side] = peer_first_global_row
+
+    def skeleton(self):
+        return torch.from_numpy(self.buf[self.cur])
+
+    def thin_launch_p2p(self):
+        b, K = self.band, bands.THIN_HALO
+        nxt = self.cur ^ 1
+        out, deleted = _subiters(self.buf[self.cur], K, b.first_global_row, self.gh)
+        keep = np.ones(self.shape[0], bool)
+        lo, hi = b.halo_lo, b.halo_lo + b.rows
+        if b.halo_lo:
+            keep[lo - K:lo] = False
+            d = self.peer[(0, nxt)]
+            r = b.first_global_row + lo - self.peer_first[0]
+            d[r:r + K] = out[lo:lo + K]
+        if b.halo_hi:
+            keep[hi:hi + K] = False
+            d = self.peer[(1, nxt)]
+            r = b.first_global_row + hi - K - self.peer_first[1]
+            d[r:r + K] = out[hi - K:hi]
+        self.buf[nxt][keep] = out[keep]
+        self.cur = nxt
+        return bool(deleted[lo:hi].any())
+
+    def close(self):
+        self.peer.clear()
+        self.buf = None
+        for m in self.peer_shm:
+            m.close()
+        for m in self.shm:
+            m.close()
+            m.unlink()
+
+
 def _make_image(h, w, seed):
     from scipy import ndimage
     rng = np.random.default_rng(seed)
@@ -60,30 +119,36 @@ def _make_image(h, w, seed):
     return img.astype(np.uint8)
 
 
-def _worker(rank, world, port, h, w, seed, q):
+def _worker(rank, world, port, h, w, seed, q, mode="sendrecv"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     full = _make_image(h, w, seed)
     band = bands.band_for(h, world, rank, halo=12)
     a = band.first_global_row
     local = full[a:a + band.local_rows].copy()
-    be = NumpyBackend(local, band, h)
-    launches = bands.run_thinning(be, band, rank, world, dist)
-    out = bands.gather_rows(be.skeleton(), band, h, rank, world, dist)
+    if mode == "p2p":
+        be = SharedMemBackend(local, band, h)
+        launches = bands.run_thinning_p2p(be, band, rank, world, dist)
+    else:
+        be = NumpyBackend(local, band, h)
+        launches = bands.run_thinning(be, band, rank, world, dist)
+    out = bands.gather_rows(be.skeleton().clone(), band, h, rank, world, dist)
     if rank == 0:
         q.put((launches, out.numpy().copy()))
     dist.barrier()
+    if mode == "p2p":
+        be.close()
     dist.destroy_process_group()
 
 
-def _run(world, h, w, seed):
+def _run(world, h, w, seed, mode="sendrecv"):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, h, w, seed, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, h, w, seed, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     launches, out = q.get(timeout=300)
@@ -113,6 +178,18 @@ def test_banded_thinning_equals_global_fixed_point(oracle):
         launches, out = _run(world, h, w, seed)
         assert launches >= 2
         assert np.array_equal(out, want), f"world {world}: {int((out != want).sum())} cells differ"
+
+
+def test_banded_thinning_p2p_protocol(oracle):
+    """Halo rows stored by the neighbour into the destination buffer (ping-pong in lockstep), flags all-reduced."""
+    h, w, seed = 150, 120, 5
+    want = _oracle_thin(oracle, _make_image(h, w, seed))
+    ref_launches = None
+    for world in (2, 3):
+        launches, out = _run(world, h, w, seed, mode="p2p")
+        assert np.array_equal(out, want), f"world {world}: {int((out != want).sum())} cells differ"
+        l2, out2 = _run(world, h, w, seed)
+        assert launches == l2 and np.array_equal(out2, want)
 
 
 def test_band_geometry():

@@ -1,5 +1,6 @@
 """Row-band sharding on real GPUs (needs >= 2; run with `gpurun --gpus 2`): the raster stages split over the
-ranks with NCCL halo exchange must reproduce the single-GPU result bit for bit -- every local grid on its band
+ranks with NCCL halo exchange ("nccl") or with the exchange fused into the thinning kernel as stores into the
+neighbour's peer-mapped buffer ("p2p") must reproduce the single-GPU result bit for bit -- every local grid on its band
 rows, and on rank 0 the gathered skeleton / occupancy, clusters, rows, seeds and the GvdGraph arrays."""
 import os
 import socket
@@ -10,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, name, seed, npts, q):
+def _worker(rank, world, port, name, seed, npts, halo, q):
     import faulthandler
     import sys
     faulthandler.dump_traceback_later(100, exit=True, file=sys.stderr)   # a hang must not eat the GPU budget
@@ -29,7 +30,9 @@ def _worker(rank, world, port, name, seed, npts, q):
           ref = lib.Context(rank)                      # single-GPU reference on this rank's own GPU
           ref.map_to_graph(params, pts)
           ctx = lib.Context(rank)
-          info = bands.banded_map_to_graph(ctx, params, pts, rank, world, dist, rank)
+          info = bands.banded_map_to_graph(ctx, params, pts, rank, world, dist, rank, halo=halo)
+          if halo == "p2p":   # a second map on the same contexts: cached peer mappings, buffers back to index 0
+              info = bands.banded_map_to_graph(ctx, params, pts, rank, world, dist, rank, halo=halo)
           # local grids on the band rows
           gi = lib.grid_geometry(params)
           band = bands.band_for(gi.height, world, rank, ctx.band_halo_rows(params))
@@ -70,8 +73,11 @@ def _worker(rank, world, port, name, seed, npts, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,name,seed,npts", [(1, "SMALL", 1, None), (2, "SMALL", 1, None), (2, "C2", 0, 600_000), (4, "C2", 2, 600_000)])
-def test_banded_equals_single_gpu(world, name, seed, npts):
+@pytest.mark.parametrize("world,name,seed,npts,halo", [(1, "SMALL", 1, None, "nccl"), (2, "SMALL", 1, None, "nccl"),
+                                                       (2, "C2", 0, 600_000, "nccl"), (4, "C2", 2, 600_000, "nccl"),
+                                                       (1, "SMALL", 1, None, "p2p"), (2, "SMALL", 1, None, "p2p"),
+                                                       (2, "C2", 0, 600_000, "p2p"), (4, "C2", 2, 600_000, "p2p")])
+def test_banded_equals_single_gpu(world, name, seed, npts, halo):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
@@ -82,7 +88,7 @@ def test_banded_equals_single_gpu(world, name, seed, npts):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, seed, npts, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, seed, npts, halo, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=150) for _ in range(world))
