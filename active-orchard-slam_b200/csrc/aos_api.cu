@@ -138,6 +138,9 @@ void aos_destroy(aos_ctx *c) {
       if (c->band_peer[s][b]) cudaIpcCloseMemHandle(c->band_peer[s][b]);
   c->band_thin[0].release();
   c->band_thin[1].release();
+  DevBuf *sdb[] = {&c->sd_quads, &c->sd_verts, &c->sd_vor, &c->sd_base};
+  for (DevBuf *b : sdb) b->release();
+  subdiv_release_pins(c);
   c->graph.release();
   c->pin_facet_xy.release();
   c->pin_enext.release();

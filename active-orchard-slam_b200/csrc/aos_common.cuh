@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "aos_gpu.h"
+#include "host_subdiv.h"
 
 #ifndef __CUDA_ARCH_LIST__
 #endif
@@ -210,6 +211,9 @@ aos_status launch_thin_once(Ctx *c, const uint32_t *src, uint32_t *dst, int w, i
                             int cnt_r1, int *d_count, const ThinHalo *halo);
 aos_status run_ror(Ctx *c, const void *dpoints, size_t n, uint32_t step, uint32_t ox, uint32_t oy, uint32_t oz, float radius,
                    int min_neighbors, size_t *n_out);
+aos_status facets_prepare(Ctx *c, const Subdiv &sd, int *n_slots);  // *n_slots = -1: structure is not a triangulation
+aos_status facets_fill(Ctx *c, float2 *d_fxy, int *d_enext);
+void subdiv_release_pins(Ctx *c);  // host_gvd.cu
 aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *nearest, int32_t *dist2);
 aos_status launch_edt_threshold(Ctx *c, const int32_t *dist2, int w, int h, int r2, uint32_t *out);
 aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h, int gx0, int gy0, int gx1, int gy1,
@@ -229,9 +233,20 @@ aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum
 bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
                          std::vector<float> *facet_xy, std::vector<int32_t> *facet_off);
 
+// device mirrors of Subdiv::QuadEdge / Subdiv::Vertex (same bytes, uploaded as they are)
+struct SdQuad {
+  int next[4];
+  int pt[4];
+};
+struct SdVertex {
+  int first_edge, type;
+  float x, y;
+};
+
 struct GraphInputs {
   const float *facet_xy = nullptr;  // pinned host: one x,y per facet-vertex slot; slot e also is Voronoi edge e (vd:97-114)
   const int *enext = nullptr;       // pinned host: slot of the edge's end point (next vertex of the same facet)
+  bool device_facets = false;       // slots and links come from facets_fill (k_facets.cu) instead of the two host arrays
   int n_slots = 0;
   const double *rows_info = nullptr;  // host, 4 per row
   int n_rows = 0;
@@ -333,6 +348,11 @@ struct Ctx {
   DevBuf gvd_buf, gvd_buf2, gvd_buf3, gvd_skel, seed_buf, seed_buf2, edt_buf, edt_out, ror_buf, ror_out;
   bool clearance = false;  // aos_set_clearance
   std::vector<double> h_merged;
+  Subdiv subdiv;                                    // lives in the context so its arrays are allocated (and pinned) once
+  DevBuf sd_quads, sd_verts, sd_vor, sd_base;       // k_facets.cu
+  int sd_nv = 0;
+  void *sd_pinned[2] = {nullptr, nullptr};          // cudaHostRegister'ed storage of subdiv's two arrays
+  size_t sd_pinned_bytes[2] = {0, 0};
   PinVec<float> pin_facet_xy;
   PinVec<int> pin_enext;
   PinVec<double> pin_rows;

@@ -16,10 +16,11 @@
 namespace aos {
 
 // VoronoiDiagram::compute, vd:16-94.
-bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
-                         std::vector<float> *facet_xy, std::vector<int32_t> *facet_off) {
-  facet_xy->clear();
-  facet_off->assign(1, 0);
+// VoronoiDiagram::compute up to the last insert (vd:16-92): bounds, Subdiv2D(rect), one insert per seed in order.
+// `before_reserve(n)` runs ahead of the only (re)allocation of sd's arrays (the context un-pins them there).
+template <typename F>
+static bool host_subdiv_build(Subdiv &sd, const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
+                              F before_reserve) {
   if (n <= 0) return false;
   if (!std::isfinite(min_x) || !std::isfinite(max_x) || !std::isfinite(min_y) || !std::isfinite(max_y)) return false;
   if (min_x > max_x) std::swap(min_x, max_x);
@@ -43,7 +44,7 @@ bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x,
   // (round-half-even), OpenCV 4.5.4 as shipped with ROS 2 Humble (package.xml:48)
   const bool dbg = getenv("AOS_DEBUG") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
-  Subdiv sd;
+  before_reserve((size_t)n);
   sd.reserve((size_t)n);
   sd.init((int)lrint((double)rx), (int)lrint((double)ry), (int)lrint((double)rw), (int)lrint((double)rh));
   const float margin = 0.1f;
@@ -55,14 +56,45 @@ bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x,
     y = std::max(ry + margin, std::min(ry + rh - margin, y));
     sd.insert(x, y);  // -1 where cv::Subdiv2D::insert throws: the reference skips the seed (vd:83-88)
   }
-  auto t1 = std::chrono::steady_clock::now();
-  sd.voronoi_facets(facet_xy, facet_off);
   if (dbg) {
-    auto t2 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[aos] subdiv: %d seeds, insert %.1f ms, voronoi+facets %.1f ms\n", n,
-            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[aos] subdiv: %d seeds, insert %.1f ms\n", n, std::chrono::duration<double, std::milli>(t1 - t0).count());
   }
   return true;
+}
+
+// ... and getVoronoiFacetList on the host (vd:94): the stand-alone aos_voronoi_facets and the fallback of the device walk
+bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
+                         std::vector<float> *facet_xy, std::vector<int32_t> *facet_off) {
+  facet_xy->clear();
+  facet_off->assign(1, 0);
+  Subdiv sd;
+  if (!host_subdiv_build(sd, seeds, n, min_x, max_x, min_y, max_y, [](size_t) {})) return false;
+  sd.voronoi_facets(facet_xy, facet_off);
+  return true;
+}
+
+// Page-lock the storage of the context's Subdiv arrays so their upload is one DMA each (cudaHostRegister; a failure
+// only means a staged copy).  Called with the arrays' current storage after reserve(); sd_unpin_if_growing runs
+// before a reserve() that would re-allocate, because registered memory must not be freed.
+static void sd_unpin(Ctx *c, int i) {
+  if (c->sd_pinned[i]) cudaHostUnregister(c->sd_pinned[i]);
+  c->sd_pinned[i] = nullptr;
+  c->sd_pinned_bytes[i] = 0;
+}
+static void sd_pin(Ctx *c, int i, const void *p, size_t bytes) {
+  if (c->sd_pinned[i] == p && c->sd_pinned_bytes[i] == bytes) return;
+  sd_unpin(c, i);
+  if (p && bytes && cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    c->sd_pinned[i] = const_cast<void *>(p);
+    c->sd_pinned_bytes[i] = bytes;
+  } else {
+    cudaGetLastError();  // not fatal
+  }
+}
+void subdiv_release_pins(Ctx *c) {
+  sd_unpin(c, 0);
+  sd_unpin(c, 1);
 }
 
 }  // namespace aos
@@ -101,6 +133,46 @@ aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, double mi
     return AOS_ERR_CAPACITY;
   if (!xy.empty()) memcpy(facet_xy, xy.data(), sizeof(float) * xy.size());
   memcpy(facet_off, off.data(), sizeof(int32_t) * off.size());
+  return AOS_OK;
+}
+
+// The device half of VoronoiDiagram::compute on its own (parity tests against aos_voronoi_facets): insertions on the
+// host, circumcentres + facet walks on the device; returns the facet-vertex slots (facets with fewer than 2 vertices
+// dropped, as vd:97-114 does) and, per slot, the slot of the next vertex of the same facet.
+aos_status aos_voronoi_facets_device(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, double min_x, double max_x,
+                                     double min_y, double max_y, float *slot_xy, int32_t *slot_next, int32_t capacity_slots,
+                                     int32_t *n_slots) {
+  if (!c || !n_slots) return AOS_ERR_INVALID;
+  if (n_seeds < 0 || (n_seeds > 0 && !seeds_xy)) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  *n_slots = 0;
+  Subdiv &sd = c->subdiv;
+  if (!host_subdiv_build(sd, seeds_xy, n_seeds, min_x, max_x, min_y, max_y, [c, &sd](size_t n) {
+        if (3 * n + 16 > sd.quad_capacity()) sd_unpin(c, 0);
+        if (3 * n + 16 > sd.vertex_capacity()) sd_unpin(c, 1);
+      }))
+    return AOS_OK;
+  sd_pin(c, 0, sd.quads(), sd.quad_capacity() * sizeof(Subdiv::QuadEdge));
+  sd_pin(c, 1, sd.vertices(), sd.vertex_capacity() * sizeof(Subdiv::Vertex));
+  int K = -1;
+  aos_status s = facets_prepare(c, sd, &K);
+  if (s != AOS_OK) return s;
+  if (K < 0) {
+    set_error(c, "subdivision is not a triangulation");
+    return AOS_ERR_STATE;
+  }
+  *n_slots = K;
+  if (!slot_xy && !slot_next) return AOS_OK;
+  if (!slot_xy || !slot_next || capacity_slots < K) return AOS_ERR_CAPACITY;
+  if (K == 0) return AOS_OK;
+  AOS_CUDA_OK(c, c->gvd_buf.reserve(12 * (size_t)K + 512));
+  float2 *d_fxy = c->gvd_buf.as<float2>();
+  int *d_enext = reinterpret_cast<int *>(c->gvd_buf.as<char>() + ((8 * (size_t)K + 255) & ~(size_t)255));
+  s = facets_fill(c, d_fxy, d_enext);
+  if (s != AOS_OK) return s;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(slot_xy, d_fxy, 8 * (size_t)K, cudaMemcpyDeviceToHost, c->stream));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(slot_next, d_enext, 4 * (size_t)K, cudaMemcpyDeviceToHost, c->stream));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return AOS_OK;
 }
 
@@ -181,13 +253,49 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   // bounds, gvd:278-281: uint32 * float -> float, widened
   const double minx = in.ox, maxx = in.ox + (double)(float)((float)(unsigned)in.w * in.res);
   const double miny = in.oy, maxy = in.oy + (double)(float)((float)(unsigned)in.h * in.res);
+  // VoronoiDiagram::compute: the Delaunay insertions are a sequential replay on the host (host_subdiv.cu); the
+  // circumcentres and the facet walks are data-parallel and run on the device (k_facets.cu)
+  Subdiv &sd = c->subdiv;
+  const bool built = host_subdiv_build(sd, c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy,
+                                       [c, &sd](size_t n) {
+                                         if (3 * n + 16 > sd.quad_capacity()) sd_unpin(c, 0);
+                                         if (3 * n + 16 > sd.vertex_capacity()) sd_unpin(c, 1);
+                                       });
+  c->mark("gvd_host_voronoi");
+  if (!c->pin_rows.resize(4 * (size_t)n_rows)) {
+    set_error(c, "cudaHostAlloc failed for the row staging buffer");
+    return AOS_ERR_CUDA;
+  }
+  if (n_rows) memcpy(c->pin_rows.data(), rows_info, sizeof(double) * 4 * (size_t)n_rows);
+  in.rows_info = c->pin_rows.data();
+  in.n_rows = n_rows;
+  int dev_slots = -1;
+  if (built) {
+    sd_pin(c, 0, sd.quads(), sd.quad_capacity() * sizeof(Subdiv::QuadEdge));
+    sd_pin(c, 1, sd.vertices(), sd.vertex_capacity() * sizeof(Subdiv::Vertex));
+    aos_status fs = facets_prepare(c, sd, &dev_slots);
+    if (fs != AOS_OK) return fs;
+  } else {
+    dev_slots = 0;
+  }
+  c->mark("gvd_facets");
+  if (dev_slots >= 0) {
+    in.device_facets = true;
+    in.n_slots = dev_slots;
+    aos_status s = run_graph(c, in);
+    if (s != AOS_OK) return s;
+    c->have_graph = true;
+    return AOS_OK;
+  }
+  // the structure is not a triangulation (never seen; Subdiv2D would have walked it all the same): host walk
   std::vector<float> fxy;
   std::vector<int32_t> foff;
-  host_voronoi_facets(c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy, &fxy, &foff);
-  c->mark("gvd_host_voronoi");
+  fxy.clear();
+  foff.assign(1, 0);
+  sd.voronoi_facets(&fxy, &foff);
   // facets -> edge slots (vd:97-114); facets with fewer than 2 vertices contribute nothing
   const int nf = (int)foff.size() - 1;
-  if (!c->pin_facet_xy.resize(fxy.size()) || !c->pin_enext.resize(fxy.size() / 2) || !c->pin_rows.resize(4 * (size_t)n_rows)) {
+  if (!c->pin_facet_xy.resize(fxy.size()) || !c->pin_enext.resize(fxy.size() / 2)) {
     set_error(c, "cudaHostAlloc failed for the facet staging buffers");
     return AOS_ERR_CUDA;
   }
@@ -202,12 +310,9 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
     en[k - 1] = base;
     slots += k;
   }
-  if (n_rows) memcpy(c->pin_rows.data(), rows_info, sizeof(double) * 4 * (size_t)n_rows);
   in.facet_xy = c->pin_facet_xy.data();
   in.enext = c->pin_enext.data();
   in.n_slots = slots;
-  in.rows_info = c->pin_rows.data();
-  in.n_rows = n_rows;
   aos_status s = run_graph(c, in);
   if (s != AOS_OK) return s;
   c->have_graph = true;

@@ -51,6 +51,7 @@ float g_outer_factor = 6.f;  // see aos_set_subdiv_outer_factor
 void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   vtx_.clear();
   q_.clear();
+  valid_geometry_ = false;
   // initDelaunay: the three outer vertices sit big_coord away (3 x max side up to OpenCV 4.5.x, 6 x in 4.13)
   const float big = g_outer_factor * (float)(rw > rh ? rw : rh);
   const float rx = (float)rx_i, ry = (float)ry_i;

@@ -21,7 +21,6 @@ class Subdiv {
   // getVoronoiFacetList(idx = {}): one polygon per inserted vertex in insertion order, flat x,y + offsets
   void voronoi_facets(std::vector<float> *xy, std::vector<int32_t> *off);
 
- private:
   struct alignas(32) QuadEdge {  // 32 bytes, never straddles a cache line
     int next[4];
     int pt[4];
@@ -31,6 +30,15 @@ class Subdiv {
     int type;  // -1 free, 0 real, 1 virtual (Voronoi vertex)
     float x, y;
   };
+  // the finished structure as it lies in memory, for the device facet kernels (k_facets.cu)
+  const QuadEdge *quads() const { return q_.data(); }
+  size_t n_quads() const { return q_.size(); }
+  size_t quad_capacity() const { return q_.capacity(); }
+  const Vertex *vertices() const { return vtx_.data(); }
+  size_t n_vertices() const { return vtx_.size(); }
+  size_t vertex_capacity() const { return vtx_.capacity(); }
+
+ private:
   int org(int e) const { return q_[e >> 2].pt[e & 3]; }
   int dst(int e) const { return q_[e >> 2].pt[(e + 2) & 3]; }
   int get_edge(int edge, int type) const;

@@ -766,8 +766,13 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   uint32_t *d_loff = A.take<uint32_t>(K + 1), *d_lcur = A.take<uint32_t>(K + 1);
   uint32_t *d_tot = reinterpret_cast<uint32_t *>(d_cnt + 8);  // scan totals
 
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_fxy, in.facet_xy, sizeof(float2) * K, cudaMemcpyHostToDevice, st));
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_enext, in.enext, sizeof(int) * K, cudaMemcpyHostToDevice, st));
+  if (in.device_facets) {
+    aos_status fs = facets_fill(c, d_fxy, d_enext);
+    if (fs != AOS_OK) return fs;
+  } else {
+    AOS_CUDA_OK(c, cudaMemcpyAsync(d_fxy, in.facet_xy, sizeof(float2) * K, cudaMemcpyHostToDevice, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(d_enext, in.enext, sizeof(int) * K, cudaMemcpyHostToDevice, st));
+  }
   if (n_rows) AOS_CUDA_OK(c, cudaMemcpyAsync(d_rows, in.rows_info, sizeof(double) * 4 * n_rows, cudaMemcpyHostToDevice, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(d_state, 0, K, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(g5.h.keys, 0xff, sizeof(unsigned long long) * cap_pts, st));

@@ -262,6 +262,14 @@ AOS_API aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, d
                                       int32_t *facet_off, int32_t off_capacity, int32_t *n_facets,
                                       int32_t *n_points);
 
+/* The same step as the gvd stage runs it: Delaunay insertions replayed on the host, cv::Subdiv2D::calcVoronoi and
+ * getVoronoiFacetList (voronoi_diagram.cpp:94) on the device.  Returns the facet-vertex slots in facet order, facets
+ * with fewer than 2 vertices dropped (voronoi_diagram.cpp:97-114 makes one edge per slot), and for every slot the
+ * slot of the facet's next vertex.  Call with slot_xy == slot_next == NULL to size the buffers. */
+AOS_API aos_status aos_voronoi_facets_device(aos_ctx *ctx, const double *seeds_xy, int32_t n_seeds, double min_x,
+                                             double max_x, double min_y, double max_y, float *slot_xy /* 2 per slot */,
+                                             int32_t *slot_next, int32_t capacity_slots, int32_t *n_slots);
+
 /* ---- row-band sharding of the raster stages (BASELINE.json config 4: one huge grid over several GPUs) --------
  * Each GPU (one process, one context) owns the image rows [row0, row0 + rows) of the global grid and keeps
  * halo_lo / halo_hi extra rows below / above them (0 at the global border).  The halo must cover the stencil
