@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
-    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_voronoi_facets_device", "aos_set_subdiv_outer_factor",
+    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_voronoi_facets_device", "aos_merge_seeds_device", "aos_trim_path", "aos_set_subdiv_outer_factor",
     "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_ipc_export", "aos_band_ipc_import",
     "aos_band_thin_launch_p2p", "aos_band_grid_device", "aos_seed_stage_tail",
 ]
@@ -162,6 +162,8 @@ def load() -> C.CDLL:
     L.aos_seed_stage_tail.argtypes = [vp, C.POINTER(CSeedParams), vp, vp]
     L.aos_map_to_graph_batch.argtypes = [C.POINTER(CBatchItem), i32, i32]
     L.aos_merge_seeds.argtypes = [vp, i32, vp, C.POINTER(i32)]
+    L.aos_trim_path.argtypes = [vp, vp, i32, C.c_double, vp, C.c_int, vp, C.POINTER(i32)]
+    L.aos_merge_seeds_device.argtypes = [vp, vp, i32, vp, C.POINTER(i32)]
     L.aos_voronoi_facets_device.argtypes = [vp, vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, i32,
                                             C.POINTER(i32)]
     L.aos_voronoi_facets.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, vp, i32, vp, i32,
@@ -406,6 +408,30 @@ class Context:
         d = C.c_int32()
         self._check(self.L.aos_band_thin_launch_p2p(self.h, C.byref(d)), "aos_band_thin_launch_p2p")
         return bool(d.value)
+
+    def trim_path(self, path_xy, safety_distance=0.2, skeleton_bits=None, info=None) -> int:
+        """aos_trim_path (trimPathNearOccupiedRegions): poses that remain.  skeleton_bits: uint32 [H, pitch] host grid
+        with info=(resolution, origin_x, origin_y, width), or None for this context's framed skeleton."""
+        p = np.ascontiguousarray(path_xy, np.float64).reshape(-1, 2)
+        n = C.c_int32()
+        if skeleton_bits is not None:
+            sk = np.ascontiguousarray(skeleton_bits, np.uint32)
+            gi = CGridInfo(int(info[3]), sk.shape[0], float(info[0]), float(info[1]), float(info[2]))
+            rc = self.L.aos_trim_path(self.h, p.ctypes.data_as(C.c_void_p), len(p), float(safety_distance),
+                                      sk.ctypes.data_as(C.c_void_p), AOS_MEM_HOST, C.byref(gi), C.byref(n))
+        else:
+            rc = self.L.aos_trim_path(self.h, p.ctypes.data_as(C.c_void_p), len(p), float(safety_distance), None, AOS_MEM_HOST,
+                                      None, C.byref(n))
+        self._check(rc, "aos_trim_path")
+        return n.value
+
+    def merge_seeds_device(self, seeds):
+        sd = np.ascontiguousarray(seeds, np.float64).reshape(-1, 2)
+        out = np.zeros((max(len(sd), 1), 2), np.float64)
+        n = C.c_int32()
+        self._check(self.L.aos_merge_seeds_device(self.h, sd.ctypes.data_as(C.c_void_p), len(sd), out.ctypes.data_as(C.c_void_p),
+                                                  C.byref(n)), "aos_merge_seeds_device")
+        return out[:n.value].copy()
 
     def voronoi_facets_device(self, seeds, minx, maxx, miny, maxy):
         """aos_voronoi_facets_device: (slot xy float32 [K,2], next slot int32 [K])."""

@@ -799,6 +799,52 @@ aos_status aos_set_clearance(aos_ctx *c, int enabled) {
   return AOS_OK;
 }
 
+// trimPathNearOccupiedRegions (src/aos_path_gen_node.cpp:1570-1630), SURVEY section 8(f) row F3
+aos_status aos_trim_path(aos_ctx *c, const double *path_xy, int32_t n_poses, double safety_distance,
+                         const uint32_t *skeleton_bits, aos_mem skeleton_mem, const aos_grid_info *info, int32_t *n_kept) {
+  if (!c || !n_kept || n_poses < 0 || (n_poses > 0 && !path_xy)) return AOS_ERR_INVALID;
+  AOS_REQUIRE(c, (skeleton_bits == nullptr) == (info == nullptr), "skeleton and info must be given together");
+  AOS_REQUIRE(c, safety_distance >= 0 && std::isfinite(safety_distance), "bad safety distance");
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  *n_kept = n_poses;
+  const uint32_t *bits = nullptr;
+  int w, h;
+  double ox, oy;
+  float res;
+  if (skeleton_bits) {
+    AOS_REQUIRE(c, info->width > 0 && info->height > 0 && info->resolution > 0.f, "bad grid info");
+    w = info->width;
+    h = info->height;
+    ox = info->origin_x;
+    oy = info->origin_y;
+    res = info->resolution;
+    if (skeleton_mem == AOS_MEM_DEVICE) {
+      bits = skeleton_bits;
+    } else {
+      const size_t bytes = (size_t)pitch_words_for(w) * h * 4;
+      AOS_CUDA_OK(c, c->gvd_skel.reserve(bytes));
+      AOS_CUDA_OK(c, cudaMemcpyAsync(c->gvd_skel.p, skeleton_bits, bytes, cudaMemcpyHostToDevice, c->stream));
+      bits = c->gvd_skel.as<uint32_t>();
+    }
+  } else {
+    if (!c->have_seed) {  // path_gen:1571: no skeleton yet -> the path is left as it is
+      set_error(c, "no skeleton: pass one or run aos_seed_stage on this context first");
+      return AOS_ERR_STATE;
+    }
+    w = c->P.w;
+    h = c->P.h;
+    ox = c->P.ox;
+    oy = c->P.oy;
+    res = c->P.res;
+    bits = c->g_framed.as<uint32_t>();
+  }
+  int kept = n_poses;
+  aos_status s = launch_trim_path(c, path_xy, n_poses, bits, w, h, ox, oy, res, safety_distance, &kept);
+  if (s != AOS_OK) return s;
+  *n_kept = kept;
+  return AOS_OK;
+}
+
 aos_status aos_edt_bits(aos_ctx *c, const uint32_t *bits, int32_t w, int32_t h, uint32_t *nearest_xy, int32_t *dist2) {
   if (!c || !bits || !nearest_xy) return AOS_ERR_INVALID;
   AOS_CUDA_OK(c, cudaSetDevice(c->device));

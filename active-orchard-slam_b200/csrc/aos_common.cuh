@@ -223,7 +223,10 @@ aos_status launch_unpack(Ctx *c, const uint32_t *src, int8_t *dst, int w, int h)
 aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel, float min_length);
 aos_status launch_labels(Ctx *c, int32_t *dst);
 void host_rows_info(const std::vector<aos_tree_row> &rows, std::vector<double> *rows_info);
+aos_status launch_trim_path(Ctx *c, const double *path_xy_host, int n, const uint32_t *bits, int w, int h, double ox, double oy,
+                            float res, double safety, int *n_kept);
 aos_status device_select_seeds(Ctx *c);
+aos_status device_merge_seeds(Ctx *c, const double *seeds, int n);  // -> c->h_merged
 void host_merge_seeds(const double *seeds, int n, std::vector<double> *out);
 aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum_buf, uint32_t *d_total);
 

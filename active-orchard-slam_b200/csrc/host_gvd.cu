@@ -119,6 +119,16 @@ aos_status aos_merge_seeds(const double *seeds_xy, int32_t n, double *out_xy, in
   return AOS_OK;
 }
 
+aos_status aos_merge_seeds_device(aos_ctx *c, const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out) {
+  if (!c || n < 0 || (n > 0 && (!seeds_xy || !out_xy))) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  aos_status s = device_merge_seeds(c, seeds_xy, n);
+  if (s != AOS_OK) return s;
+  if (!c->h_merged.empty()) memcpy(out_xy, c->h_merged.data(), sizeof(double) * c->h_merged.size());
+  if (n_out) *n_out = (int32_t)(c->h_merged.size() / 2);
+  return AOS_OK;
+}
+
 aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, double min_x, double max_x, double min_y,
                               double max_y, float *facet_xy, int32_t xy_capacity_points, int32_t *facet_off,
                               int32_t off_capacity, int32_t *n_facets, int32_t *n_points) {
@@ -244,7 +254,11 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   c->mark("gvd_skeleton_in");
 
   // voronoiSeedsCallback merge (gvd:93-125); processGraph drops non-finite seeds (gvd:266-270)
-  host_merge_seeds(seeds_xy, n_seeds, &c->h_merged);
+  {
+    aos_status ms = device_merge_seeds(c, seeds_xy, n_seeds);
+    if (ms != AOS_OK) return ms;
+  }
+  c->mark("gvd_merge_seeds");
   c->graph.n_merged_seeds = (int)(c->h_merged.size() / 2);
   if (c->h_merged.empty()) {  // gvd:257 / :273: nothing to do
     set_error(c, "no valid seeds");

@@ -146,4 +146,59 @@ aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h,
   return AOS_OK;
 }
 
+// ---- trimPathNearOccupiedRegions (src/aos_path_gen_node.cpp:1570-1630) ----------
+// One thread per pose: is a skeleton cell set inside the +-ceil(d/res) stencil (cells whose offset length
+// sqrt(dx^2+dy^2)*res <= d)?  The reference stops at the first pose i > 0 for which that holds (pose 0 is tested
+// but never trims), so the answer is the minimum such i.  Cell indices with the reference's expression order in
+// double; (int) of an out-of-range or NaN value is INT_MIN on x86, i.e. outside the grid.
+__global__ void trim_path_kernel(const double2 *__restrict__ path, int n, const uint32_t *__restrict__ bits, int w, int h,
+                                 int pitch, double ox, double oy, double resolution, double safety, int radius_cells,
+                                 int *__restrict__ first_hit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 1 || i >= n) return;
+  const double2 p = path[i];
+  for (int dx = -radius_cells; dx <= radius_cells; ++dx)
+    for (int dy = -radius_cells; dy <= radius_cells; ++dy) {
+      const double dist = sqrt((double)(dx * dx + dy * dy)) * resolution;
+      if (dist > safety) continue;
+      const double fx = ((p.x + dx * resolution) - ox) / resolution, fy = ((p.y + dy * resolution) - oy) / resolution;
+      if (!(fx > -2147483649.0 && fx < 2147483648.0 && fy > -2147483649.0 && fy < 2147483648.0)) continue;
+      const int mx = (int)fx, my = (int)fy;
+      if (mx < 0 || mx >= w || my < 0 || my >= h) continue;
+      if ((__ldg(bits + (size_t)my * pitch + (mx >> 5)) >> (mx & 31)) & 1u) {
+        atomicMin(first_hit, i);
+        return;
+      }
+    }
+}
+
+// *n_kept = poses that remain.  `bits`: device, framed skeleton, pitch_words_for(w) words per row.
+aos_status launch_trim_path(Ctx *c, const double *path_xy_host, int n, const uint32_t *bits, int w, int h, double ox, double oy,
+                            float res, double safety, int *n_kept) {
+  *n_kept = n;
+  if (n <= 1) return AOS_OK;  // pose 0 never trims
+  const double resolution = (double)res;
+  const double rc = ceil(safety / resolution);
+  if (!(rc >= 0 && rc < 4096)) {
+    set_error(c, "safety_distance / resolution out of range");
+    return AOS_ERR_INVALID;
+  }
+  AOS_CUDA_OK(c, c->seed_buf.reserve(sizeof(double2) * (size_t)n + 256));
+  AOS_CUDA_OK(c, c->misc.reserve(4096));
+  int *d_first = c->misc.as<int>() + 100;
+  double2 *d_path = c->seed_buf.as<double2>();
+  cudaStream_t st = c->stream;
+  c->h_flag[0] = n;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_first, c->h_flag, 4, cudaMemcpyHostToDevice, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_path, path_xy_host, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+  trim_path_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_path, n, bits, w, h, pitch_words_for(w), ox, oy, resolution, safety,
+                                                      (int)rc, d_first);
+  ++c->launches;
+  AOS_CUDA_OK(c, cudaGetLastError());
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_first, 4, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  *n_kept = c->h_flag[0];
+  return AOS_OK;
+}
+
 }  // namespace aos

@@ -341,6 +341,102 @@ aos_status dedup_and_fetch(Ctx *c, double2 *d_pts, unsigned char *d_state, int n
 }
 }  // namespace
 
+// ---- voronoiSeedsCallback's greedy 0.5 m merge (src/aos_gvd_node.cpp:84-128) -------------------------------------
+// The reference walks the seeds in order; an unused seed i becomes a leader and absorbs every later unused seed j
+// with |s_i - s_j| <= 0.5 (distance to the LEADER, sqrt of the squared norm, inclusive), and the cluster's point is
+// the mean taken in index order.  So: j is a leader iff no earlier leader lies within 0.5 m -- the same monotone
+// rounds as the first-come filters above -- a member belongs to the EARLIEST such leader, and each leader adds up
+// its members in ascending index.  Non-finite seeds never merge (their norm is NaN/inf) and are dropped afterwards
+// (gvd:266-270), so they simply stay out of the grid.
+__global__ void merge_init_kernel(const double2 *__restrict__ pts, int n, unsigned char *__restrict__ state) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double2 p = pts[i];
+    state[i] = (isfinite(p.x) && isfinite(p.y)) ? kSeedUndecided : kSeedReject;
+  }
+}
+
+__global__ void merge_round_kernel(const double2 *__restrict__ pts, int n, PointGrid g, volatile unsigned char *state,
+                                   double radius, int *pending_flag) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    if (state[v] != kSeedUndecided) continue;
+    const double2 p = pts[v];
+    const long long cx = cell_coord(p.x, g.inv), cy = cell_coord(p.y, g.inv);
+    bool member = false, pending = false;
+    for (int oy = -1; oy <= 1 && !member; ++oy)
+      for (int ox = -1; ox <= 1 && !member; ++ox) {
+        int slot = hash_find(g.h, cell_key(cx + ox, cy + oy));
+        if (slot < 0) continue;
+        for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
+          if (u >= v) continue;
+          unsigned char su = state[u];
+          if (su == kSeedReject) continue;  // a member absorbs nobody
+          double ex = pts[u].x - p.x, ey = pts[u].y - p.y;
+          if (!(sqrt(ex * ex + ey * ey) <= radius)) continue;
+          if (su == kSeedAccept) {
+            member = true;
+            break;
+          }
+          pending = true;
+        }
+      }
+    if (member) state[v] = kSeedReject;
+    else if (!pending) state[v] = kSeedAccept;
+    else *pending_flag = 1;
+  }
+}
+
+// member -> its leader: the earliest leader within the radius
+__global__ void merge_owner_kernel(const double2 *__restrict__ pts, int n, PointGrid g, const unsigned char *__restrict__ state,
+                                   double radius, int *__restrict__ owner) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    int best = -1;
+    const double2 p = pts[v];
+    if (state[v] == kSeedReject && isfinite(p.x) && isfinite(p.y)) {
+      const long long cx = cell_coord(p.x, g.inv), cy = cell_coord(p.y, g.inv);
+      for (int oy = -1; oy <= 1; ++oy)
+        for (int ox = -1; ox <= 1; ++ox) {
+          int slot = hash_find(g.h, cell_key(cx + ox, cy + oy));
+          if (slot < 0) continue;
+          for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
+            if (u >= v || state[u] != kSeedAccept || (best >= 0 && u > best)) continue;
+            double ex = pts[u].x - p.x, ey = pts[u].y - p.y;
+            if (sqrt(ex * ex + ey * ey) <= radius) best = u;
+          }
+        }
+    }
+    owner[v] = best;
+  }
+}
+
+// leader -> mean of (itself, its members in ascending index), written at its rank among the leaders
+__global__ void merge_emit_kernel(const double2 *__restrict__ pts, int n, PointGrid g, const unsigned char *__restrict__ state,
+                                  const int *__restrict__ owner, const uint32_t *__restrict__ pos, double2 *__restrict__ out) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    if (state[v] != kSeedAccept) continue;
+    const double2 p = pts[v];
+    const long long cx = cell_coord(p.x, g.inv), cy = cell_coord(p.y, g.inv);
+    double sx = p.x, sy = p.y;
+    int last = v, count = 1;
+    for (;;) {  // next member in index order; clusters hold a handful of seeds
+      int nxt = 0x7fffffff;
+      for (int oy = -1; oy <= 1; ++oy)
+        for (int ox = -1; ox <= 1; ++ox) {
+          int slot = hash_find(g.h, cell_key(cx + ox, cy + oy));
+          if (slot < 0) continue;
+          for (int u = g.h.val[slot]; u >= 0; u = g.next[u])
+            if (u > last && u < nxt && owner[u] == v) nxt = u;
+        }
+      if (nxt == 0x7fffffff) break;
+      sx += pts[nxt].x;
+      sy += pts[nxt].y;
+      ++count;
+      last = nxt;
+    }
+    const double cnt = (double)count;
+    out[pos[v]] = make_double2(sx / cnt, sy / cnt);
+  }
+}
+
 // rows: all_tree_rows in cluster order (c->h_rows).  Fills c->h_seeds / c->seed_counts.
 aos_status device_select_seeds(Ctx *c) {
   cudaStream_t st = c->stream;
@@ -429,6 +525,74 @@ aos_status device_select_seeds(Ctx *c) {
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_seeds.data(), d_out, sizeof(double2) * (size_t)total, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
   for (int k = 0; k < 3; ++k) c->seed_counts[k] = counts[k];
+  return AOS_OK;
+}
+
+// seeds (host, n x,y pairs) -> c->h_merged (merged seeds in leader order, non-finite dropped)
+aos_status device_merge_seeds(Ctx *c, const double *seeds, int n) {
+  cudaStream_t st = c->stream;
+  c->h_merged.clear();
+  if (n <= 0) return AOS_OK;
+  const unsigned cap = pow2_at_least((size_t)n * 2);
+  const size_t N = (size_t)n;
+  size_t need = sizeof(double2) * 2 * (N + 1) + (N + 1) + (sizeof(int) * 2 + sizeof(uint32_t)) * (N + 1) +
+                (sizeof(unsigned long long) + sizeof(int)) * (size_t)cap + 8192;
+  AOS_CUDA_OK(c, c->seed_buf2.reserve(need));
+  char *base = c->seed_buf2.as<char>();
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    char *p = base + off;
+    off += bytes;
+    return p;
+  };
+  double2 *d_pts = reinterpret_cast<double2 *>(take(sizeof(double2) * (N + 1)));
+  double2 *d_out = reinterpret_cast<double2 *>(take(sizeof(double2) * (N + 1)));
+  unsigned char *d_state = reinterpret_cast<unsigned char *>(take(N + 1));
+  uint32_t *d_scan = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (N + 1)));
+  int *d_owner = reinterpret_cast<int *>(take(sizeof(int) * (N + 1)));
+  PointGrid g;
+  g.h.keys = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * cap));
+  g.h.val = reinterpret_cast<int *>(take(sizeof(int) * cap));
+  g.h.mask = cap - 1;
+  g.next = reinterpret_cast<int *>(take(sizeof(int) * (N + 1)));
+  g.inv = 1.0 / (0.5 * (1.0 + 1e-9));
+  uint32_t *d_tot = reinterpret_cast<uint32_t *>(take(64));
+  int *d_flag = reinterpret_cast<int *>(d_tot + 4);
+
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_pts, seeds, sizeof(double2) * N, cudaMemcpyHostToDevice, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(g.h.keys, 0xff, sizeof(unsigned long long) * cap, st));
+  AOS_CUDA_OK(c, cudaMemsetAsync(g.h.val, 0xff, sizeof(int) * cap, st));
+  merge_init_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, d_state);
+  ++c->launches;
+  seed_grid_build_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, d_state, n, g);
+  ++c->launches;
+  for (int round = 0; round < 100000; ++round) {
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_flag, 0, 4, st));
+    merge_round_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, d_flag);
+    ++c->launches;
+    AOS_CUDA_OK(c, cudaGetLastError());
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    if (!c->h_flag[0]) break;
+  }
+  merge_owner_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, d_owner);
+  ++c->launches;
+  seed_flags_kernel<<<blocks_for(N), 256, 0, st>>>(d_state, n, d_scan);
+  ++c->launches;
+  aos_status s = exclusive_scan_u32(c, d_scan, N, c->cc_blocksum, d_tot);
+  if (s != AOS_OK) return s;
+  merge_emit_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, g, d_state, d_owner, d_scan, d_out);
+  ++c->launches;
+  AOS_CUDA_OK(c, cudaGetLastError());
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
+  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  const int m = c->h_flag[0];
+  c->h_merged.resize(2 * (size_t)m);
+  if (m > 0) {
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_merged.data(), d_out, sizeof(double2) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  }
   return AOS_OK;
 }
 

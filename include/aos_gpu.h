@@ -262,6 +262,20 @@ AOS_API aos_status aos_voronoi_facets(const double *seeds_xy, int32_t n_seeds, d
                                       int32_t *facet_off, int32_t off_capacity, int32_t *n_facets,
                                       int32_t *n_points);
 
+/* ---- consumer of the skeleton next to the path --------------------------------------
+ * trimPathNearOccupiedRegions of aos_path_gen_node (src/aos_path_gen_node.cpp:1570-1630; call sites :1018, :1270,
+ * :1552): a path is cut at the first pose i > 0 that has a cell == 100 of /skeletonized_occupancy_grid within
+ * safety_distance (0.2 m in the reference; stencil of +-ceil(d/res) cells, offsets with sqrt(dx^2+dy^2)*res <= d).
+ * *n_kept = number of poses that remain (path.poses.resize(i)).  skeleton_bits == NULL (and info == NULL): the
+ * framed skeleton of this context's last seed stage; otherwise a bit-packed grid (aos_bits_pitch_words) in host or
+ * device memory.  AOS_ERR_STATE when there is no skeleton (the reference returns without trimming, :1571). */
+AOS_API aos_status aos_trim_path(aos_ctx *ctx, const double *path_xy, int32_t n_poses, double safety_distance,
+                                 const uint32_t *skeleton_bits, aos_mem skeleton_mem, const aos_grid_info *info,
+                                 int32_t *n_kept);
+
+/* The merge as the gvd stage runs it (k_seeds.cu: leaders by monotone rounds over a 0.5 m hash grid, members summed
+ * in index order); non-finite seeds are dropped, as processGraph does right after (gvd:266-270). */
+AOS_API aos_status aos_merge_seeds_device(aos_ctx *ctx, const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out);
 /* The same step as the gvd stage runs it: Delaunay insertions replayed on the host, cv::Subdiv2D::calcVoronoi and
  * getVoronoiFacetList (voronoi_diagram.cpp:94) on the device.  Returns the facet-vertex slots in facet order, facets
  * with fewer than 2 vertices dropped (voronoi_diagram.cpp:97-114 makes one edge per slot), and for every slot the

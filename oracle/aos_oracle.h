@@ -97,6 +97,9 @@ int  orc_point_in_polygon(double px, double py, const double *poly, int n_poly);
 
 /* voronoiSeedsCallback greedy 0.5 m merge, gvd:84-128.  out must hold 2*n doubles. */
 int orc_gvd_merge_seeds(const double *seeds, int n, double *out);
+/* trimPathNearOccupiedRegions (src/aos_path_gen_node.cpp:1570-1630): new pose count */
+int orc_trim_path(const double *path_xy, int n, const int8_t *grid, int width, int height, double origin_x,
+                  double origin_y, float res, double safety_distance);
 
 /* VoronoiDiagram::compute up to the Subdiv2D call, vd:16-89: bounding rect (as the int Rect that
  * OpenCV 4.5.4's Subdiv2D(Rect) receives from the Rect2f) and the clipped float32 points.

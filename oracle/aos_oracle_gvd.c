@@ -438,3 +438,40 @@ void orc_graph_free(orc_graph *g) {
   free(g->edge_clearances); free(g->corner_points);
   memset(g, 0, sizeof(*g));
 }
+
+
+/* trimPathNearOccupiedRegions, src/aos_path_gen_node.cpp:1570-1630: the first pose
+ * i > 0 with a skeleton cell == 100 inside the 0.2 m stencil around it truncates the path to i poses; pose 0 is
+ * tested but never trims (":1620  if (too_close && i > 0)").  Returns the new number of poses.
+ * grid: the published (framed) skeleton, int8 row-major; resolution is the message's float widened to double. */
+int orc_trim_path(const double *path_xy, int n, const int8_t *grid, int width, int height, double origin_x,
+                  double origin_y, float res, double safety_distance) {
+  const double resolution = (double)res;
+  if (!grid || n <= 0) return n;
+  for (int i = 0; i < n; ++i) {
+    const double px = path_xy[2 * i], py = path_xy[2 * i + 1];
+    int too_close = 0;
+    const int check_radius_cells = (int)ceil(safety_distance / resolution);
+    for (int dx = -check_radius_cells; dx <= check_radius_cells && !too_close; ++dx) {
+      for (int dy = -check_radius_cells; dy <= check_radius_cells && !too_close; ++dy) {
+        const double check_x = px + dx * resolution;
+        const double check_y = py + dy * resolution;
+        const double dist = sqrt((double)(dx * dx + dy * dy)) * resolution;
+        if (dist > safety_distance) continue;
+        const int mx = (int)((check_x - origin_x) / resolution);
+        const int my = (int)((check_y - origin_y) / resolution);
+        if (mx >= 0 && mx < width && my >= 0 && my < height) {
+          const int index = mx + my * width;
+          if (index >= 0 && (size_t)index < (size_t)width * (size_t)height) {
+            if (grid[index] == 100) {
+              too_close = 1;
+              break;
+            }
+          }
+        }
+      }
+    }
+    if (too_close && i > 0) return i;
+  }
+  return n;
+}

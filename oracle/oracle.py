@@ -78,6 +78,8 @@ def lib():
         _lib.orc_seed_stage.restype = C.c_int
         _lib.orc_gvd_merge_seeds.argtypes = [_PD, C.c_int, _PD]
         _lib.orc_gvd_merge_seeds.restype = C.c_int
+        _lib.orc_trim_path.argtypes = [_PD, C.c_int, _P8, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float, C.c_double]
+        _lib.orc_trim_path.restype = C.c_int
         _lib.orc_gvd_graph.argtypes = [_PF, _P32, C.c_int, _P8, C.c_int, C.c_int, C.c_double, C.c_double,
                                        C.c_float, _PD, C.c_int, C.POINTER(_Graph)]
         _lib.orc_gvd_graph.restype = C.c_int
@@ -159,6 +161,15 @@ def merge_seeds(seeds: np.ndarray) -> np.ndarray:
     out = np.zeros_like(s)
     m = lib().orc_gvd_merge_seeds(s.ctypes.data_as(_PD), len(s), out.ctypes.data_as(_PD))
     return out[:m].copy()
+
+
+def trim_path(path_xy: np.ndarray, grid: np.ndarray, origin_x: float, origin_y: float, res, safety_distance: float = 0.2) -> int:
+    """trimPathNearOccupiedRegions (path_gen:1570-1630): number of poses that remain."""
+    p = np.ascontiguousarray(path_xy, dtype=np.float64).reshape(-1, 2)
+    g = np.ascontiguousarray(grid, dtype=np.int8)
+    h, w = g.shape
+    return int(lib().orc_trim_path(p.ctypes.data_as(_PD), len(p), g.ctypes.data_as(_P8), w, h, float(origin_x), float(origin_y),
+                                   float(np.float32(res)), float(safety_distance)))
 
 
 def gvd_stage(seeds: np.ndarray, skel_framed: np.ndarray, origin_x: float, origin_y: float, res,

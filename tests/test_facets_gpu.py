@@ -79,3 +79,32 @@ def test_device_facets_empty(ctx):
     hx, ho = lib.voronoi_facets(np.array([[1.0, 2.0]]), 0, 10, 0, 10)
     want_xy, want_next = _slots_from_facets(hx, ho)
     assert np.array_equal(nxt, want_next) and np.array_equal(xy.view(np.uint32), want_xy.view(np.uint32))
+
+
+def test_device_merge_matches_reference_loop(oracle, ctx):
+    """voronoiSeedsCallback's greedy 0.5 m merge on the device vs the oracle's literal O(S^2) loop (gvd:84-128)."""
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        n = int(rng.integers(0, 900))
+        s = rng.uniform(0, 12 if trial % 2 else 6, (n, 2))
+        if n > 10:
+            s[5] = s[4] + [0.5, 0.0]      # exactly at the merge distance (<=)
+            s[9] = [np.nan, 1.0]
+            s[20:28] = s[19]              # a pile of identical seeds
+        if trial % 5 == 0 and n > 50:     # chains: every seed within 0.5 m of its predecessor
+            s[30:50, 0] = 3 + 0.3 * np.arange(20)
+            s[30:50, 1] = 3
+        want = oracle.merge_seeds(s)
+        want = want[np.isfinite(want).all(axis=1)]   # processGraph drops non-finite merged seeds (gvd:266-270)
+        got = ctx.merge_seeds_device(s)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"trial {trial}"
+        assert np.array_equal(got, lib.merge_seeds(s))
+
+
+def test_device_merge_dense_pile(ctx):
+    """2000 seeds inside one 0.5 m disc plus a far one: one leader absorbs them all, in index order."""
+    rng = np.random.default_rng(3)
+    s = np.concatenate([rng.uniform(0, 0.2, (2000, 2)) + 5.0, [[50.0, 50.0]]])
+    got = ctx.merge_seeds_device(s)
+    want = lib.merge_seeds(s)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))

@@ -175,3 +175,33 @@ def test_oracle_reproduces_golden_vectors(oracle, name):
     gr = oracle.gvd_stage(r["seeds"], r["skel_framed"], r["origin_x"], r["origin_y"], r["res"], r["rows_info"])
     for k in make_golden.GRAPH_KEYS:
         assert np.array_equal(gr[k], g["g_" + k]), k
+
+
+def test_trim_path_oracle_against_vectorised_restatement(oracle):
+    """orc_trim_path (path_gen:1570-1630) vs an independent numpy statement of the same rule: the set of stencil
+    offsets with sqrt(dx^2+dy^2)*res <= d, cell = trunc((p + offset*res - origin)/res), first pose i > 0 that hits."""
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        h, w = int(rng.integers(8, 90)), int(rng.integers(8, 90))
+        res = float(np.float32([0.05, 0.1, 0.025][trial % 3]))
+        ox, oy = [(0.0, 0.0), (-4.5, -2.4)][trial % 2]
+        g = np.zeros((h, w), np.int8)
+        g[rng.random((h, w)) < 0.004] = 100
+        n = int(rng.integers(1, 200))
+        path = np.array([ox + w * res / 2, oy + h * res / 2]) + np.cumsum(rng.normal(0, res, (n, 2)), axis=0)
+        d = 0.2
+        rc = int(np.ceil(d / res))
+        off = [(dx, dy) for dx in range(-rc, rc + 1) for dy in range(-rc, rc + 1) if np.sqrt(float(dx * dx + dy * dy)) * res <= d]
+        want = n
+        for i in range(1, n):
+            hit = False
+            for dx, dy in off:
+                mx = int(np.trunc(((path[i, 0] + dx * res) - ox) / res))
+                my = int(np.trunc(((path[i, 1] + dy * res) - oy) / res))
+                if 0 <= mx < w and 0 <= my < h and g[my, mx] == 100:
+                    hit = True
+                    break
+            if hit:
+                want = i
+                break
+        assert oracle.trim_path(path, g, ox, oy, res, d) == want
