@@ -236,14 +236,10 @@ aos_status exclusive_scan_u32(Ctx *c, uint32_t *data, size_t n, DevBuf &blocksum
 bool host_voronoi_facets(const double *seeds, int n, double min_x, double max_x, double min_y, double max_y,
                          std::vector<float> *facet_xy, std::vector<int32_t> *facet_off);
 
-// device mirrors of Subdiv::QuadEdge / Subdiv::Vertex (same bytes, uploaded as they are)
-struct SdQuad {
-  int next[4];
-  int pt[4];
-};
+// device mirror of Subdiv::Vertex (same bytes, uploaded as they are; x, y are float32 values widened to double)
 struct SdVertex {
+  double x, y, n2;
   int first_edge, type;
-  float x, y;
 };
 
 struct GraphInputs {
@@ -353,9 +349,9 @@ struct Ctx {
   std::vector<double> h_merged;
   Subdiv subdiv;                                    // lives in the context so its arrays are allocated (and pinned) once
   DevBuf sd_quads, sd_verts, sd_vor, sd_base;       // k_facets.cu
-  int sd_nv = 0;
-  void *sd_pinned[2] = {nullptr, nullptr};          // cudaHostRegister'ed storage of subdiv's two arrays
-  size_t sd_pinned_bytes[2] = {0, 0};
+  int sd_nv = 0, sd_nq = 0;
+  void *sd_pinned[3] = {nullptr, nullptr, nullptr};  // cudaHostRegister'ed storage of subdiv's three arrays
+  size_t sd_pinned_bytes[3] = {0, 0, 0};
   PinVec<float> pin_facet_xy;
   PinVec<int> pin_enext;
   PinVec<double> pin_rows;

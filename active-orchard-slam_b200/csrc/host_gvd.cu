@@ -93,8 +93,19 @@ static void sd_pin(Ctx *c, int i, const void *p, size_t bytes) {
   }
 }
 void subdiv_release_pins(Ctx *c) {
-  sd_unpin(c, 0);
-  sd_unpin(c, 1);
+  for (int i = 0; i < 3; ++i) sd_unpin(c, i);
+}
+static void sd_unpin_if_growing(Ctx *c, const Subdiv &sd, size_t n) {
+  if (3 * n + 16 > sd.quad_capacity()) {
+    sd_unpin(c, 0);
+    sd_unpin(c, 1);
+  }
+  if (3 * n + 16 > sd.vertex_capacity()) sd_unpin(c, 2);
+}
+static void sd_pin_all(Ctx *c, const Subdiv &sd) {
+  sd_pin(c, 0, sd.edge_next(), sd.quad_capacity() * 4 * sizeof(int));
+  sd_pin(c, 1, sd.edge_pt(), sd.quad_capacity() * 4 * sizeof(int));
+  sd_pin(c, 2, sd.vertices(), sd.vertex_capacity() * sizeof(Subdiv::Vertex));
 }
 
 }  // namespace aos
@@ -157,13 +168,9 @@ aos_status aos_voronoi_facets_device(aos_ctx *c, const double *seeds_xy, int32_t
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
   *n_slots = 0;
   Subdiv &sd = c->subdiv;
-  if (!host_subdiv_build(sd, seeds_xy, n_seeds, min_x, max_x, min_y, max_y, [c, &sd](size_t n) {
-        if (3 * n + 16 > sd.quad_capacity()) sd_unpin(c, 0);
-        if (3 * n + 16 > sd.vertex_capacity()) sd_unpin(c, 1);
-      }))
+  if (!host_subdiv_build(sd, seeds_xy, n_seeds, min_x, max_x, min_y, max_y, [c, &sd](size_t n) { sd_unpin_if_growing(c, sd, n); }))
     return AOS_OK;
-  sd_pin(c, 0, sd.quads(), sd.quad_capacity() * sizeof(Subdiv::QuadEdge));
-  sd_pin(c, 1, sd.vertices(), sd.vertex_capacity() * sizeof(Subdiv::Vertex));
+  sd_pin_all(c, sd);
   int K = -1;
   aos_status s = facets_prepare(c, sd, &K);
   if (s != AOS_OK) return s;
@@ -271,10 +278,7 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   // circumcentres and the facet walks are data-parallel and run on the device (k_facets.cu)
   Subdiv &sd = c->subdiv;
   const bool built = host_subdiv_build(sd, c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy,
-                                       [c, &sd](size_t n) {
-                                         if (3 * n + 16 > sd.quad_capacity()) sd_unpin(c, 0);
-                                         if (3 * n + 16 > sd.vertex_capacity()) sd_unpin(c, 1);
-                                       });
+                                       [c, &sd](size_t n) { sd_unpin_if_growing(c, sd, n); });
   c->mark("gvd_host_voronoi");
   if (!c->pin_rows.resize(4 * (size_t)n_rows)) {
     set_error(c, "cudaHostAlloc failed for the row staging buffer");
@@ -285,8 +289,7 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   in.n_rows = n_rows;
   int dev_slots = -1;
   if (built) {
-    sd_pin(c, 0, sd.quads(), sd.quad_capacity() * sizeof(Subdiv::QuadEdge));
-    sd_pin(c, 1, sd.vertices(), sd.vertex_capacity() * sizeof(Subdiv::Vertex));
+    sd_pin_all(c, sd);
     aos_status fs = facets_prepare(c, sd, &dev_slots);
     if (fs != AOS_OK) return fs;
   } else {

@@ -15,7 +15,8 @@
 // quad-edge algorithm step for step (same predicates in double, same walk, same edge/vertex numbering).
 // tests/test_subdiv_cpu.py pins it bit-for-bit against the real cv2.Subdiv2D.
 //
-// Quad-edge encoding: edge id = 4 * quad + rot (rot 0..3); sym = id ^ 2; rot +1 = dual edge.
+// Quad-edge encoding: edge id = 4 * quad + rot (rot 0..3); sym = id ^ 2; rot +1 = dual edge.  next_[id] / pt_[id] are
+// flat arrays indexed by the id itself; vertices carry their float32 coordinates widened to double plus |v|^2.
 #include <float.h>
 #include <math.h>
 
@@ -38,6 +39,9 @@ enum {
 };
 enum { LOC_ERROR = -2, LOC_INSIDE = 0, LOC_VERTEX = 1, LOC_ON_EDGE = 2 };
 
+inline double tri_aread(double ax, double ay, double bx, double by, double cx, double cy) {
+  return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
 inline double tri_area(float ax, float ay, float bx, float by, float cx, float cy) {
   return ((double)bx - ax) * ((double)cy - ay) - ((double)by - ay) * ((double)cx - ax);
 }
@@ -50,7 +54,8 @@ float g_outer_factor = 6.f;  // see aos_set_subdiv_outer_factor
 
 void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   vtx_.clear();
-  q_.clear();
+  next_.clear();
+  pt_.clear();
   valid_geometry_ = false;
   // initDelaunay: the three outer vertices sit big_coord away (3 x max side up to OpenCV 4.5.x, 6 x in 4.13)
   const float big = g_outer_factor * (float)(rw > rh ? rw : rh);
@@ -59,8 +64,9 @@ void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   tly_ = ry;
   brx_ = rx + rw;
   bry_ = ry + rh;
-  vtx_.push_back(Vertex{0, -1, 0.f, 0.f});
-  q_.push_back(QuadEdge{{0, 0, 0, 0}, {0, 0, 0, 0}});
+  vtx_.push_back(Vertex{0, 0, 0, 0, -1});
+  next_.resize(4, 0);
+  pt_.resize(4, 0);
   free_q_ = 0;
   free_pt_ = 0;
   int pA = new_point(rx + big, ry, false);
@@ -77,18 +83,23 @@ void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
 }
 
 int Subdiv::get_edge(int edge, int type) const {
-  edge = q_[edge >> 2].next[(edge + type) & 3];
+  edge = next_[(edge & ~3) + ((edge + type) & 3)];
   return (edge & ~3) + ((edge + (type >> 4)) & 3);
 }
 
 int Subdiv::new_edge() {
   if (free_q_ <= 0) {
-    q_.push_back(QuadEdge{{0, 0, 0, 0}, {0, 0, 0, 0}});
-    free_q_ = (int)q_.size() - 1;
+    next_.resize(next_.size() + 4, 0);
+    pt_.resize(pt_.size() + 4, 0);
+    free_q_ = (int)(next_.size() / 4) - 1;
   }
   int edge = free_q_ * 4;
-  free_q_ = q_[edge >> 2].next[1];
-  q_[edge >> 2] = QuadEdge{{edge, edge + 3, edge + 2, edge + 1}, {0, 0, 0, 0}};
+  free_q_ = next_[edge + 1];
+  next_[edge] = edge;
+  next_[edge + 1] = edge + 3;
+  next_[edge + 2] = edge + 2;
+  next_[edge + 3] = edge + 1;
+  pt_[edge] = pt_[edge + 1] = pt_[edge + 2] = pt_[edge + 3] = 0;
   return edge;
 }
 
@@ -97,36 +108,36 @@ void Subdiv::delete_edge(int edge) {
   int sedge = edge ^ 2;
   splice(sedge, get_edge(sedge, PREV_AROUND_ORG));
   edge >>= 2;
-  q_[edge].next[0] = 0;
-  q_[edge].next[1] = free_q_;
+  next_[4 * edge] = 0;
+  next_[4 * edge + 1] = free_q_;
   free_q_ = edge;
 }
 
 int Subdiv::new_point(float x, float y, bool is_virtual) {
   if (free_pt_ == 0) {
-    vtx_.push_back(Vertex{0, -1, 0.f, 0.f});
+    vtx_.push_back(Vertex{0, 0, 0, 0, -1});
     free_pt_ = (int)vtx_.size() - 1;
   }
   int v = free_pt_;
   free_pt_ = vtx_[v].first_edge;
-  vtx_[v] = Vertex{0, is_virtual ? 1 : 0, x, y};
+  vtx_[v] = Vertex{(double)x, (double)y, (double)x * x + (double)y * y, 0, is_virtual ? 1 : 0};
   return v;
 }
 
 void Subdiv::splice(int a, int b) {
-  int &a_next = q_[a >> 2].next[a & 3];
-  int &b_next = q_[b >> 2].next[b & 3];
+  int &a_next = next_[a];
+  int &b_next = next_[b];
   int a_rot = (a_next & ~3) + ((a_next + 1) & 3);
   int b_rot = (b_next & ~3) + ((b_next + 1) & 3);
-  int &a_rot_next = q_[a_rot >> 2].next[a_rot & 3];
-  int &b_rot_next = q_[b_rot >> 2].next[b_rot & 3];
+  int &a_rot_next = next_[a_rot];
+  int &b_rot_next = next_[b_rot];
   std::swap(a_next, b_next);
   std::swap(a_rot_next, b_rot_next);
 }
 
 void Subdiv::set_edge_points(int edge, int org, int dst) {
-  q_[edge >> 2].pt[edge & 3] = org;
-  q_[edge >> 2].pt[(edge + 2) & 3] = dst;
+  pt_[edge] = org;
+  pt_[edge ^ 2] = dst;
   vtx_[org].first_edge = edge;
   vtx_[dst].first_edge = edge ^ 2;
 }
@@ -141,15 +152,16 @@ int Subdiv::connect_edges(int a, int b) {
 
 int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
   int vertex = 0;
-  const int max_edges = (int)(q_.size() * 4);
+  const int max_edges = (int)next_.size();
   if (px < tlx_ || py < tly_ || px >= brx_ || py >= bry_) return LOC_ERROR;  // cv::Exception(StsOutOfRange)
   int edge = recent_;
   int location = LOC_ERROR;
-  const QuadEdge *const q = q_.data();
-  const Vertex *const vtx = vtx_.data();
-  auto right_of = [q, vtx](float x, float y, int e) {  // isRightOf
-    const Vertex &o = vtx[q[e >> 2].pt[e & 3]], &d = vtx[q[e >> 2].pt[(e + 2) & 3]];
-    const double cw = tri_area(x, y, d.x, d.y, o.x, o.y);
+  const int *const nx = next_.data();
+  const int *const pt = pt_.data();
+  const Vertex *const vd = vtx_.data();
+  auto right_of = [nx, pt, vd](double x, double y, int e) {  // isRightOf
+    const Vertex &o = vd[pt[e]], &d = vd[pt[e ^ 2]];
+    const double cw = tri_aread(x, y, d.x, d.y, o.x, o.y);
     return (cw > 0) - (cw < 0);
   };
   int right_of_curr = right_of(px, py, edge);
@@ -158,8 +170,8 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
     right_of_curr = -right_of_curr;
   }
   for (int i = 0; i < max_edges; ++i) {
-    const int onext = q[edge >> 2].next[edge & 3];
-    int dprev = q[edge >> 2].next[(edge + PREV_AROUND_DST) & 3];
+    const int onext = nx[edge];
+    int dprev = nx[(edge & ~3) + ((edge + PREV_AROUND_DST) & 3)];
     dprev = (dprev & ~3) + ((dprev + (PREV_AROUND_DST >> 4)) & 3);
     const int right_of_onext = right_of(px, py, onext);
     const int right_of_dprev = right_of(px, py, dprev);
@@ -179,7 +191,7 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
         right_of_curr = right_of_dprev;
         edge = dprev;
       } else if (right_of_curr == 0) {
-        const Vertex &dn = vtx[q[onext >> 2].pt[(onext + 2) & 3]];
+        const Vertex &dn = vd[pt[onext ^ 2]];
         if (right_of(dn.x, dn.y, edge) >= 0) {
           edge ^= 2;
         } else {
@@ -194,7 +206,8 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
   }
   recent_ = edge;
   if (location == LOC_INSIDE) {
-    const Vertex &o = vtx_[org(edge)], &d = vtx_[dst(edge)];
+    const Vertex &vo = vtx_[org(edge)], &vd2 = vtx_[dst(edge)];
+    struct { float x, y; } o{(float)vo.x, (float)vo.y}, d{(float)vd2.x, (float)vd2.y};  // the float32 coordinates
     double t1 = fabs(px - o.x);  // float differences, as cv::Point2f arithmetic
     t1 += fabs(py - o.y);
     double t2 = fabs(px - d.x);
@@ -253,39 +266,40 @@ int Subdiv::insert(float px, float py) {
 // pointers (no re-loading of the vectors' data pointers after every store) and re-uses the orientation determinant
 // that isRightOf and isPtInCircle3 share.
 void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
-  QuadEdge *const q = q_.data();
-  Vertex *const vtx = vtx_.data();
-  const int max_edges = (int)(q_.size() * 4);
-  auto gedge = [q](int edge, int type) {
-    edge = q[edge >> 2].next[(edge + type) & 3];
+  int *const nx = next_.data();
+  int *const pt = pt_.data();
+  Vertex *const vd = vtx_.data();
+  const int max_edges = (int)next_.size();
+  auto gedge = [nx](int edge, int type) {
+    edge = nx[(edge & ~3) + ((edge + type) & 3)];
     return (edge & ~3) + ((edge + (type >> 4)) & 3);
   };
-  auto splice_raw = [q](int a, int b) {
-    int &a_next = q[a >> 2].next[a & 3];
-    int &b_next = q[b >> 2].next[b & 3];
+  auto splice_raw = [nx](int a, int b) {
+    int &a_next = nx[a];
+    int &b_next = nx[b];
     const int a_rot = (a_next & ~3) + ((a_next + 1) & 3);
     const int b_rot = (b_next & ~3) + ((b_next + 1) & 3);
-    int &a_rot_next = q[a_rot >> 2].next[a_rot & 3];
-    int &b_rot_next = q[b_rot >> 2].next[b_rot & 3];
+    int &a_rot_next = nx[a_rot];
+    int &b_rot_next = nx[b_rot];
     std::swap(a_next, b_next);
     std::swap(a_rot_next, b_rot_next);
   };
   const double pxx = (double)px * px + (double)py * py;
+  const double pxd = px, pyd = py;
   for (int i = 0; i < max_edges; ++i) {
     const int temp_edge = gedge(curr_edge, PREV_AROUND_ORG);
-    const QuadEdge &qc = q[curr_edge >> 2];
-    const int curr_org = qc.pt[curr_edge & 3], curr_dst = qc.pt[(curr_edge + 2) & 3];
-    const int temp_dst = q[temp_edge >> 2].pt[(temp_edge + 2) & 3];
-    const Vertex &t = vtx[temp_dst], &o = vtx[curr_org], &d = vtx[curr_dst];
+    const int curr_org = pt[curr_edge], curr_dst = pt[curr_edge ^ 2];
+    const int temp_dst = pt[temp_edge ^ 2];
+    const Vertex &t = vd[temp_dst], &o = vd[curr_org], &d = vd[curr_dst];
     // isRightOf(t, curr_edge) = sign of triangleArea(t, dst, org); the same determinant is the third term of
     // isPtInCircle3(pt = org, a = t, b = dst, c = p)
-    const double area_tdo = tri_area(t.x, t.y, d.x, d.y, o.x, o.y);
+    const double area_tdo = tri_aread(t.x, t.y, d.x, d.y, o.x, o.y);
     // evaluated unconditionally: the two data-dependent tests collapse into one branch
     const double eps = FLT_EPSILON * 0.125;
-    double val = ((double)t.x * t.x + (double)t.y * t.y) * tri_area(d.x, d.y, px, py, o.x, o.y);
-    val -= ((double)d.x * d.x + (double)d.y * d.y) * tri_area(t.x, t.y, px, py, o.x, o.y);
+    double val = t.n2 * tri_aread(d.x, d.y, pxd, pyd, o.x, o.y);
+    val -= d.n2 * tri_aread(t.x, t.y, pxd, pyd, o.x, o.y);
     val += pxx * area_tdo;
-    val -= ((double)o.x * o.x + (double)o.y * o.y) * tri_area(t.x, t.y, d.x, d.y, px, py);
+    val -= o.n2 * tri_aread(t.x, t.y, d.x, d.y, pxd, pyd);
     const bool flip = (area_tdo > 0) & (val < -eps);
     if (flip) {
       // swapEdges(curr_edge): splice(e, a); splice(s, b); setEdgePoints(e, dst(a), dst(b)); splice(e, Lnext(a));
@@ -296,9 +310,7 @@ void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
       const int e = curr_edge, sedge = curr_edge ^ 2;
       const int a = temp_edge;  // == getEdge(curr_edge, PREV_AROUND_ORG)
       const int b = gedge(sedge, PREV_AROUND_ORG);
-      int *const nx = &q[0].next[0];  // next[edge] = nx[(edge >> 2) * (sizeof(QuadEdge) / 4) + (edge & 3)]
-      constexpr int kStride = (int)(sizeof(QuadEdge) / sizeof(int));
-      auto slot = [nx](int edge) -> int & { return nx[(edge >> 2) * kStride + (edge & 3)]; };
+      auto slot = [nx](int edge) -> int & { return nx[edge]; };
       auto rot = [](int edge) { return (edge & ~3) + ((edge + 1) & 3); };
       auto invrot = [](int edge) { return (edge & ~3) + ((edge + 3) & 3); };
       const int c = slot(e), d = slot(sedge);
@@ -320,19 +332,21 @@ void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
         slot(rd) = Q2;
         slot(rs) = U2;
         slot(ib) = P2;
-        const int no = q[a >> 2].pt[(a + 2) & 3], nd = q[b >> 2].pt[(b + 2) & 3];
-        q[e >> 2].pt[e & 3] = no;
-        q[e >> 2].pt[(e + 2) & 3] = nd;
-        vtx[no].first_edge = e;
-        vtx[nd].first_edge = e ^ 2;
+        const int no = pt[a ^ 2], nd = pt[b ^ 2];
+        pt[e] = no;
+        pt[e ^ 2] = nd;
+        vd[no].first_edge = e;
+        vd[nd].first_edge = e ^ 2;
+        curr_edge = la;  // == getEdge(e, PREV_AROUND_ORG) after the flip: rot(next[rot e]) with next[rot e] = U
+        continue;
       } else {
         splice_raw(e, a);
         splice_raw(sedge, b);
-        const int no = q[a >> 2].pt[(a + 2) & 3], nd = q[b >> 2].pt[(b + 2) & 3];
-        q[e >> 2].pt[e & 3] = no;
-        q[e >> 2].pt[(e + 2) & 3] = nd;
-        vtx[no].first_edge = e;
-        vtx[nd].first_edge = e ^ 2;
+        const int no = pt[a ^ 2], nd = pt[b ^ 2];
+        pt[e] = no;
+        pt[e ^ 2] = nd;
+        vd[no].first_edge = e;
+        vd[nd].first_edge = e ^ 2;
         splice_raw(e, gedge(a, NEXT_AROUND_LEFT));
         splice_raw(sedge, gedge(b, NEXT_AROUND_LEFT));
       }
@@ -340,13 +354,15 @@ void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
     } else if (curr_org == first_point) {
       break;
     } else {
-      curr_edge = gedge(q[curr_edge >> 2].next[curr_edge & 3], PREV_AROUND_LEFT);
+      curr_edge = gedge(nx[curr_edge], PREV_AROUND_LEFT);
     }
   }
 }
 
 // intersection of the bisectors of (org0,dst0) and (org1,dst1): float differences and sums, double solve
-bool Subdiv::voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y) {
+bool Subdiv::voronoi_point(const Vertex &vo0, const Vertex &vd0, const Vertex &vo1, const Vertex &vd1, float *x, float *y) {
+  struct P2f { float x, y; };  // Point2f arithmetic: the differences and sums below are float32 operations
+  const P2f o0{(float)vo0.x, (float)vo0.y}, d0{(float)vd0.x, (float)vd0.y}, o1{(float)vo1.x, (float)vo1.y}, d1{(float)vd1.x, (float)vd1.y};
   double a0 = d0.x - o0.x;
   double b0 = d0.y - o0.y;
   double c0 = -0.5 * (a0 * (d0.x + o0.x) + b0 * (d0.y + o0.y));
@@ -368,26 +384,26 @@ bool Subdiv::voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1,
 void Subdiv::calc_voronoi() {
   if (valid_geometry_) return;
   // clearVoronoi: nothing to clear, the structure is built once per compute()
-  const int total = (int)q_.size();
+  const int total = (int)(next_.size() / 4);
   for (int i = 4; i < total; ++i) {
-    if (q_[i].next[0] <= 0) continue;  // free quad-edge
+    if (next_[4 * i] <= 0) continue;  // free quad-edge
     const int edge0 = i * 4;
-    if (!q_[i].pt[3]) {
+    if (!pt_[4 * i + 3]) {
       int edge1 = get_edge(edge0, NEXT_AROUND_LEFT);
       int edge2 = get_edge(edge1, NEXT_AROUND_LEFT);
       float x, y;
       if (voronoi_point(vtx_[org(edge0)], vtx_[dst(edge0)], vtx_[org(edge1)], vtx_[dst(edge1)], &x, &y)) {
         int v = new_point(x, y, true);
-        q_[i].pt[3] = q_[edge1 >> 2].pt[3 - (edge1 & 2)] = q_[edge2 >> 2].pt[3 - (edge2 & 2)] = v;
+        pt_[4 * i + 3] = pt_[(edge1 & ~3) + 3 - (edge1 & 2)] = pt_[(edge2 & ~3) + 3 - (edge2 & 2)] = v;
       }
     }
-    if (!q_[i].pt[1]) {
+    if (!pt_[4 * i + 1]) {
       int edge1 = get_edge(edge0, NEXT_AROUND_RIGHT);
       int edge2 = get_edge(edge1, NEXT_AROUND_RIGHT);
       float x, y;
       if (voronoi_point(vtx_[org(edge0)], vtx_[dst(edge0)], vtx_[org(edge1)], vtx_[dst(edge1)], &x, &y)) {
         int v = new_point(x, y, true);
-        q_[i].pt[1] = q_[edge1 >> 2].pt[1 + (edge1 & 2)] = q_[edge2 >> 2].pt[1 + (edge2 & 2)] = v;
+        pt_[4 * i + 1] = pt_[(edge1 & ~3) + 1 + (edge1 & 2)] = pt_[(edge2 & ~3) + 1 + (edge2 & 2)] = v;
       }
     }
   }
@@ -405,8 +421,8 @@ void Subdiv::voronoi_facets(std::vector<float> *xy, std::vector<int32_t> *off) {
     int edge = (vtx_[k].first_edge & ~3) + ((vtx_[k].first_edge + 1) & 3), t = edge;
     do {
       const Vertex &v = vtx_[org(t)];
-      xy->push_back(v.x);
-      xy->push_back(v.y);
+      xy->push_back((float)v.x);
+      xy->push_back((float)v.y);
       t = get_edge(t, NEXT_AROUND_LEFT);
     } while (t != edge);
     off->push_back((int32_t)(xy->size() / 2));

@@ -13,34 +13,36 @@ class Subdiv {
   // integer rectangle, as cv::Subdiv2D(Rect) receives it
   void init(int rx, int ry, int rw, int rh);
   void reserve(size_t n_points) {
-    q_.reserve(3 * n_points + 16);
-    vtx_.reserve(3 * n_points + 16);  // real vertices + one Voronoi vertex per triangle
+    next_.reserve(4 * (3 * n_points + 16));
+    pt_.reserve(4 * (3 * n_points + 16));
+    vtx_.reserve(3 * n_points + 16);
   }
   // vertex id, or -1 where cv::Subdiv2D::insert would throw (point outside the rectangle / walk failure)
   int insert(float x, float y);
   // getVoronoiFacetList(idx = {}): one polygon per inserted vertex in insertion order, flat x,y + offsets
   void voronoi_facets(std::vector<float> *xy, std::vector<int32_t> *off);
 
-  struct alignas(32) QuadEdge {  // 32 bytes, never straddles a cache line
-    int next[4];
-    int pt[4];
-  };
-  struct alignas(16) Vertex {
+  // Edges live in two flat arrays indexed by the edge id itself (id = 4 * quad + rot): next_[e] and pt_[e].  The
+  // flip loop touches about 25 `next` slots per flip; with an array of {next[4], pt[4]} records every one of them
+  // cost a shift/mask/scale to address, which was a quarter of the replay's time.
+  struct alignas(32) Vertex {  // 32 bytes, never straddles a cache line
+    double x, y;      // the float32 coordinates, widened once (the predicates are evaluated in double)
+    double n2;        // x*x + y*y in double, the in-circle test's weight
     int first_edge;
-    int type;  // -1 free, 0 real, 1 virtual (Voronoi vertex)
-    float x, y;
+    int type;         // -1 free, 0 real, 1 virtual (Voronoi vertex)
   };
-  // the finished structure as it lies in memory, for the device facet kernels (k_facets.cu)
-  const QuadEdge *quads() const { return q_.data(); }
-  size_t n_quads() const { return q_.size(); }
-  size_t quad_capacity() const { return q_.capacity(); }
+  // the finished structure as it lies in memory, for the device facet kernels (k_facets.cu): next / pt per edge id, 4 per quad
+  const int *edge_next() const { return next_.data(); }
+  const int *edge_pt() const { return pt_.data(); }
+  size_t n_quads() const { return next_.size() / 4; }
+  size_t quad_capacity() const { return next_.capacity() / 4; }
   const Vertex *vertices() const { return vtx_.data(); }
   size_t n_vertices() const { return vtx_.size(); }
   size_t vertex_capacity() const { return vtx_.capacity(); }
 
  private:
-  int org(int e) const { return q_[e >> 2].pt[e & 3]; }
-  int dst(int e) const { return q_[e >> 2].pt[(e + 2) & 3]; }
+  int org(int e) const { return pt_[e]; }
+  int dst(int e) const { return pt_[e ^ 2]; }
   int get_edge(int edge, int type) const;
   int new_edge();
   void delete_edge(int edge);
@@ -53,7 +55,7 @@ class Subdiv {
   static bool voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y);
   void calc_voronoi();
 
-  std::vector<QuadEdge> q_;
+  std::vector<int> next_, pt_;  // SoA: next_[e], pt_[e] for edge id e = 4 * quad + rot
   std::vector<Vertex> vtx_;
   int free_q_ = 0, free_pt_ = 0, recent_ = 0;
   bool valid_geometry_ = false;

@@ -4,7 +4,7 @@
 // follows it is not: VoronoiDiagram::compute (src/utils/voronoi_diagram.cpp:94-114) asks Subdiv2D for one polygon
 // per seed, and Subdiv2D derives those from the finished quad-edge structure -- a circumcentre per triangle
 // (calcVoronoi) and a walk around every vertex (getVoronoiFacetList).  The quad-edge and vertex arrays are uploaded
-// as they are (32 B per quad-edge, 16 B per vertex) and three kernels produce the facet-vertex slots + cycle links
+// as they are (two int arrays indexed by edge id, 32 B per vertex) and three kernels produce the facet-vertex slots + cycle links
 // that k_graph.cu consumes, so the 1.4 M facet vertices of a C3 map are never materialised on the host.
 //
 // Sequential semantics reproduced exactly (host_subdiv.cu Subdiv::calc_voronoi is the restatement of OpenCV's loop):
@@ -24,16 +24,22 @@ namespace aos {
 namespace {
 constexpr int kNextAroundLeft = 0x13, kNextAroundRight = 0x31;
 
-__device__ __forceinline__ int d_get_edge(const SdQuad *q, int edge, int type) {
-  edge = q[edge >> 2].next[(edge + type) & 3];
+// the subdivision as host_subdiv.cu keeps it: next / pt per edge id (4 per quad), 32-byte vertices
+struct SdEdges {
+  const int *next, *pt;
+};
+__device__ __forceinline__ int d_get_edge(const SdEdges &q, int edge, int type) {
+  edge = q.next[(edge & ~3) + ((edge + type) & 3)];
   return (edge & ~3) + ((edge + (type >> 4)) & 3);
 }
-__device__ __forceinline__ int d_org(const SdQuad *q, int e) { return q[e >> 2].pt[e & 3]; }
-__device__ __forceinline__ int d_dst(const SdQuad *q, int e) { return q[e >> 2].pt[(e + 2) & 3]; }
+__device__ __forceinline__ int d_org(const SdEdges &q, int e) { return q.pt[e]; }
+__device__ __forceinline__ int d_dst(const SdEdges &q, int e) { return q.pt[e ^ 2]; }
 
 // computeVoronoiPoint (host_subdiv.cu Subdiv::voronoi_point): float differences and sums, double solve, no FMA
-__device__ bool d_voronoi_point(const SdVertex &o0, const SdVertex &d0, const SdVertex &o1, const SdVertex &d1, float *x,
+__device__ bool d_voronoi_point(const SdVertex &vo0, const SdVertex &vd0, const SdVertex &vo1, const SdVertex &vd1, float *x,
                                 float *y) {
+  const float2 o0 = make_float2((float)vo0.x, (float)vo0.y), d0 = make_float2((float)vd0.x, (float)vd0.y);
+  const float2 o1 = make_float2((float)vo1.x, (float)vo1.y), d1 = make_float2((float)vd1.x, (float)vd1.y);
   double a0 = __fsub_rn(d0.x, o0.x);
   double b0 = __fsub_rn(d0.y, o0.y);
   double c0 = -0.5 * (a0 * (double)__fadd_rn(d0.x, o0.x) + b0 * (double)__fadd_rn(d0.y, o0.y));
@@ -58,12 +64,12 @@ __device__ __forceinline__ int left_face_slot(int e) { return 2 * (e >> 2) + ((e
 __device__ __forceinline__ int right_face_slot(int e) { return 2 * (e >> 2) + ((e & 2) ? 0 : 1); }
 
 // one thread per face slot fs = 2 * quad + side (side 0: left of edge 4*quad, side 1: right of it)
-__global__ void vor_points_kernel(const SdQuad *__restrict__ q, const SdVertex *__restrict__ vtx, int n_quads,
+__global__ void vor_points_kernel(const SdEdges q, const SdVertex *__restrict__ vtx, int n_quads,
                                   float2 *__restrict__ vor, int *__restrict__ err) {
   const int fs = blockIdx.x * blockDim.x + threadIdx.x;
   if (fs >= 2 * n_quads || fs < 8) return;  // the loop starts at quad 4
   const int i = fs >> 1, side = fs & 1;
-  if (q[i].next[0] <= 0) return;  // free quad-edge
+  if (q.next[4 * i] <= 0) return;  // free quad-edge
   const int type = side ? kNextAroundRight : kNextAroundLeft;
   const int e0 = 4 * i;
   const int e1 = d_get_edge(q, e0, type), e2 = d_get_edge(q, e1, type);
@@ -84,7 +90,7 @@ __global__ void vor_points_kernel(const SdQuad *__restrict__ q, const SdVertex *
   walk[2] = (s2 & 1) ? kNextAroundRight : kNextAroundLeft;
   // only visits from quads >= 4 that are not free act; the earliest of them owns the face
   bool can[3];
-  for (int k = 0; k < 3; ++k) can[k] = slot[k] >= 8 && q[slot[k] >> 1].next[0] > 0;
+  for (int k = 0; k < 3; ++k) can[k] = slot[k] >= 8 && q.next[4 * (slot[k] >> 1)] > 0;
   for (int k = 1; k < 3; ++k)
     if (can[k] && slot[k] < fs) return;
   // try the visits in ascending order (at most three, tiny insertion sort)
@@ -103,7 +109,7 @@ __global__ void vor_points_kernel(const SdQuad *__restrict__ q, const SdVertex *
 }
 
 // facet sizes: one thread per vertex; facets with fewer than 2 vertices contribute no edge (vd:97-114)
-__global__ void facet_count_kernel(const SdQuad *__restrict__ q, const SdVertex *__restrict__ vtx, int n_vtx,
+__global__ void facet_count_kernel(const SdEdges q, const SdVertex *__restrict__ vtx, int n_vtx,
                                    uint32_t *__restrict__ count, int *__restrict__ err) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n_vtx) return;
@@ -122,7 +128,7 @@ __global__ void facet_count_kernel(const SdQuad *__restrict__ q, const SdVertex 
   count[k] = n;  // count[n_vtx] = 0 closes the scan
 }
 
-__global__ void facet_fill_kernel(const SdQuad *__restrict__ q, const SdVertex *__restrict__ vtx, int n_vtx,
+__global__ void facet_fill_kernel(const SdEdges q, const SdVertex *__restrict__ vtx, int n_vtx,
                                   const float2 *__restrict__ vor, const uint32_t *__restrict__ base,
                                   float2 *__restrict__ fxy, int *__restrict__ enext) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,19 +150,22 @@ __global__ void facet_fill_kernel(const SdQuad *__restrict__ q, const SdVertex *
 aos_status facets_prepare(Ctx *c, const Subdiv &sd, int *n_slots) {
   cudaStream_t st = c->stream;
   const int nq = (int)sd.n_quads(), nv = (int)sd.n_vertices();
-  static_assert(sizeof(SdQuad) == sizeof(Subdiv::QuadEdge) && sizeof(SdVertex) == sizeof(Subdiv::Vertex), "layout");
-  AOS_CUDA_OK(c, c->sd_quads.reserve(sizeof(SdQuad) * (size_t)nq));
+  static_assert(sizeof(SdVertex) == sizeof(Subdiv::Vertex), "layout");
+  const size_t ebytes = sizeof(int) * 4 * (size_t)nq;
+  AOS_CUDA_OK(c, c->sd_quads.reserve(2 * ebytes));  // next | pt
   AOS_CUDA_OK(c, c->sd_verts.reserve(sizeof(SdVertex) * (size_t)nv));
   AOS_CUDA_OK(c, c->sd_vor.reserve(sizeof(float2) * 2 * (size_t)nq));
   AOS_CUDA_OK(c, c->sd_base.reserve(sizeof(uint32_t) * ((size_t)nv + 1)));
   AOS_CUDA_OK(c, c->misc.reserve(4096));
   int *d_err = c->misc.as<int>() + 96;
   uint32_t *d_tot = reinterpret_cast<uint32_t *>(c->misc.as<int>() + 97);
-  AOS_CUDA_OK(c, cudaMemcpyAsync(c->sd_quads.p, sd.quads(), sizeof(SdQuad) * (size_t)nq, cudaMemcpyHostToDevice, st));
+  int *d_next = c->sd_quads.as<int>(), *d_pt = d_next + 4 * (size_t)nq;
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_next, sd.edge_next(), ebytes, cudaMemcpyHostToDevice, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(d_pt, sd.edge_pt(), ebytes, cudaMemcpyHostToDevice, st));
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->sd_verts.p, sd.vertices(), sizeof(SdVertex) * (size_t)nv, cudaMemcpyHostToDevice, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(c->sd_vor.p, 0, sizeof(float2) * 2 * (size_t)nq, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(d_err, 0, 8, st));
-  const SdQuad *q = c->sd_quads.as<SdQuad>();
+  const SdEdges q{d_next, d_pt};
   const SdVertex *v = c->sd_verts.as<SdVertex>();
   vor_points_kernel<<<(2 * nq + 255) / 256, 256, 0, st>>>(q, v, nq, c->sd_vor.as<float2>(), d_err);
   ++c->launches;
@@ -173,12 +182,14 @@ aos_status facets_prepare(Ctx *c, const Subdiv &sd, int *n_slots) {
   }
   *n_slots = c->h_flag[1];
   c->sd_nv = nv;
+  c->sd_nq = nq;
   return AOS_OK;
 }
 
 // Write the facet-vertex slots and their cycle links (what run_graph otherwise receives from the host).
 aos_status facets_fill(Ctx *c, float2 *d_fxy, int *d_enext) {
-  facet_fill_kernel<<<(c->sd_nv + 255) / 256, 256, 0, c->stream>>>(c->sd_quads.as<SdQuad>(), c->sd_verts.as<SdVertex>(), c->sd_nv,
+  const SdEdges q{c->sd_quads.as<int>(), c->sd_quads.as<int>() + 4 * (size_t)c->sd_nq};
+  facet_fill_kernel<<<(c->sd_nv + 255) / 256, 256, 0, c->stream>>>(q, c->sd_verts.as<SdVertex>(), c->sd_nv,
                                                                    c->sd_vor.as<float2>(), c->sd_base.as<uint32_t>(), d_fxy,
                                                                    d_enext);
   ++c->launches;
