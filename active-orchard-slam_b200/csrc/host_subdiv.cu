@@ -51,6 +51,7 @@ inline double tri_area(float ax, float ay, float bx, float by, float cx, float c
 }  // namespace
 
 float g_outer_factor = 6.f;  // see aos_set_subdiv_outer_factor
+bool g_literal_splices = false;  // see aos_set_subdiv_literal_splices (tests: take swapEdges' literal splice sequence)
 
 void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   vtx_.clear();
@@ -154,27 +155,45 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
   int vertex = 0;
   const int max_edges = (int)next_.size();
   if (px < tlx_ || py < tly_ || px >= brx_ || py >= bry_) return LOC_ERROR;  // cv::Exception(StsOutOfRange)
-  int edge = recent_;
+  typedef unsigned U32;
+  U32 edge = (U32)recent_;
   int location = LOC_ERROR;
-  const int *const nx = next_.data();
-  const int *const pt = pt_.data();
+  const U32 *const nx = reinterpret_cast<const U32 *>(next_.data());
+  const U32 *const pt = reinterpret_cast<const U32 *>(pt_.data());
   const Vertex *const vd = vtx_.data();
-  auto right_of = [nx, pt, vd](double x, double y, int e) {  // isRightOf
+  auto right_of = [nx, pt, vd](double x, double y, U32 e) {  // isRightOf
     const Vertex &o = vd[pt[e]], &d = vd[pt[e ^ 2]];
     const double cw = tri_aread(x, y, d.x, d.y, o.x, o.y);
     return (cw > 0) - (cw < 0);
   };
-  int right_of_curr = right_of(px, py, edge);
+  // The walk keeps the end points of `edge` as offsets from the query point: Onext(edge) shares its origin and
+  // Dprev(edge) its destination (quad-edge ring invariants), so a step loads one or two new vertices, and isRightOf
+  // (sign of triangleArea(p, dst, org) = (dst - p) x (org - p), the same subtractions and products) needs no others.
+  const double pxd = px, pyd = py;
+  double eox, eoy, edx, edy;
+  {
+    const Vertex &o = vd[pt[edge]], &d = vd[pt[edge ^ 2]];
+    eox = o.x - pxd;
+    eoy = o.y - pyd;
+    edx = d.x - pxd;
+    edy = d.y - pyd;
+  }
+  auto sgn = [](double cw) { return (cw > 0) - (cw < 0); };
+  int right_of_curr = sgn(edx * eoy - edy * eox);
   if (right_of_curr > 0) {
-    edge ^= 2;
+    edge ^= 2u;
+    std::swap(eox, edx);
+    std::swap(eoy, edy);
     right_of_curr = -right_of_curr;
   }
   for (int i = 0; i < max_edges; ++i) {
-    const int onext = nx[edge];
-    int dprev = nx[(edge & ~3) + ((edge + PREV_AROUND_DST) & 3)];
-    dprev = (dprev & ~3) + ((dprev + (PREV_AROUND_DST >> 4)) & 3);
-    const int right_of_onext = right_of(px, py, onext);
-    const int right_of_dprev = right_of(px, py, dprev);
+    const U32 onext = nx[edge];
+    U32 dprev = nx[(edge & ~3u) | ((edge + 3u) & 3u)];  // Dprev(e) = InvRot(next[InvRot e])
+    dprev = (dprev & ~3u) | ((dprev + 3u) & 3u);
+    const Vertex &c1 = vd[pt[onext ^ 2]], &c2 = vd[pt[dprev]];
+    const double e1x = c1.x - pxd, e1y = c1.y - pyd, e2x = c2.x - pxd, e2y = c2.y - pyd;
+    const int right_of_onext = sgn(e1x * eoy - e1y * eox);
+    const int right_of_dprev = sgn(edx * e2y - edy * e2x);
     if (right_of_dprev > 0) {
       if (right_of_onext > 0 || (right_of_onext == 0 && right_of_curr == 0)) {
         location = LOC_INSIDE;
@@ -182,6 +201,8 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
       }
       right_of_curr = right_of_onext;
       edge = onext;
+      edx = e1x;
+      edy = e1y;
     } else {
       if (right_of_onext > 0) {
         if (right_of_dprev == 0 && right_of_curr == 0) {
@@ -190,23 +211,31 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
         }
         right_of_curr = right_of_dprev;
         edge = dprev;
+        eox = e2x;
+        eoy = e2y;
       } else if (right_of_curr == 0) {
-        const Vertex &dn = vd[pt[onext ^ 2]];
-        if (right_of(dn.x, dn.y, edge) >= 0) {
-          edge ^= 2;
+        if (right_of(c1.x, c1.y, edge) >= 0) {
+          edge ^= 2u;
+          std::swap(eox, edx);
+          std::swap(eoy, edy);
         } else {
           right_of_curr = right_of_onext;
           edge = onext;
+          edx = e1x;
+          edy = e1y;
         }
       } else {
         right_of_curr = right_of_onext;
         edge = onext;
+        edx = e1x;
+        edy = e1y;
       }
     }
   }
-  recent_ = edge;
+  recent_ = (int)edge;
+  int edge_out = (int)edge;
   if (location == LOC_INSIDE) {
-    const Vertex &vo = vtx_[org(edge)], &vd2 = vtx_[dst(edge)];
+    const Vertex &vo = vtx_[org(edge_out)], &vd2 = vtx_[dst(edge_out)];
     struct { float x, y; } o{(float)vo.x, (float)vo.y}, d{(float)vd2.x, (float)vd2.y};  // the float32 coordinates
     double t1 = fabs(px - o.x);  // float differences, as cv::Point2f arithmetic
     t1 += fabs(py - o.y);
@@ -216,22 +245,22 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
     t3 += fabs(o.y - d.y);
     if (t1 < FLT_EPSILON) {
       location = LOC_VERTEX;
-      vertex = org(edge);
-      edge = 0;
+      vertex = org(edge_out);
+      edge_out = 0;
     } else if (t2 < FLT_EPSILON) {
       location = LOC_VERTEX;
-      vertex = dst(edge);
-      edge = 0;
+      vertex = dst(edge_out);
+      edge_out = 0;
     } else if ((t1 < t3 || t2 < t3) && fabs(tri_area(px, py, o.x, o.y, d.x, d.y)) < FLT_EPSILON) {
       location = LOC_ON_EDGE;
       vertex = 0;
     }
   }
   if (location == LOC_ERROR) {
-    edge = 0;
+    edge_out = 0;
     vertex = 0;
   }
-  *out_edge = edge;
+  *out_edge = edge_out;
   *out_vertex = vertex;
   return location;
 }
@@ -265,96 +294,111 @@ int Subdiv::insert(float px, float py) {
 // splices.  Hot loop of the whole gvd half (about 55 flips per seed for seeds sorted along rows), so it works on raw
 // pointers (no re-loading of the vectors' data pointers after every store) and re-uses the orientation determinant
 // that isRightOf and isPtInCircle3 share.
-void Subdiv::flip_around(int curr_edge, int first_point, float px, float py) {
-  int *const nx = next_.data();
-  int *const pt = pt_.data();
+void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
+  // edge ids and vertex ids are non-negative: unsigned arithmetic keeps the index computations free of sign extensions
+  typedef unsigned U32;
+  U32 *const nx = reinterpret_cast<U32 *>(next_.data());
+  U32 *const pt = reinterpret_cast<U32 *>(pt_.data());
   Vertex *const vd = vtx_.data();
   const int max_edges = (int)next_.size();
-  auto gedge = [nx](int edge, int type) {
-    edge = nx[(edge & ~3) + ((edge + type) & 3)];
-    return (edge & ~3) + ((edge + (type >> 4)) & 3);
-  };
-  auto splice_raw = [nx](int a, int b) {
-    int &a_next = nx[a];
-    int &b_next = nx[b];
-    const int a_rot = (a_next & ~3) + ((a_next + 1) & 3);
-    const int b_rot = (b_next & ~3) + ((b_next + 1) & 3);
-    int &a_rot_next = nx[a_rot];
-    int &b_rot_next = nx[b_rot];
+  auto rot = [](U32 e) -> U32 { return (e & ~3u) | ((e + 1u) & 3u); };
+  auto splice_raw = [nx, rot](U32 a, U32 b) {
+    U32 &a_next = nx[a];
+    U32 &b_next = nx[b];
+    U32 &a_rot_next = nx[rot(a_next)];
+    U32 &b_rot_next = nx[rot(b_next)];
     std::swap(a_next, b_next);
     std::swap(a_rot_next, b_rot_next);
   };
   const double pxx = (double)px * px + (double)py * py;
   const double pxd = px, pyd = py;
+  const double eps = FLT_EPSILON * 0.125;
+  const bool fused = !g_literal_splices;
+  U32 e = (U32)curr_edge_i;
+  // The end points of e are carried from iteration to iteration (ring invariants: Oprev(e) shares e's origin, and the
+  // next link edge Lprev(Onext(e)) ends where e starts), so an iteration loads one or two vertices, not three.
+  U32 curr_org = pt[e];
+  double ox, oy, on2, dx, dy, dn2;
+  {
+    const Vertex &o = vd[curr_org], &d = vd[pt[e ^ 2u]];
+    ox = o.x, oy = o.y, on2 = o.n2;
+    dx = d.x, dy = d.y, dn2 = d.n2;
+  }
   for (int i = 0; i < max_edges; ++i) {
-    const int temp_edge = gedge(curr_edge, PREV_AROUND_ORG);
-    const int curr_org = pt[curr_edge], curr_dst = pt[curr_edge ^ 2];
-    const int temp_dst = pt[temp_edge ^ 2];
-    const Vertex &t = vd[temp_dst], &o = vd[curr_org], &d = vd[curr_dst];
-    // isRightOf(t, curr_edge) = sign of triangleArea(t, dst, org); the same determinant is the third term of
-    // isPtInCircle3(pt = org, a = t, b = dst, c = p)
-    const double area_tdo = tri_aread(t.x, t.y, d.x, d.y, o.x, o.y);
-    // evaluated unconditionally: the two data-dependent tests collapse into one branch
-    const double eps = FLT_EPSILON * 0.125;
-    double val = t.n2 * tri_aread(d.x, d.y, pxd, pyd, o.x, o.y);
-    val -= d.n2 * tri_aread(t.x, t.y, pxd, pyd, o.x, o.y);
+    // a = Oprev(e) = rot(next[rot e])
+    const U32 re = rot(e), Q = nx[re], a = rot(Q);
+    const U32 temp_dst = pt[a ^ 2u];
+    const Vertex &t = vd[temp_dst];
+    const double tx = t.x, ty = t.y, tn2 = t.n2;
+    // isRightOf(t, e) = sign of triangleArea(t, dst, org); the same determinant is the third term of
+    // isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated unconditionally: one branch for both tests
+    const double area_tdo = tri_aread(tx, ty, dx, dy, ox, oy);
+    double val = tn2 * tri_aread(dx, dy, pxd, pyd, ox, oy);
+    val -= dn2 * tri_aread(tx, ty, pxd, pyd, ox, oy);
     val += pxx * area_tdo;
-    val -= o.n2 * tri_aread(t.x, t.y, d.x, d.y, pxd, pyd);
-    const bool flip = (area_tdo > 0) & (val < -eps);
-    if (flip) {
-      // swapEdges(curr_edge): splice(e, a); splice(s, b); setEdgePoints(e, dst(a), dst(b)); splice(e, Lnext(a));
-      // splice(s, Lnext(b)) with a = Oprev(e), b = Oprev(s).  In a triangulation the four splices touch twelve
-      // `next` slots whose final values follow from the initial ones (derivation in DESIGN.md section 4, "Host hot loop"); they are
-      // read once and written once here instead of going through four dependent read-modify-write rounds.  The
-      // guards check the local structure that derivation assumes; anything else takes the literal splice sequence.
-      const int e = curr_edge, sedge = curr_edge ^ 2;
-      const int a = temp_edge;  // == getEdge(curr_edge, PREV_AROUND_ORG)
-      const int b = gedge(sedge, PREV_AROUND_ORG);
-      auto slot = [nx](int edge) -> int & { return nx[edge]; };
-      auto rot = [](int edge) { return (edge & ~3) + ((edge + 1) & 3); };
-      auto invrot = [](int edge) { return (edge & ~3) + ((edge + 3) & 3); };
-      const int c = slot(e), d = slot(sedge);
-      const int ia = invrot(a), ib = invrot(b);
-      const int U = slot(ia), U2 = slot(ib);
-      const int la = rot(U), lb = rot(U2);
-      if (slot(a) == e && slot(b) == sedge && la == (d ^ 2) && lb == (c ^ 2) && slot(la) == (a ^ 2) && slot(lb) == (b ^ 2)) {
-        const int rc = rot(c), re = rot(e), rd = rot(d), rs = rot(sedge);
-        const int P = slot(rc), Q = slot(re), P2 = slot(rd), Q2 = slot(rs);
-        slot(e) = a ^ 2;
-        slot(a) = c;
-        slot(la) = e;
-        slot(sedge) = b ^ 2;
-        slot(b) = d;
-        slot(lb) = sedge;
-        slot(rc) = Q;
-        slot(re) = U;
-        slot(ia) = P;
-        slot(rd) = Q2;
-        slot(rs) = U2;
-        slot(ib) = P2;
-        const int no = pt[a ^ 2], nd = pt[b ^ 2];
+    val -= on2 * tri_aread(tx, ty, dx, dy, pxd, pyd);
+    if ((area_tdo > 0) & (val < -eps)) {
+      // swapEdges(e): splice(e, a); splice(s, b); setEdgePoints(e, dst(a), dst(b)); splice(e, Lnext(a));
+      // splice(s, Lnext(b)) with s = Sym e, a = Oprev(e), b = Oprev(s).  In a triangulation the four splices touch
+      // twelve `next` slots whose final values follow from the initial ones ("Host hot loop");
+      // they are read once and written once.  Ring identities spare most of the rotations: with Q = next[rot e],
+      // Q2 = next[rot s], U = next[Q], U2 = next[Q2]:  a = rot Q, b = rot Q2, InvRot a = Q, InvRot b = Q2,
+      // Lnext-side edges la = rot U, lb = rot U2, and -- once the guards hold (la = Sym d, lb = Sym c) -- rot d = U,
+      // rot c = U2.  The guards check the local structure the derivation assumes; anything else takes the literal
+      // splice sequence.
+      const U32 s = e ^ 2u, rs = re ^ 2u;
+      const U32 Q2 = nx[rs], b = rot(Q2);
+      const U32 c = nx[e], dd = nx[s];
+      const U32 Uu = nx[Q], U2 = nx[Q2];
+      const U32 la = rot(Uu), lb = rot(U2);
+      const U32 no = pt[a ^ 2u], nd = pt[b ^ 2u];
+      if (fused & (nx[a] == e) & (nx[b] == s) & (la == (dd ^ 2u)) & (lb == (c ^ 2u)) & (nx[la] == (a ^ 2u)) & (nx[lb] == (b ^ 2u))) {
+        const U32 P = nx[U2], P2 = nx[Uu];  // slots rot c, rot d
+        nx[e] = a ^ 2u;
+        nx[a] = c;
+        nx[la] = e;
+        nx[s] = b ^ 2u;
+        nx[b] = dd;
+        nx[lb] = s;
+        nx[U2] = Q;   // rot c
+        nx[re] = Uu;
+        nx[Q] = P;    // InvRot a
+        nx[Uu] = Q2;  // rot d
+        nx[rs] = U2;
+        nx[Q2] = P2;  // InvRot b
         pt[e] = no;
-        pt[e ^ 2] = nd;
-        vd[no].first_edge = e;
-        vd[nd].first_edge = e ^ 2;
-        curr_edge = la;  // == getEdge(e, PREV_AROUND_ORG) after the flip: rot(next[rot e]) with next[rot e] = U
-        continue;
+        pt[s] = nd;
+        vd[no].first_edge = (int)e;
+        vd[nd].first_edge = (int)s;
+        e = la;  // == Oprev(e) after the flip: rot(next[rot e]) with next[rot e] = U
+        curr_org = no;  // Oprev shares the origin of the flipped edge, which now starts at dst(a) = t
+        ox = tx, oy = ty, on2 = tn2;
+        const Vertex &d = vd[pt[e ^ 2u]];
+        dx = d.x, dy = d.y, dn2 = d.n2;
       } else {
         splice_raw(e, a);
-        splice_raw(sedge, b);
-        const int no = pt[a ^ 2], nd = pt[b ^ 2];
+        splice_raw(s, b);
         pt[e] = no;
-        pt[e ^ 2] = nd;
-        vd[no].first_edge = e;
-        vd[nd].first_edge = e ^ 2;
-        splice_raw(e, gedge(a, NEXT_AROUND_LEFT));
-        splice_raw(sedge, gedge(b, NEXT_AROUND_LEFT));
+        pt[s] = nd;
+        vd[no].first_edge = (int)e;
+        vd[nd].first_edge = (int)s;
+        // Lnext(x) = rot(next[InvRot x]) with InvRot a = Q, InvRot b = Q2 read AFTER the first two splices
+        splice_raw(e, rot(nx[Q]));
+        splice_raw(s, rot(nx[Q2]));
+        e = rot(nx[rot(e)]);
+        curr_org = pt[e];
+        const Vertex &o = vd[curr_org], &d = vd[pt[e ^ 2u]];
+        ox = o.x, oy = o.y, on2 = o.n2;
+        dx = d.x, dy = d.y, dn2 = d.n2;
       }
-      curr_edge = gedge(curr_edge, PREV_AROUND_ORG);
-    } else if (curr_org == first_point) {
+    } else if (curr_org == (U32)first_point) {
       break;
     } else {
-      curr_edge = gedge(nx[curr_edge], PREV_AROUND_LEFT);
+      e = nx[nx[e]] ^ 2u;  // Lprev(Onext(e)) = Sym(next[next[e]]): ends at the old origin
+      dx = ox, dy = oy, dn2 = on2;
+      curr_org = pt[e];
+      const Vertex &o = vd[curr_org];
+      ox = o.x, oy = o.y, on2 = o.n2;
     }
   }
 }

@@ -7,6 +7,7 @@
 namespace aos {
 
 extern float g_outer_factor;
+extern bool g_literal_splices;
 
 class Subdiv {
  public:

@@ -236,6 +236,9 @@ AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, cons
  * only moves the far-away Voronoi vertices of hull cells, which filterNodesAndEdgesOutsideGrid crops.
  * Process-wide; default 6. */
 AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
+/* Test switch (process-wide): make every Lawson flip of the replay run swapEdges' four literal splices instead of
+ * the fused read-once / write-once update of the twelve `next` slots.  Same result; off by default. */
+AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
 
 /* Independent maps in flight (BASELINE.json config 5: sweeps over maps / parameters): item i runs aos_map_to_graph on
  * its own context (contexts may sit on different devices) from a pool of at most max_threads host threads

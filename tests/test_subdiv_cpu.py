@@ -84,3 +84,23 @@ def test_host_voronoi_reproduces_golden_facets():
         maxy = miny + float(np.float32(np.float32(int(g["h"])) * np.float32(g["res"])))
         xy, off = lib.voronoi_facets(g["g_merged_seeds"], minx, maxx, miny, maxy)
         assert np.array_equal(off, g["g_facet_off"]) and np.array_equal(xy.view(np.uint32), g["g_facets_xy"].view(np.uint32))
+
+
+def test_literal_splice_path_gives_the_same_facets(oracle):
+    """swapEdges as four literal splices (the replay's guarded fallback) == the fused slot update == cv2."""
+    from oracle import subdiv
+    L = lib.load()
+    rng = np.random.default_rng(321)
+    try:
+        for trial in range(25):
+            s = _seed_sets(rng, trial)
+            b = (0.0, 50.0, 0.0, 40.0)
+            fx, fo, _ = subdiv.voronoi_facets(s, *b)
+            L.aos_set_subdiv_literal_splices(1)
+            gx, go = lib.voronoi_facets(s, *b)
+            L.aos_set_subdiv_literal_splices(0)
+            hx, ho = lib.voronoi_facets(s, *b)
+            assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32))
+            assert np.array_equal(fo, ho) and np.array_equal(fx.view(np.uint32), hx.view(np.uint32))
+    finally:
+        L.aos_set_subdiv_literal_splices(0)
