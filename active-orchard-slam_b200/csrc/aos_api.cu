@@ -325,8 +325,6 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
   const size_t gbytes = (size_t)P.pitch * P.h * 4;
   DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch};
   for (DevBuf *g : grids) AOS_CUDA_OK(c, g->reserve(gbytes));
-  AOS_CUDA_OK(c, c->band_thin[0].reserve(gbytes));
-  AOS_CUDA_OK(c, c->band_thin[1].reserve(gbytes));
   AOS_CUDA_OK(c, c->misc.reserve(4096));
   cudaStream_t st = c->stream;
   AOS_CUDA_OK(c, cudaMemsetAsync(c->g_raw.p, 0, gbytes, st));
