@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "aos_grid_device_bits", "aos_get_labels", "aos_get_clusters", "aos_get_tree_rows", "aos_inflate_bits",
     "aos_open_bits", "aos_thin_bits", "aos_pack_int8", "aos_unpack_int8",
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
-    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_voronoi_facets_device", "aos_merge_seeds_device", "aos_trim_path", "aos_set_subdiv_outer_factor", "aos_set_subdiv_literal_splices",
+    "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_voronoi_facets_device", "aos_merge_seeds_device", "aos_trim_path", "aos_set_subdiv_outer_factor", "aos_set_subdiv_literal_splices", "aos_set_device_gate",
     "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_ipc_export", "aos_band_ipc_import",
     "aos_band_thin_launch_p2p", "aos_band_grid_device", "aos_seed_stage_tail",
 ]

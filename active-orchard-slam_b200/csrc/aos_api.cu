@@ -4,6 +4,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 
@@ -20,6 +22,47 @@ namespace {
 // finish together, which keeps the threads in lockstep (all uploading, then all computing); one copy at a time runs
 // at the full link rate and staggers the threads, so the upload of one map overlaps the host/GPU stages of the others.
 std::mutex g_upload_gate;
+
+// Kernel-phase gate (aos_set_device_gate): a counting semaphore per device.  Identical maps in flight on one GPU (one
+// context + host thread each) run in lockstep: all of them in their kernel phase at once -- the GPU time-slices 16
+// seed stages and every one of them finishes late -- then all in their host phase with the GPU idle.  Admitting only
+// a few maps at a time to the kernel phase staggers the threads after the first round, so later kernel phases meet a
+// mostly free GPU.  (One at a time is too strict: the phases are latency-bound and overlap each other well.)
+struct GateSlot {  // first come, first served: ticket t is admitted once fewer than `cap` earlier tickets are still inside
+  std::mutex m;
+  std::condition_variable cv;
+  unsigned long long next_ticket = 0, released = 0;
+};
+GateSlot g_device_gates[64];
+std::atomic<int> g_device_gate_cap{0};
+}  // namespace
+
+namespace aos {
+DeviceGate::DeviceGate(const Ctx *c) {
+  const int cap = g_device_gate_cap.load(std::memory_order_relaxed);
+  if (cap <= 0 || !c || c->device < 0 || c->device >= 64) return;
+  GateSlot &g = g_device_gates[c->device];
+  std::unique_lock<std::mutex> lk(g.m);
+  const unsigned long long t = g.next_ticket++;
+  g.cv.wait(lk, [&] {
+    const int k = g_device_gate_cap.load(std::memory_order_relaxed);
+    return k <= 0 || t < g.released + (unsigned long long)k;
+  });
+  dev = c->device;
+}
+void DeviceGate::release() {
+  if (dev < 0) return;
+  GateSlot &g = g_device_gates[dev];
+  {
+    std::lock_guard<std::mutex> lk(g.m);
+    ++g.released;
+  }
+  g.cv.notify_all();
+  dev = -1;
+}
+}  // namespace aos
+
+namespace {
 aos_status upload_points(aos_ctx *c, const void *points, size_t bytes, const void **dpoints) {
   AOS_CUDA_OK(c, c->points_stage.reserve(bytes));
   if (bytes >= ((size_t)64 << 20)) {
@@ -166,6 +209,12 @@ aos_status aos_set_stream(aos_ctx *c, void *cuda_stream) {
   }
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
+  return AOS_OK;
+}
+
+aos_status aos_set_device_gate(int32_t max_concurrent) {
+  g_device_gate_cap.store(max_concurrent > 0 ? max_concurrent : 0);
+  for (auto &g : g_device_gates) g.cv.notify_all();
   return AOS_OK;
 }
 
@@ -339,6 +388,8 @@ aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *poin
     if (s != AOS_OK) return s;
   }
   c->mark("h2d_points");
+  DeviceGate gate(c);  // kernel phase of this map: held to the end of the stage
+  c->mark("gate");
   unsigned long long *d_kept = reinterpret_cast<unsigned long long *>(c->misc.as<char>() + 1024);
   s = launch_bin(c, P, dpoints, n_points, point_step, off_x, off_y, off_z, c->g_raw.as<uint32_t>(), d_kept);
   if (s != AOS_OK) return s;

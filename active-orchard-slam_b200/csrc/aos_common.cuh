@@ -214,6 +214,16 @@ aos_status run_ror(Ctx *c, const void *dpoints, size_t n, uint32_t step, uint32_
 aos_status facets_prepare(Ctx *c, const Subdiv &sd, int *n_slots);  // *n_slots = -1: structure is not a triangulation
 aos_status facets_fill(Ctx *c, float2 *d_fxy, int *d_enext);
 void subdiv_release_pins(Ctx *c);  // host_gvd.cu
+
+// RAII hold of one slot of the per-device kernel-phase gate (aos_api.cu; a no-op unless aos_set_device_gate(n > 0))
+struct DeviceGate {
+  int dev = -1;
+  explicit DeviceGate(const Ctx *c);
+  ~DeviceGate() { release(); }
+  void release();
+  DeviceGate(const DeviceGate &) = delete;
+  DeviceGate &operator=(const DeviceGate &) = delete;
+};
 aos_status launch_edt(Ctx *c, const uint32_t *bits, int w, int h, uint32_t *nearest, int32_t *dist2);
 aos_status launch_edt_threshold(Ctx *c, const int32_t *dist2, int w, int h, int r2, uint32_t *out);
 aos_status launch_frame(Ctx *c, const uint32_t *in, uint32_t *out, int w, int h, int gx0, int gy0, int gx1, int gy1,

@@ -397,6 +397,7 @@ aos_status aos_map_to_graph_batch(aos_batch_item *items, int32_t n_items, int32_
       if (items[j].ctx == items[i].ctx && max_threads != 1) return AOS_ERR_INVALID;  // a context is not thread-safe
   }
   int nt = max_threads > 0 ? std::min(max_threads, n_items) : n_items;
+  if (nt >= 4) aos_set_device_gate(2);  // stagger the kernel phases of the maps in flight (see aos_set_device_gate)
   std::atomic<int> next{0};
   auto work = [&]() {
     for (int i = next.fetch_add(1); i < n_items; i = next.fetch_add(1)) {

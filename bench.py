@@ -122,6 +122,8 @@ def bench_ours(args):
         per_map = 2 * 16 * spec_probe.n_points + 1.5e9
         free_b, _ = torch.cuda.mem_get_info(local)
         T = max(1, min(T, int(0.85 * free_b / per_map)))
+    gate = (2 if T >= 4 else 0) if args.device_gate < 0 else args.device_gate
+    lib.load().aos_set_device_gate(gate)   # maps admitted to the seed stage's kernel phase at a time (0 = no limit)
     spec0 = synth.config(args.workload, seed=rank * 64, n_points=args.points)
     params = make_params(lib, spec0)
     gi = lib.grid_geometry(params)
@@ -236,7 +238,7 @@ def bench_ours(args):
             "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec0.grid_resolution} m, "
                                    f"{n_pts} points per map",
-                       "maps_in_flight": T, "step": f"{T} independent maps per GPU, one per stream/host thread "
+                       "maps_in_flight": T, "device_gate": gate, "step": f"{T} independent maps per GPU, one per stream/host thread "
                                                     "(the Subdiv2D replay of each map runs on its own host core)",
                        "host_cores": ncpu, "e2e_source": "pinned host memory" if pinned else "pageable host memory (pinning failed)",
                        "l2": "inputs (16 B x points per map) larger than L2; every map is re-read from HBM",
@@ -594,6 +596,9 @@ def main():
     ap.add_argument("--shard", default="maps", choices=["maps", "bands"],
                     help="maps: independent maps per GPU (default, weak scaling); bands: one grid row-band sharded")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--device-gate", type=int, default=-1,
+                    help="maps admitted to the seed stage's kernel phase at a time per GPU (aos_set_device_gate); 0 = no limit; "
+                         "default 2 when at least 4 maps are in flight")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -240,6 +240,13 @@ AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
  * the fused read-once / write-once update of the twelve `next` slots.  Same result; off by default. */
 AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
 
+/* Kernel-phase gate, process-wide, off (0) by default: at most `max_concurrent` maps per device are admitted to the
+ * seed stage's kernel phase (after the upload of their cloud) at a time; the others wait.  Identical maps in flight
+ * on one GPU otherwise run in lockstep -- all in their kernel phase, time-slicing the GPU, then all in their host
+ * phase (the Subdiv2D insertion replay) with the GPU idle; the gate staggers them after the first round.  Results
+ * do not change. */
+AOS_API aos_status aos_set_device_gate(int32_t max_concurrent);
+
 /* Independent maps in flight (BASELINE.json config 5: sweeps over maps / parameters): item i runs aos_map_to_graph on
  * its own context (contexts may sit on different devices) from a pool of at most max_threads host threads
  * (0 = one per item).  Two items may share a context only with max_threads == 1.  items[i].status receives each
