@@ -56,16 +56,50 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
+    def _sample_nvml(self, h, nv):
+        """One in-process NVML sample (microseconds of host time; `nvidia-smi` per sample costs a tenth of a second
+        of one core, which the maps in flight need)."""
+        R = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        def bit(*names):
+            for n in names:
+                v = getattr(nv, n, None)
+                if v is not None:
+                    return "Active" if (R & v) else "Not Active"
+            return "Not Active"
+        return [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                bit("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                bit("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+
     def _run(self):
+        h = nv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:   # NVML enumerates physical devices
+                tok = [t for t in vis.split(",") if t.strip()]
+                if idx < len(tok) and tok[idx].strip().isdigit():
+                    idx = int(tok[idx])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.index_physical = idx
+        except Exception:
+            h = None
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                if h is not None:
+                    self.rows.append(self._sample_nvml(h, nv))
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                h = None   # NVML call failed: fall back to nvidia-smi
+            self._stop.wait(0.1 if h is not None else 0.5)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
