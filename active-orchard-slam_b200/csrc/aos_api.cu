@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -66,9 +67,21 @@ namespace {
 aos_status upload_points(aos_ctx *c, const void *points, size_t bytes, const void **dpoints) {
   AOS_CUDA_OK(c, c->points_stage.reserve(bytes));
   if (bytes >= ((size_t)64 << 20)) {
+    static const bool dbg = getenv("AOS_DEBUG") != nullptr;
+    const auto t_wait = std::chrono::steady_clock::now();
     std::lock_guard<std::mutex> lock(g_upload_gate);
+    const auto t0 = std::chrono::steady_clock::now();
+    // One copy: cutting it into pieces (even with only two queued at a time) neither frees the copy engine for other
+    // streams' transfers -- it stays with this stream until it runs dry -- nor is it free (59.9 vs 57.7 ms per 3.2 GB).
+    // The other maps' small inputs therefore do not use the copy engine at all (h2d_small, k_misc.cu).
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, bytes, cudaMemcpyHostToDevice, c->stream));
     AOS_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (dbg) {
+      const auto t1 = std::chrono::steady_clock::now();
+      const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+      fprintf(stderr, "[aos] upload %.2f GB in %.1f ms (%.1f GB/s), waited %.1f ms at the gate\n", bytes / 1e9, ms,
+              bytes / 1e6 / ms, std::chrono::duration<double, std::milli>(t0 - t_wait).count());
+    }
   } else {
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->points_stage.p, points, bytes, cudaMemcpyHostToDevice, c->stream));
   }
@@ -188,6 +201,12 @@ void aos_destroy(aos_ctx *c) {
   c->pin_facet_xy.release();
   c->pin_enext.release();
   c->pin_rows.release();
+  c->h_seeds.release();
+  c->h_merged.release();
+  c->pin_seed_in.release();
+  c->pin_a.release();
+  c->pin_b.release();
+  c->pin_c.release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (int k = 0; k < 3; ++k) {
     if (c->aux[k]) cudaStreamDestroy(c->aux[k]);

@@ -85,7 +85,7 @@ static void sd_unpin(Ctx *c, int i) {
 static void sd_pin(Ctx *c, int i, const void *p, size_t bytes) {
   if (c->sd_pinned[i] == p && c->sd_pinned_bytes[i] == bytes) return;
   sd_unpin(c, i);
-  if (p && bytes && cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+  if (p && bytes && cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterMapped) == cudaSuccess) {
     c->sd_pinned[i] = const_cast<void *>(p);
     c->sd_pinned_bytes[i] = bytes;
   } else {
@@ -140,7 +140,7 @@ aos_status aos_merge_seeds_device(aos_ctx *c, const double *seeds_xy, int32_t n,
   AOS_CUDA_OK(c, cudaSetDevice(c->device));
   aos_status s = device_merge_seeds(c, seeds_xy, n);
   if (s != AOS_OK) return s;
-  if (!c->h_merged.empty()) memcpy(out_xy, c->h_merged.data(), sizeof(double) * c->h_merged.size());
+  if (c->h_merged.size()) memcpy(out_xy, c->h_merged.data(), sizeof(double) * c->h_merged.size());
   if (n_out) *n_out = (int32_t)(c->h_merged.size() / 2);
   return AOS_OK;
 }
@@ -266,13 +266,17 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   c->mark("gvd_skeleton_in");
 
   // voronoiSeedsCallback merge (gvd:93-125); processGraph drops non-finite seeds (gvd:266-270)
+  static const bool dbg = getenv("AOS_DEBUG") != nullptr;
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tg0 = dbg ? wall() : 0;
   {
     aos_status ms = device_merge_seeds(c, seeds_xy, n_seeds);
     if (ms != AOS_OK) return ms;
   }
+  const double tg1 = dbg ? wall() : 0;
   c->mark("gvd_merge_seeds");
   c->graph.n_merged_seeds = (int)(c->h_merged.size() / 2);
-  if (c->h_merged.empty()) {  // gvd:257 / :273: nothing to do
+  if (c->h_merged.size() == 0) {  // gvd:257 / :273: nothing to do
     set_error(c, "no valid seeds");
     return AOS_ERR_STATE;
   }
@@ -285,6 +289,7 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   const bool built = host_subdiv_build(sd, c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy,
                                        [c, &sd](size_t n) { sd_unpin_if_growing(c, sd, n); });
   c->mark("gvd_host_voronoi");
+  const double tg2 = dbg ? wall() : 0;
   if (!c->pin_rows.resize(4 * (size_t)n_rows)) {
     set_error(c, "cudaHostAlloc failed for the row staging buffer");
     return AOS_ERR_CUDA;
@@ -301,11 +306,13 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
     dev_slots = 0;
   }
   c->mark("gvd_facets");
+  const double tg3 = dbg ? wall() : 0;
   if (dev_slots >= 0) {
     in.device_facets = true;
     in.n_slots = dev_slots;
     aos_status s = run_graph(c, in);
     if (s != AOS_OK) return s;
+    if (dbg) fprintf(stderr, "[aos] gvd split: merge %.1f facets %.1f graph %.1f\n", tg1 - tg0, tg3 - tg2, wall() - tg3);
     c->have_graph = true;
     return AOS_OK;
   }
@@ -375,14 +382,23 @@ aos_status aos_get_graph(aos_ctx *c, aos_gvd_graph *out) {
 aos_status aos_map_to_graph(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points, uint32_t point_step,
                             uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
   if (!c) return AOS_ERR_INVALID;
+  static const bool dbg = getenv("AOS_DEBUG") != nullptr;
+  static const auto t_proc = std::chrono::steady_clock::now();
+  auto now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_proc).count(); };
+  const double t0 = dbg ? now() : 0;
   aos_status s = aos_seed_stage(c, p, points, n_points, point_step, off_x, off_y, off_z, points_mem);
   if (s != AOS_OK) return s;
+  const double t1 = dbg ? now() : 0;
   c->composite = true;  // keep one list of stage timers for the whole call
   s = aos_select_seeds(c, nullptr, nullptr);
+  const double t2 = dbg ? now() : 0;
   if (s == AOS_OK)
     s = aos_gvd_stage(c, c->h_seeds.data(), (int32_t)(c->h_seeds.size() / 2), c->h_rows_info.data(),
                       (int32_t)(c->h_rows_info.size() / 4), nullptr, nullptr);
   c->composite = false;
+  if (dbg)
+    fprintf(stderr, "[aos] map ctx %p start %.1f seed_stage %.1f select %.1f gvd %.1f end %.1f\n", (void *)c, t0, t1 - t0, t2 - t1,
+            now() - t2, now());
   return s;
 }
 

@@ -917,12 +917,22 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
 
+  // the per-cluster tables come back through page-locked staging (plain DMA; see Ctx::h_merged)
   c->h_clusters.resize(nc);
-  std::vector<RowOut> h_rows(nc);
-  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_clusters.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc,
-                                 cudaMemcpyDeviceToHost, st));
-  AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
-  AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+  if (!c->pin_a.resize(sizeof(aos_cluster) * (size_t)nc) || !c->pin_b.resize(sizeof(RowOut) * (size_t)nc)) {
+    set_error(c, "cudaHostAlloc failed (cluster tables)");
+    return AOS_ERR_CUDA;
+  }
+  RowOut *h_rows = reinterpret_cast<RowOut *>(c->pin_b.data());
+  auto fetch_tables = [&]() -> aos_status {
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->pin_a.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows, d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    memcpy(c->h_clusters.data(), c->pin_a.data(), sizeof(aos_cluster) * (size_t)nc);
+    return AOS_OK;
+  };
+  s = fetch_tables();
+  if (s != AOS_OK) return s;
 
   c->mark("cc_finalize");
   // ---- order-dependent clusters: replay the reference's BFS and finalise again --------------------
@@ -932,8 +942,12 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     if (h_rows[i].flags & (kFlagNeedsOrder | kFlagTie)) need.push_back(i);
   if (!need.empty()) {
     // bounding boxes come from the directional extremes already on the host-side? no: take them from acc
-    std::vector<ClusterAcc> h_acc(nc);
-    AOS_CUDA_OK(c, cudaMemcpyAsync(h_acc.data(), acc, sizeof(ClusterAcc) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    if (!c->pin_c.resize(sizeof(ClusterAcc) * (size_t)nc)) {
+      set_error(c, "cudaHostAlloc failed (cluster accumulators)");
+      return AOS_ERR_CUDA;
+    }
+    const ClusterAcc *h_acc = reinterpret_cast<const ClusterAcc *>(c->pin_c.data());
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->pin_c.data(), acc, sizeof(ClusterAcc) * (size_t)nc, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
     // shared-memory classes: bitmap words <= 2K (8 KB), <= 12K (48 KB), <= 50K (200 KB), else global bitmap
     const size_t class_words[3] = {2048, 12288, 51200};
@@ -972,15 +986,23 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     AOS_CUDA_OK(c, c->cl_stats.reserve(sizeof(ReplayJob) * total_jobs + sizeof(int) * total_jobs));
     ReplayJob *d_jobs = c->cl_stats.as<ReplayJob>();
     int *d_flagged = reinterpret_cast<int *>(d_jobs + total_jobs);
-    std::vector<ReplayJob> all;
-    std::vector<int> order;
-    for (int k = 0; k < 4; ++k)
-      for (const ReplayJob &j : jobs[k]) {
-        all.push_back(j);
-        order.push_back(j.cluster);
-      }
-    AOS_CUDA_OK(c, cudaMemcpyAsync(d_jobs, all.data(), sizeof(ReplayJob) * total_jobs, cudaMemcpyHostToDevice, st));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(d_flagged, order.data(), sizeof(int) * total_jobs, cudaMemcpyHostToDevice, st));
+    // jobs | cluster ids, staged in page-locked memory (pin_a is free again: h_clusters holds its copy)
+    if (!c->pin_a.resize((sizeof(ReplayJob) + sizeof(int)) * total_jobs)) {
+      set_error(c, "cudaHostAlloc failed (replay jobs)");
+      return AOS_ERR_CUDA;
+    }
+    ReplayJob *all = reinterpret_cast<ReplayJob *>(c->pin_a.data());
+    int *order = reinterpret_cast<int *>(all + total_jobs);
+    {
+      size_t q = 0;
+      for (int k = 0; k < 4; ++k)
+        for (const ReplayJob &j : jobs[k]) {
+          all[q] = j;
+          order[q++] = j.cluster;
+        }
+    }
+    s = h2d_small(c, d_jobs, all, (sizeof(ReplayJob) + sizeof(int)) * total_jobs, true);  // jobs | ids, contiguous on both sides
+    if (s != AOS_OK) return s;
     uint32_t *gvisited = prefix;  // compact indices are no longer needed: reuse as the global "unvisited" bitmap
     if (!jobs[3].empty()) AOS_CUDA_OK(c, cudaMemcpyAsync(gvisited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
     c->mark("replay_prep");
@@ -1023,10 +1045,8 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
                                                                          d_flagged, queue, centre, d_clusters, d_rows);
   ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_clusters.data(), d_clusters, sizeof(aos_cluster) * (size_t)nc,
-                                   cudaMemcpyDeviceToHost, st));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(RowOut) * (size_t)nc, cudaMemcpyDeviceToHost, st));
-    AOS_CUDA_OK(c, cudaStreamSynchronize(st));
+    s = fetch_tables();  // after the replay kernels consumed the job list: the copy engine has read pin_a by now
+    if (s != AOS_OK) return s;
   }
   c->mark("replay_finalize");
   for (int i = 0; i < nc; ++i)

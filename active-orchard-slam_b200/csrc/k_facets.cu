@@ -160,9 +160,12 @@ aos_status facets_prepare(Ctx *c, const Subdiv &sd, int *n_slots) {
   int *d_err = c->misc.as<int>() + 96;
   uint32_t *d_tot = reinterpret_cast<uint32_t *>(c->misc.as<int>() + 97);
   int *d_next = c->sd_quads.as<int>(), *d_pt = d_next + 4 * (size_t)nq;
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_next, sd.edge_next(), ebytes, cudaMemcpyHostToDevice, st));
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_pt, sd.edge_pt(), ebytes, cudaMemcpyHostToDevice, st));
-  AOS_CUDA_OK(c, cudaMemcpyAsync(c->sd_verts.p, sd.vertices(), sizeof(SdVertex) * (size_t)nv, cudaMemcpyHostToDevice, st));
+  {  // registered in place by the caller (sd_pinned[i] says whether that worked)
+    aos_status hs = h2d_small(c, d_next, sd.edge_next(), ebytes, c->sd_pinned[0] != nullptr);
+    if (hs == AOS_OK) hs = h2d_small(c, d_pt, sd.edge_pt(), ebytes, c->sd_pinned[1] != nullptr);
+    if (hs == AOS_OK) hs = h2d_small(c, c->sd_verts.p, sd.vertices(), sizeof(SdVertex) * (size_t)nv, c->sd_pinned[2] != nullptr);
+    if (hs != AOS_OK) return hs;
+  }
   AOS_CUDA_OK(c, cudaMemsetAsync(c->sd_vor.p, 0, sizeof(float2) * 2 * (size_t)nq, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(d_err, 0, 8, st));
   const SdEdges q{d_next, d_pt};

@@ -773,7 +773,10 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
     AOS_CUDA_OK(c, cudaMemcpyAsync(d_fxy, in.facet_xy, sizeof(float2) * K, cudaMemcpyHostToDevice, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(d_enext, in.enext, sizeof(int) * K, cudaMemcpyHostToDevice, st));
   }
-  if (n_rows) AOS_CUDA_OK(c, cudaMemcpyAsync(d_rows, in.rows_info, sizeof(double) * 4 * n_rows, cudaMemcpyHostToDevice, st));
+  if (n_rows) {
+    aos_status hs = h2d_small(c, d_rows, in.rows_info, sizeof(double) * 4 * n_rows, true);  // pin_rows
+    if (hs != AOS_OK) return hs;
+  }
   AOS_CUDA_OK(c, cudaMemsetAsync(d_state, 0, K, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(g5.h.keys, 0xff, sizeof(unsigned long long) * cap_pts, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(g5.h.val, 0xff, sizeof(int) * cap_pts, st));

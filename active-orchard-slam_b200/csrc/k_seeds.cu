@@ -442,10 +442,14 @@ aos_status device_select_seeds(Ctx *c) {
   cudaStream_t st = c->stream;
   const SeedDeviceParams &P = c->P;
   const int n_rows = (int)c->h_rows.size();
-  c->h_seeds.clear();
+  c->h_seeds.resize(0);
   c->seed_counts[0] = c->seed_counts[1] = c->seed_counts[2] = 0;
   if (n_rows == 0) return AOS_OK;
-  std::vector<RowDev> hr(n_rows);
+  if (!c->pin_a.resize(sizeof(RowDev) * (size_t)n_rows)) {
+    set_error(c, "cudaHostAlloc failed (rows staging)");
+    return AOS_ERR_CUDA;
+  }
+  RowDev *hr = reinterpret_cast<RowDev *>(c->pin_a.data());
   for (int i = 0; i < n_rows; ++i) {
     const aos_tree_row &r = c->h_rows[i];
     hr[i] = RowDev{r.center_x, r.center_y, r.start_x, r.start_y, r.end_x, r.end_y};
@@ -455,7 +459,10 @@ aos_status device_select_seeds(Ctx *c) {
   RowDev *d_rows = c->seed_buf.as<RowDev>();
   uint32_t *d_offs = reinterpret_cast<uint32_t *>(d_rows + n_rows);
   uint32_t *d_tot = d_offs + n_rows + 2;  // [0..3] totals, [4] pending flag
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_rows, hr.data(), sizeof(RowDev) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+  {
+    aos_status hs = h2d_small(c, d_rows, hr, sizeof(RowDev) * (size_t)n_rows, true);
+    if (hs != AOS_OK) return hs;
+  }
   vs_count_kernel<<<blocks_for((size_t)n_rows + 1), 256, 0, st>>>(P, d_rows, n_rows, d_offs);
   ++c->launches;
   aos_status s = exclusive_scan_u32(c, d_offs, (size_t)n_rows + 1, c->cc_blocksum, d_tot);
@@ -520,7 +527,10 @@ aos_status device_select_seeds(Ctx *c) {
   s = dedup_and_fetch(c, d_epts, d_est, n_end, g, cap, d_scan, d_out + counts[0] + counts[1], d_flag, d_tot + 3, &counts[2]);
   if (s != AOS_OK) return s;
   const int total = counts[0] + counts[1] + counts[2];
-  c->h_seeds.resize(2 * (size_t)total);
+  if (!c->h_seeds.resize(2 * (size_t)total)) {
+    set_error(c, "cudaHostAlloc failed (seeds)");
+    return AOS_ERR_CUDA;
+  }
   if (total > 0)
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_seeds.data(), d_out, sizeof(double2) * (size_t)total, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
@@ -531,7 +541,7 @@ aos_status device_select_seeds(Ctx *c) {
 // seeds (host, n x,y pairs) -> c->h_merged (merged seeds in leader order, non-finite dropped)
 aos_status device_merge_seeds(Ctx *c, const double *seeds, int n) {
   cudaStream_t st = c->stream;
-  c->h_merged.clear();
+  c->h_merged.resize(0);
   if (n <= 0) return AOS_OK;
   const unsigned cap = pow2_at_least((size_t)n * 2);
   const size_t N = (size_t)n;
@@ -560,7 +570,18 @@ aos_status device_merge_seeds(Ctx *c, const double *seeds, int n) {
   uint32_t *d_tot = reinterpret_cast<uint32_t *>(take(64));
   int *d_flag = reinterpret_cast<int *>(d_tot + 4);
 
-  AOS_CUDA_OK(c, cudaMemcpyAsync(d_pts, seeds, sizeof(double2) * N, cudaMemcpyHostToDevice, st));
+  if (seeds != c->h_seeds.data()) {  // caller-owned (pageable) memory: stage it, the copy below must be a plain DMA
+    if (!c->pin_seed_in.resize(2 * N)) {
+      set_error(c, "cudaHostAlloc failed (seed staging)");
+      return AOS_ERR_CUDA;
+    }
+    memcpy(c->pin_seed_in.data(), seeds, sizeof(double2) * N);
+    seeds = c->pin_seed_in.data();
+  }
+  {
+    aos_status hs = h2d_small(c, d_pts, seeds, sizeof(double2) * N, true);
+    if (hs != AOS_OK) return hs;
+  }
   AOS_CUDA_OK(c, cudaMemsetAsync(g.h.keys, 0xff, sizeof(unsigned long long) * cap, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(g.h.val, 0xff, sizeof(int) * cap, st));
   merge_init_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, d_state);
@@ -588,7 +609,10 @@ aos_status device_merge_seeds(Ctx *c, const double *seeds, int n) {
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
   const int m = c->h_flag[0];
-  c->h_merged.resize(2 * (size_t)m);
+  if (!c->h_merged.resize(2 * (size_t)m)) {
+    set_error(c, "cudaHostAlloc failed (merged seeds)");
+    return AOS_ERR_CUDA;
+  }
   if (m > 0) {
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_merged.data(), d_out, sizeof(double2) * (size_t)m, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
