@@ -67,5 +67,33 @@ def main():
               len(g["nodes"]), "edges", len(g["edges"]), os.path.getsize(path), "bytes")
 
 
+def trim_paths(name, g):
+    """Deterministic paths over a golden case's grid: random chords (some cross tree rows) and one along the frame."""
+    rng = np.random.default_rng(sum(map(ord, name)))
+    w, h, res, ox, oy = int(g["w"]), int(g["h"]), float(g["res"]), float(g["origin_x"]), float(g["origin_y"])
+    paths = []
+    for k in range(12):
+        a = np.array([ox + rng.uniform(1, w * res - 1), oy + rng.uniform(1, h * res - 1)])
+        b = np.array([ox + rng.uniform(1, w * res - 1), oy + rng.uniform(1, h * res - 1)])
+        t = np.linspace(0, 1, int(rng.integers(2, 600)))[:, None]
+        paths.append(a + (b - a) * t)
+    paths.append(np.stack([np.linspace(ox + 0.3, ox + w * res - 0.3, 200), np.full(200, oy + 0.12)], 1))   # hugs the frame
+    return paths
+
+
+def main_trim():
+    """tests/golden/trim_paths.npz: trimPathNearOccupiedRegions (path_gen:1570-1630) on the golden skeletons."""
+    out = {}
+    for name in CASES:
+        g = np.load(os.path.join(HERE, name + ".npz"))
+        skel = np.unpackbits(g["skel_framed"], axis=1, bitorder="little")[:, :int(g["w"])].astype(np.int8) * 100
+        kept = [O.trim_path(p, skel, float(g["origin_x"]), float(g["origin_y"]), g["res"], 0.2) for p in trim_paths(name, g)]
+        out[name] = np.array(kept, np.int32)
+        print(name, "trim kept", kept)
+    np.savez_compressed(os.path.join(HERE, "trim_paths.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--trim-only" not in sys.argv:
+        main()
+    main_trim()

@@ -47,3 +47,33 @@ def test_library_reproduces_golden_vectors(gpu_ctx, name):
         assert np.array_equal(gr[k], g["g_" + k]), k
     assert gr["n_voronoi_edges"] == int(g["g_counts"][0]) and gr["n_boundary_points"] == int(g["g_counts"][1])
     assert gr["n_merged_seeds"] == len(g["g_merged_seeds"])
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_device_steps_reproduce_golden_vectors(gpu_ctx, name):
+    """The device-side pieces of the gvd half on their own, against the golden vectors (no oracle at run time): the
+    0.5 m seed merge, circumcentres + facet walks (cv2.Subdiv2D's facets), and trimPathNearOccupiedRegions."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(here, name + ".npz"))
+    merged = gpu_ctx.merge_seeds_device(g["seeds"])
+    assert np.array_equal(merged.view(np.uint64), g["g_merged_seeds"].view(np.uint64))
+    minx, miny = float(g["origin_x"]), float(g["origin_y"])
+    maxx = minx + float(np.float32(np.float32(int(g["w"])) * np.float32(g["res"])))
+    maxy = miny + float(np.float32(np.float32(int(g["h"])) * np.float32(g["res"])))
+    xy, nxt = gpu_ctx.voronoi_facets_device(g["g_merged_seeds"], minx, maxx, miny, maxy)
+    off, fxy = g["g_facet_off"], g["g_facets_xy"]
+    keep = [(int(off[f]), int(off[f + 1])) for f in range(len(off) - 1) if off[f + 1] - off[f] >= 2]
+    want_xy = np.concatenate([fxy[a:b] for a, b in keep]) if keep else np.zeros((0, 2), np.float32)
+    assert np.array_equal(xy.view(np.uint32), want_xy.view(np.uint32))
+    base, want_next = 0, []
+    for a, b in keep:
+        n = np.arange(base + 1, base + (b - a) + 1, dtype=np.int32)
+        n[-1] = base
+        want_next.append(n)
+        base += b - a
+    assert np.array_equal(nxt, np.concatenate(want_next) if want_next else np.zeros(0, np.int32))
+    trim = np.load(os.path.join(here, "trim_paths.npz"))[name]
+    bits = np.ascontiguousarray(lib.pack_bits(np.unpackbits(g["skel_framed"], axis=1, bitorder="little")[:, :int(g["w"])] != 0))
+    info = (float(g["res"]), minx, miny, int(g["w"]))
+    got = [gpu_ctx.trim_path(p, 0.2, skeleton_bits=bits, info=info) for p in make_golden.trim_paths(name, g)]
+    assert got == list(trim)

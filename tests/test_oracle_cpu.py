@@ -205,3 +205,19 @@ def test_trim_path_oracle_against_vectorised_restatement(oracle):
                 want = i
                 break
         assert oracle.trim_path(path, g, ox, oy, res, d) == want
+
+
+def test_trim_path_oracle_reproduces_golden_counts(oracle):
+    """Drift check: orc_trim_path on the golden skeletons gives the committed pose counts (tests/golden/trim_paths.npz)."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_golden
+    trim = np.load(os.path.join(here, "trim_paths.npz"))
+    for name in sorted(make_golden.CASES):
+        g = np.load(os.path.join(here, name + ".npz"))
+        skel = np.unpackbits(g["skel_framed"], axis=1, bitorder="little")[:, :int(g["w"])].astype(np.int8) * 100
+        got = [oracle.trim_path(p, skel, float(g["origin_x"]), float(g["origin_y"]), g["res"], 0.2) for p in make_golden.trim_paths(name, g)]
+        assert got == list(trim[name])
+        assert any(1 < k < len(p) for k, p in zip(got, make_golden.trim_paths(name, g)))   # some paths are really cut mid-way
