@@ -284,8 +284,8 @@ def bench_ours(args):
             "gpu_launches": int(round(launches)),
             "roofline": {"bound": "hbm", "kernel": "bin_points_xyz16", "achieved": round(achieved, 1) if achieved else None,
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": 3281386832 if args.workload == "C3" and args.points is None else None,
-                         "traffic_source": "ncu --set full, profiles/r01_e_final_pipeline_c3.txt (dram read + write per launch)",
+                         "traffic": 3280462840 if args.workload == "C3" and args.points is None else None,
+                         "traffic_source": "ncu --set full, profiles/r01_n_pipeline_c3.txt (dram__bytes_read.sum 3.241483 GB + dram__bytes_write.sum 38.98 MB per launch)",
                          "peak_source": peak_src,
                          "whole_map": {"algorithmic_bytes": int(b_alg),
                                        "device_stages_gbs": round(b_alg / (gpu_ms * 1e-3) / 1e9, 1) if gpu_ms > 0 else None,
