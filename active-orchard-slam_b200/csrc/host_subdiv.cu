@@ -329,6 +329,8 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
     const U32 re = rot(e), Q = nx[re], a = rot(Q);
     const U32 temp_dst = pt[a ^ 2u];
     const Vertex &t = vd[temp_dst];
+    const U32 rs_h = re ^ 2u;
+    const U32 Q2_h = nx[rs_h], Uu_h = nx[Q], c_h = nx[e], dd_h = nx[e ^ 2u];  // the flip path's first loads, issued early
     const double tx = t.x, ty = t.y, tn2 = t.n2;
     // isRightOf(t, e) = sign of triangleArea(t, dst, org); the same determinant is the third term of
     // isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated unconditionally: one branch for both tests
@@ -344,15 +346,16 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
       // they are read once and written once.  Ring identities spare most of the rotations: with Q = next[rot e],
       // Q2 = next[rot s], U = next[Q], U2 = next[Q2]:  a = rot Q, b = rot Q2, InvRot a = Q, InvRot b = Q2,
       // Lnext-side edges la = rot U, lb = rot U2, and -- once the guards hold (la = Sym d, lb = Sym c) -- rot d = U,
-      // rot c = U2.  The guards check the local structure the derivation assumes; anything else takes the literal
-      // splice sequence.
-      const U32 s = e ^ 2u, rs = re ^ 2u;
-      const U32 Q2 = nx[rs], b = rot(Q2);
-      const U32 c = nx[e], dd = nx[s];
-      const U32 Uu = nx[Q], U2 = nx[Q2];
+      // rot c = U2.  The guards check the local structure the derivation assumes (that both faces are triangles;
+      // next[a] == e and next[b] == s are identities of the edge algebra and are not re-checked); anything else takes
+      // the literal splice sequence.
+      const U32 s = e ^ 2u, rs = rs_h;
+      const U32 Q2 = Q2_h, b = rot(Q2);
+      const U32 c = c_h, dd = dd_h;
+      const U32 Uu = Uu_h, U2 = nx[Q2];
       const U32 la = rot(Uu), lb = rot(U2);
       const U32 no = pt[a ^ 2u], nd = pt[b ^ 2u];
-      if (fused & (nx[a] == e) & (nx[b] == s) & (la == (dd ^ 2u)) & (lb == (c ^ 2u)) & (nx[la] == (a ^ 2u)) & (nx[lb] == (b ^ 2u))) {
+      if (fused & (la == (dd ^ 2u)) & (lb == (c ^ 2u)) & (nx[la] == (a ^ 2u)) & (nx[lb] == (b ^ 2u))) {
         const U32 P = nx[U2], P2 = nx[Uu];  // slots rot c, rot d
         nx[e] = a ^ 2u;
         nx[a] = c;
