@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -71,7 +72,10 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
+    // growing frees and re-allocates, and cudaFree / cudaFreeHost wait for the whole device: with many maps of varying
+    // size in flight every growth step stalls all of them.  Small buffers therefore start at 1 MB and double (a
+    // handful of steps to the steady state); only the big ones (point clouds, full-size planes) grow by an eighth.
+    size_t want = bytes < ((size_t)64 << 20) ? std::max<size_t>(2 * bytes, (size_t)1 << 20) : bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -96,7 +100,7 @@ struct PinVec {
       if (p) cudaFreeHost(p);
       p = nullptr;
       cap = 0;
-      size_t want = count + count / 4 + 64;
+      size_t want = std::max<size_t>(2 * count, ((size_t)64 << 10) / sizeof(T));  // see DevBuf::reserve
       if (cudaHostAlloc(reinterpret_cast<void **>(&p), want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) {
         n = 0;
         return false;

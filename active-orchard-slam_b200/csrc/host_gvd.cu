@@ -44,8 +44,12 @@ static bool host_subdiv_build(Subdiv &sd, const double *seeds, int n, double min
   // (round-half-even), OpenCV 4.5.4 as shipped with ROS 2 Humble (package.xml:48)
   const bool dbg = getenv("AOS_DEBUG") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
-  before_reserve((size_t)n);
-  sd.reserve((size_t)n);
+  // room for twice the seeds when the arrays have to grow at all (re-allocation also means un-pinning and pinning
+  // again, which stalls every map in flight), and never less than 4096 seeds
+  size_t want = std::max<size_t>((size_t)n, 4096);
+  if (3 * want + 16 > sd.quad_capacity() || 3 * want + 16 > sd.vertex_capacity()) want *= 2;
+  before_reserve(want);
+  sd.reserve(want);
   sd.init((int)lrint((double)rx), (int)lrint((double)ry), (int)lrint((double)rw), (int)lrint((double)rh));
   const float margin = 0.1f;
   for (int i = 0; i < n; ++i) {
