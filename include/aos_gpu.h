@@ -244,7 +244,8 @@ AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
  * seed stage's kernel phase (after the upload of their cloud) at a time; the others wait.  Identical maps in flight
  * on one GPU otherwise run in lockstep -- all in their kernel phase, time-slicing the GPU, then all in their host
  * phase (the Subdiv2D insertion replay) with the GPU idle; the gate staggers them after the first round.  Results
- * do not change. */
+ * do not change.  aos_map_to_graph_batch sets it to 2 when it runs four or more maps at a time (measured best at 16
+ * maps in flight; 1 serialises latency-bound phases that overlap well, larger values stagger less). */
 AOS_API aos_status aos_set_device_gate(int32_t max_concurrent);
 
 /* Independent maps in flight (BASELINE.json config 5: sweeps over maps / parameters): item i runs aos_map_to_graph on
