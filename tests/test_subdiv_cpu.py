@@ -104,3 +104,51 @@ def test_literal_splice_path_gives_the_same_facets(oracle):
             assert np.array_equal(fo, ho) and np.array_equal(fx.view(np.uint32), hx.view(np.uint32))
     finally:
         L.aos_set_subdiv_literal_splices(0)
+
+
+def _orchard_seed_order(rng, n_rows, per_row, pitch=4.0, half=1.95):
+    """Seeds in the order a real map produces them: row after row, walking along the row, alternating between the two
+    sides of the tree line (the insertion pattern with ~55 Lawson flips per seed that the replay's hot loop is tuned for)."""
+    out = []
+    for r in range(n_rows):
+        x0 = rng.uniform(0, 1)
+        slope = 0.002 * rng.uniform(-1, 1)
+        for i in range(per_row):
+            x = x0 + i * 0.98 + rng.normal(0, 0.01)
+            yc = 3.0 + pitch * r + slope * x
+            out.append((x, yc + half + rng.normal(0, 0.03)))
+            out.append((x + 0.006, yc - half + rng.normal(0, 0.03)))
+    return np.array(out)
+
+
+def test_replay_matches_cv2_on_a_map_sized_seed_order(oracle):
+    """16 k seeds in map order (rows of alternating sides), then 6 k uniform ones: the facets of the replay -- fused
+    flips and literal splices -- equal cv2.Subdiv2D's bit for bit."""
+    from oracle import subdiv
+    rng = np.random.default_rng(2024)
+    s = np.concatenate([_orchard_seed_order(rng, 20, 400), rng.uniform(1, 395, (6000, 2)) * [1.0, 0.2]])
+    b = (0.0, 400.0, 0.0, 90.0)
+    fx, fo, _ = subdiv.voronoi_facets(s, *b)
+    gx, go = lib.voronoi_facets(s, *b)
+    assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32))
+    L = lib.load()
+    try:
+        L.aos_set_subdiv_literal_splices(1)
+        hx, ho = lib.voronoi_facets(s[:6000], *b)
+    finally:
+        L.aos_set_subdiv_literal_splices(0)
+    kx, ko = lib.voronoi_facets(s[:6000], *b)
+    assert np.array_equal(ho, ko) and np.array_equal(hx.view(np.uint32), kx.view(np.uint32))
+
+
+def test_replay_matches_cv2_at_c3_size(oracle):
+    """240 k seeds in map order over 1 km x 1 km (the size of a C3 map's merged seed set): 1.4 M facet vertices,
+    bit for bit against cv2.Subdiv2D."""
+    from oracle import subdiv
+    rng = np.random.default_rng(77)
+    s = _orchard_seed_order(rng, 245, 490)
+    b = (0.0, 1000.0, 0.0, 1000.0)
+    fx, fo, _ = subdiv.voronoi_facets(s, *b)
+    gx, go = lib.voronoi_facets(s, *b)
+    assert len(go) - 1 == len(s) and len(gx) > 1_300_000
+    assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32))
