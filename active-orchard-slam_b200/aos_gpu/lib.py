@@ -222,6 +222,10 @@ class DevicePoints:
         return 4
 
 
+GRAPH_DIGEST_KEYS = ("nodes_xyz", "node_labels", "node_cluster_indices", "node_label_counts", "node_label_clusters",
+                     "node_label_types", "edges", "edge_lengths", "edge_clearances")
+
+
 class Context:
     """One libaos_gpu context (device buffers are reused call after call)."""
 
@@ -533,6 +537,44 @@ class Context:
         seeds = np.zeros((n.value, 2), np.float64)
         if n.value:
             self._check(self.L.aos_get_seeds(self.h, seeds.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_seeds")
+        m = C.c_int32()
+        self._check(self.L.aos_get_rows_info(self.h, None, 0, C.byref(m)), "aos_get_rows_info")
+        rows = np.zeros((m.value, 4), np.float64)
+        if m.value:
+            self._check(self.L.aos_get_rows_info(self.h, rows.ctypes.data_as(C.c_void_p), m.value, C.byref(m)), "aos_get_rows_info")
+        return seeds, tuple(counts), rows
+
+    def result_digest(self, parts: bool = False):
+        """sha256 over everything the path publishes after aos_map_to_graph / the band tail: the three published bit
+        grids (occupancy with its frame, skeleton, framed skeleton), the cluster table, rows, seeds and every GvdGraph
+        array in message order.  Used by bench.py and the tests to compare runs (maps in flight, GPUs, band splits,
+        the CPU oracle) without moving the arrays around.  parts=True also returns the per-array digests."""
+        import hashlib
+        per = {}
+        for name, gid in (("occupancy", GRID_OCCUPANCY), ("skeleton", GRID_SKELETON), ("skeleton_framed", GRID_SKELETON_FRAMED)):
+            per[name] = hashlib.sha256(np.ascontiguousarray(self.grid_bits(gid)).tobytes()).hexdigest()
+        per["clusters"] = hashlib.sha256(self.clusters().tobytes()).hexdigest()
+        per["rows"] = hashlib.sha256(self.tree_rows().tobytes()).hexdigest()
+        seeds, counts, rows_info = self.select_seeds_cached()
+        per["seeds"] = hashlib.sha256(seeds.tobytes()).hexdigest()
+        per["rows_info"] = hashlib.sha256(rows_info.tobytes()).hexdigest()
+        try:
+            g = self.graph()
+        except AosError:
+            g = None
+        for k in GRAPH_DIGEST_KEYS:
+            per["graph." + k] = hashlib.sha256(b"" if g is None else np.ascontiguousarray(g[k]).tobytes()).hexdigest()
+        total = hashlib.sha256("".join(f"{k}={per[k]};" for k in sorted(per)).encode()).hexdigest()
+        return (total, per) if parts else total
+
+    def select_seeds_cached(self):
+        """Seeds / counts / rows_info of the last aos_select_seeds or aos_map_to_graph on this context (no recompute)."""
+        n = C.c_int32()
+        self._check(self.L.aos_get_seeds(self.h, None, 0, C.byref(n)), "aos_get_seeds")
+        seeds = np.zeros((n.value, 2), np.float64)
+        if n.value:
+            self._check(self.L.aos_get_seeds(self.h, seeds.ctypes.data_as(C.c_void_p), n.value, C.byref(n)), "aos_get_seeds")
+        counts = (0, 0, 0)   # the split into virtual / ray / endpoint seeds is only returned by aos_select_seeds
         m = C.c_int32()
         self._check(self.L.aos_get_rows_info(self.h, None, 0, C.byref(m)), "aos_get_rows_info")
         rows = np.zeros((m.value, 4), np.float64)

@@ -168,3 +168,54 @@ def make_orchard_torch(spec: OrchardSpec, device, chunk: int = 1 << 24, y_range=
         out[s:s + m, 2] = torch.where(zc < 0.5, -1.5 + 2.0 * zc, 0.6 + 4.8 * (zc - 0.5))
     out[:, 3] = 1.0
     return out
+
+
+N_STRIPS = 64
+
+
+def make_orchard_strips_torch(spec: OrchardSpec, device, y_range=None, n_strips: int = N_STRIPS, chunk: int = 1 << 24):
+    """The orchard cloud generated in `n_strips` fixed horizontal strips, each from its OWN generator seed, so that the
+    union of the strips is one global cloud whatever subset a process generates: row-band sharding on N GPUs (every
+    rank generates the strips that touch its rows, y_range=(lo, hi)) then works on exactly the points a single GPU
+    gets with y_range=None, and the results can be compared digest for digest at N = 1, 2, 4, 8.
+    Strip s holds the trees whose centre y lies in it (all their points) and the clutter with y in it; the point count
+    of a strip is fixed by the spec alone."""
+    import torch
+
+    rng = np.random.default_rng(spec.seed)
+    centres_all = tree_centres(spec, rng)
+    y0, y1 = spec.origin_y - 1.0, spec.origin_y + spec.extent_y + 1.0
+    edges = np.linspace(y0, y1, n_strips + 1)
+    strip_of = np.clip(np.searchsorted(edges, centres_all[:, 1], side="right") - 1, 0, n_strips - 1)
+    n_clutter = int(spec.n_points * spec.clutter_frac)
+    n_tree_pts = spec.n_points - n_clutter
+    per_tree = n_tree_pts // max(len(centres_all), 1)
+    clutter_per_strip = n_clutter // n_strips
+    parts = []
+    for s in range(n_strips):
+        lo, hi = float(edges[s]), float(edges[s + 1])
+        if y_range is not None and (hi + spec.tree_radius + 0.01 < y_range[0] or lo - spec.tree_radius - 0.01 > y_range[1]):
+            continue
+        g = torch.Generator(device=device)
+        g.manual_seed(spec.seed * 1000003 + 7919 * s + 17)
+        c = torch.from_numpy(centres_all[strip_of == s]).to(device=device, dtype=torch.float32)
+        m = per_tree * c.shape[0]
+        out = torch.empty((m + clutter_per_strip, 4), dtype=torch.float32, device=device)
+        for a in range(0, m, chunk):
+            k = min(chunk, m - a)
+            idx = torch.randint(0, c.shape[0], (k,), generator=g, device=device)
+            r = spec.tree_radius * torch.sqrt(torch.rand(k, generator=g, device=device))
+            th = 2.0 * np.pi * torch.rand(k, generator=g, device=device)
+            out[a:a + k, 0] = c[idx, 0] + r * torch.cos(th)
+            out[a:a + k, 1] = c[idx, 1] + r * torch.sin(th)
+            out[a:a + k, 2] = -1.0 + 4.0 * torch.rand(k, generator=g, device=device)
+        k = clutter_per_strip
+        out[m:, 0] = spec.origin_x - 1.0 + (spec.extent_x + 2.0) * torch.rand(k, generator=g, device=device)
+        out[m:, 1] = lo + (hi - lo) * torch.rand(k, generator=g, device=device)
+        zc = torch.rand(k, generator=g, device=device)
+        out[m:, 2] = torch.where(zc < 0.5, -1.5 + 2.0 * zc, 0.6 + 4.8 * (zc - 0.5))
+        out[:, 3] = 1.0
+        parts.append(out)
+    if not parts:
+        return torch.empty((0, 4), dtype=torch.float32, device=device)
+    return torch.cat(parts, dim=0)
