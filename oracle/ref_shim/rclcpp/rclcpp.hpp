@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdio>
 #include <functional>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -91,6 +92,16 @@ struct Publisher {
 };
 template <class M>
 struct Subscription { using SharedPtr = std::shared_ptr<Subscription<M>>; };
+template <class S>
+struct Service { using SharedPtr = std::shared_ptr<Service<S>>; };
+template <class S>
+struct Client {
+  using SharedPtr = std::shared_ptr<Client<S>>;
+  using SharedFuture = std::shared_future<typename S::Response::SharedPtr>;
+  bool service_is_ready() const { return false; }
+  template <class... A> bool wait_for_service(A &&...) { return false; }
+  template <class R, class... A> SharedFuture async_send_request(R, A &&...) { return SharedFuture(); }
+};
 struct TimerBase { using SharedPtr = std::shared_ptr<TimerBase>; void cancel() {} };
 
 struct Parameter {
@@ -138,6 +149,10 @@ class Node {
   typename Subscription<M>::SharedPtr create_subscription(const std::string &, A &&...) {
     return std::make_shared<Subscription<M>>();
   }
+  template <class S, class... A>
+  typename Service<S>::SharedPtr create_service(const std::string &, A &&...) { return std::make_shared<Service<S>>(); }
+  template <class S, class... A>
+  typename Client<S>::SharedPtr create_client(const std::string &, A &&...) { return std::make_shared<Client<S>>(); }
   template <class... A>
   TimerBase::SharedPtr create_wall_timer(A &&...) { return std::make_shared<TimerBase>(); }
 

@@ -27,6 +27,8 @@ struct MultiArrayDimension { std::string label; uint32_t size = 0, stride = 0; }
 struct MultiArrayLayout { std::vector<MultiArrayDimension> dim; uint32_t data_offset = 0; };
 struct Float64MultiArray { MultiArrayLayout layout; std::vector<double> data; REF_SHIM_MSG_PTRS(Float64MultiArray) };
 struct Bool { bool data = false; REF_SHIM_MSG_PTRS(Bool) };
+struct Int32 { int32_t data = 0; REF_SHIM_MSG_PTRS(Int32) };
+struct String { std::string data; REF_SHIM_MSG_PTRS(String) };
 struct ColorRGBA { float r = 0, g = 0, b = 0, a = 0; };
 }}
 
@@ -37,6 +39,7 @@ struct Vector3 { double x = 0, y = 0, z = 0; };
 struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
 struct Pose { Point position; Quaternion orientation; REF_SHIM_MSG_PTRS(Pose) };
 struct PoseArray { std_msgs::msg::Header header; std::vector<Pose> poses; REF_SHIM_MSG_PTRS(PoseArray) };
+struct PoseStamped { std_msgs::msg::Header header; Pose pose; REF_SHIM_MSG_PTRS(PoseStamped) };
 struct Polygon { std::vector<Point32> points; };
 struct PolygonStamped { std_msgs::msg::Header header; Polygon polygon; REF_SHIM_MSG_PTRS(PolygonStamped) };
 }}
@@ -53,6 +56,23 @@ struct OccupancyGrid {
   MapMetaData info;
   std::vector<int8_t> data;
   REF_SHIM_MSG_PTRS(OccupancyGrid)
+};
+}}
+
+namespace nav_msgs { namespace msg {
+struct Path { std_msgs::msg::Header header; std::vector<geometry_msgs::msg::PoseStamped> poses; REF_SHIM_MSG_PTRS(Path) };
+}}
+
+namespace std_srvs { namespace srv {
+struct Empty {
+  struct Request { REF_SHIM_MSG_PTRS(Request) };
+  struct Response { REF_SHIM_MSG_PTRS(Response) };
+};
+}}
+namespace lio_sam_wo { namespace srv {   // external package (package.xml:38), only its type name is needed
+struct SaveMap {
+  struct Request { float resolution = 0; std::string destination; REF_SHIM_MSG_PTRS(Request) };
+  struct Response { bool success = false; REF_SHIM_MSG_PTRS(Response) };
 };
 }}
 
