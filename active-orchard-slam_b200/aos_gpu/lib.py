@@ -222,6 +222,30 @@ class DevicePoints:
         return 4
 
 
+CLUSTER_DIGEST_FIELDS = ("label", "size", "center_x", "center_y", "length", "sum_x", "sum_y", "max_d2")
+ROW_DIGEST_FIELDS = ("center_x", "center_y", "start_x", "start_y", "end_x", "end_y", "length", "cluster")
+DIGEST_DTYPES = {"occupancy": np.uint32, "skeleton": np.uint32, "skeleton_framed": np.uint32, "clusters.label": np.int32,
+                 "clusters.size": np.int32, "clusters.center_x": np.float32, "clusters.center_y": np.float32,
+                 "clusters.length": np.float32, "clusters.sum_x": np.int64, "clusters.sum_y": np.int64, "clusters.max_d2": np.int64,
+                 "rows.cluster": np.int32, "graph.nodes_xyz": np.float64, "graph.edge_lengths": np.float32,
+                 "graph.edge_clearances": np.float32}
+
+
+def digest_of(artefacts: dict, parts: bool = False):
+    """sha256 per named array (fixed dtype per name, C order) and one digest over all of them."""
+    import hashlib
+    per = {}
+    for k in sorted(artefacts):
+        v = artefacts[k]
+        if v is None:
+            per[k] = hashlib.sha256(b"").hexdigest()
+            continue
+        dt = DIGEST_DTYPES.get(k, np.float64 if k.startswith("rows.") or k in ("seeds", "rows_info") else np.int32)
+        per[k] = hashlib.sha256(np.ascontiguousarray(v, dtype=dt).tobytes()).hexdigest()
+    total = hashlib.sha256("".join(f"{k}={per[k]};" for k in sorted(per)).encode()).hexdigest()
+    return (total, per) if parts else total
+
+
 GRAPH_DIGEST_KEYS = ("nodes_xyz", "node_labels", "node_cluster_indices", "node_label_counts", "node_label_clusters",
                      "node_label_types", "edges", "edge_lengths", "edge_clearances")
 
@@ -544,28 +568,31 @@ class Context:
             self._check(self.L.aos_get_rows_info(self.h, rows.ctypes.data_as(C.c_void_p), m.value, C.byref(m)), "aos_get_rows_info")
         return seeds, tuple(counts), rows
 
-    def result_digest(self, parts: bool = False):
-        """sha256 over everything the path publishes after aos_map_to_graph / the band tail: the three published bit
-        grids (occupancy with its frame, skeleton, framed skeleton), the cluster table, rows, seeds and every GvdGraph
-        array in message order.  Used by bench.py and the tests to compare runs (maps in flight, GPUs, band splits,
-        the CPU oracle) without moving the arrays around.  parts=True also returns the per-array digests."""
-        import hashlib
-        per = {}
+    def result_artefacts(self) -> dict:
+        """Everything the path publishes after aos_map_to_graph / the band tail, as plain arrays keyed like
+        digest_of() expects: the three published bit grids, the cluster table, rows, seeds and every GvdGraph array."""
+        art = {}
         for name, gid in (("occupancy", GRID_OCCUPANCY), ("skeleton", GRID_SKELETON), ("skeleton_framed", GRID_SKELETON_FRAMED)):
-            per[name] = hashlib.sha256(np.ascontiguousarray(self.grid_bits(gid)).tobytes()).hexdigest()
-        per["clusters"] = hashlib.sha256(self.clusters().tobytes()).hexdigest()
-        per["rows"] = hashlib.sha256(self.tree_rows().tobytes()).hexdigest()
-        seeds, counts, rows_info = self.select_seeds_cached()
-        per["seeds"] = hashlib.sha256(seeds.tobytes()).hexdigest()
-        per["rows_info"] = hashlib.sha256(rows_info.tobytes()).hexdigest()
+            art[name] = self.grid_bits(gid)
+        cl, rows = self.clusters(), self.tree_rows()
+        for f in CLUSTER_DIGEST_FIELDS:
+            art["clusters." + f] = np.ascontiguousarray(cl[f])
+        for f in ROW_DIGEST_FIELDS:
+            art["rows." + f] = np.ascontiguousarray(rows[f])
+        seeds, _counts, rows_info = self.select_seeds_cached()
+        art["seeds"], art["rows_info"] = seeds, rows_info
         try:
             g = self.graph()
         except AosError:
             g = None
         for k in GRAPH_DIGEST_KEYS:
-            per["graph." + k] = hashlib.sha256(b"" if g is None else np.ascontiguousarray(g[k]).tobytes()).hexdigest()
-        total = hashlib.sha256("".join(f"{k}={per[k]};" for k in sorted(per)).encode()).hexdigest()
-        return (total, per) if parts else total
+            art["graph." + k] = None if g is None else g[k]
+        return art
+
+    def result_digest(self, parts: bool = False):
+        """sha256 over result_artefacts().  Used by bench.py and the tests to compare runs (maps in flight, GPUs, band
+        splits, the CPU oracle) without moving the arrays around.  parts=True also returns the per-array digests."""
+        return digest_of(self.result_artefacts(), parts)
 
     def select_seeds_cached(self):
         """Seeds / counts / rows_info of the last aos_select_seeds or aos_map_to_graph on this context (no recompute)."""

@@ -219,3 +219,59 @@ def make_orchard_strips_torch(spec: OrchardSpec, device, y_range=None, n_strips:
     if not parts:
         return torch.empty((0, 4), dtype=torch.float32, device=device)
     return torch.cat(parts, dim=0)
+
+
+def make_orchard_strips(spec: OrchardSpec, n_strips: int = N_STRIPS, threads: int = 0) -> np.ndarray:
+    """Full-size clouds on the CPU in seconds, bit-identical on every machine: the orchard recipe of make_orchard()
+    generated strip by strip (one numpy Generator per strip, strips in parallel threads) using only IEEE-exact
+    operations -- points are drawn in the square around a trunk and kept when x^2 + y^2 <= r^2 (no sin/cos, whose
+    vectorised implementations differ between CPUs), so digests of results on these clouds can be committed as golden
+    values (tests/golden/fullsize_digests.json).  Points are ordered strip by strip, tree-interleaved inside a strip."""
+    import concurrent.futures as cf
+    import os
+
+    rng0 = np.random.default_rng(spec.seed)
+    centres_all = tree_centres(spec, rng0).astype(np.float32)
+    y0, y1 = spec.origin_y - 1.0, spec.origin_y + spec.extent_y + 1.0
+    edges = np.linspace(y0, y1, n_strips + 1)
+    strip_of = np.clip(np.searchsorted(edges, centres_all[:, 1], side="right") - 1, 0, n_strips - 1)
+    n_clutter = int(spec.n_points * spec.clutter_frac)
+    n_tree_pts = spec.n_points - n_clutter
+    per_tree = n_tree_pts // max(len(centres_all), 1)
+    clutter_per_strip = n_clutter // n_strips
+    rad = np.float32(spec.tree_radius)
+
+    def one(s):
+        rng = np.random.default_rng([spec.seed, 7919, s])
+        c = centres_all[strip_of == s]
+        m = per_tree * len(c)
+        out = np.empty((m + clutter_per_strip, 4), np.float32)
+        got = 0
+        if m:
+            cand = int(m * 1.30) + 4096
+            u = rng.random((cand, 2), dtype=np.float32) * np.float32(2.0) - np.float32(1.0)
+            keep = np.nonzero(u[:, 0] * u[:, 0] + u[:, 1] * u[:, 1] <= np.float32(1.0))[0][:m]
+            got = len(keep)
+            idx = rng.integers(0, len(c), size=got)
+            out[:got, 0] = c[idx, 0] + rad * u[keep, 0]
+            out[:got, 1] = c[idx, 1] + rad * u[keep, 1]
+            out[:got, 2] = rng.random(got, dtype=np.float32) * np.float32(4.0) - np.float32(1.0)
+        k = clutter_per_strip
+        lo, hi = np.float32(edges[s]), np.float32(edges[s + 1])
+        out[got:got + k, 0] = np.float32(spec.origin_x - 1.0) + np.float32(spec.extent_x + 2.0) * rng.random(k, dtype=np.float32)
+        out[got:got + k, 1] = lo + (hi - lo) * rng.random(k, dtype=np.float32)
+        zc = rng.random(k, dtype=np.float32)
+        out[got:got + k, 2] = np.where(zc < np.float32(0.5), np.float32(-1.5) + np.float32(2.0) * zc,
+                                       np.float32(0.6) + np.float32(4.8) * (zc - np.float32(0.5)))
+        out[:, 3] = 1.0
+        return out[:got + k]
+
+    with cf.ThreadPoolExecutor(max_workers=threads or min(16, os.cpu_count() or 1)) as pool:
+        parts = list(pool.map(one, range(n_strips)))
+    total = sum(len(p) for p in parts)
+    pts = np.empty((total, 4), np.float32)
+    a = 0
+    for p in parts:
+        pts[a:a + len(p)] = p
+        a += len(p)
+    return pts

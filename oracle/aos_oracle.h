@@ -80,6 +80,11 @@ int orc_seed_stage(const orc_seed_params *p, const float *points, size_t n_point
                    size_t stride_floats, orc_seed_result *out);
 void orc_seed_result_free(orc_seed_result *r);
 
+/* Fast mode (aos_oracle_fast.h): hash-grid / convex-hull / multi-threaded variants of the quadratic and full-image
+ * loops with IDENTICAL results (tests/test_oracle_fast_cpu.py), so that config 3 finishes on a CPU.  Process-wide.
+ * skip_labels: do not materialise the per-cell label map (1.6 GB at config 3); result->labels is NULL then. */
+void orc_set_fast(int on, int threads, int skip_labels);
+
 /* individual steps, exposed for unit tests and for the bounded-sample CPU timing */
 void orc_active_bounds(const orc_seed_params *p, float *minx, float *maxx, float *miny, float *maxy);
 void orc_grid_dims(float minx, float maxx, float miny, float maxy, float res, int *w, int *h);

@@ -6,6 +6,7 @@
  * Python glue in oracle/subdiv.py calls the real cv2.Subdiv2D and hands the facets to this file.
  */
 #include "aos_oracle.h"
+#include "aos_oracle_fast.h"
 
 #include <float.h>
 #include <math.h>
@@ -15,7 +16,49 @@
 #define OCC 100
 
 /* ---- voronoiSeedsCallback, gvd:84-128 ----------------------------------------------------- */
+/* indexed variant: the members of seed i's group are the unused j > i within 0.5 m, visited in ascending j (the
+ * summation order); a 0.5 m hash grid yields the same candidates, sorted before use */
+static int merge_seeds_fast(const double *seeds, int n, double *out) {
+  const double merge_distance = 0.5;
+  uint8_t *used = (uint8_t *)calloc((size_t)n + 1, 1);
+  orc_sgrid g;
+  orc_sgrid_init(&g, 0.5005, n);
+  for (int i = 0; i < n; ++i) orc_sgrid_add(&g, seeds[2 * i], seeds[2 * i + 1]);
+  int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1));
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (used[i]) continue;
+    used[i] = 1;
+    double sx = seeds[2 * i], sy = seeds[2 * i + 1];
+    int cnt = 1;
+    if (isfinite(seeds[2 * i]) && isfinite(seeds[2 * i + 1])) { /* a non-finite seed is within 0.5 m of nothing */
+      int k = orc_sgrid_gather(&g, seeds[2 * i], seeds[2 * i + 1], 1, cand, n);
+      orc_sort_i32(cand, k);
+      for (int c = 0; c < k; ++c) {
+        int j = cand[c];
+        if (j <= i || used[j]) continue;
+        double dx = seeds[2 * i] - seeds[2 * j], dy = seeds[2 * i + 1] - seeds[2 * j + 1];
+        double dist = sqrt(dx * dx + dy * dy);
+        if (dist <= merge_distance) {
+          used[j] = 1;
+          sx += seeds[2 * j];
+          sy += seeds[2 * j + 1];
+          cnt++;
+        }
+      }
+    }
+    out[2 * m] = sx / (double)cnt;
+    out[2 * m + 1] = sy / (double)cnt;
+    m++;
+  }
+  free(cand);
+  free(used);
+  orc_sgrid_free(&g);
+  return m;
+}
+
 int orc_gvd_merge_seeds(const double *seeds, int n, double *out) {
+  if (orc_fast_enabled()) return merge_seeds_fast(seeds, n, out);
   const double merge_distance = 0.5;
   uint8_t *used = (uint8_t *)calloc((size_t)n + 1, 1);
   int m = 0;
@@ -213,6 +256,8 @@ static v2 cast_ray(const gridview *g, v2 sp, v2 other, double angle_offset_deg, 
 }
 
 /* ---- findVoronoiBoundaryPointNearEndpoint, gvd:686-790 -------------------------------------- */
+static const orc_sgrid *g_corner_grid = NULL; /* fast mode: 1 m hash grid over the cropped nodes, in node order */
+
 static v2 find_corner(const gridview *g, const v2 *nodes, int M, v2 endpoint, v2 other,
                       double target_angle_deg, double min_distance, double max_distance) {
   double mx = other.x - endpoint.x, my = other.y - endpoint.y;
@@ -227,7 +272,19 @@ static v2 find_corner(const gridview *g, const v2 *nodes, int M, v2 endpoint, v2
     double search_radius = radii[ri];
     double best = DBL_MAX;
     int best_i = -1;
-    for (int i = 0; i < M; ++i) {
+    /* fast mode: only nodes in the grid cells the search disc touches can pass `dist <= search_radius`; the winner is
+       the smallest distance, the lowest index among equals -- the same as the first strict minimum in node order */
+    int32_t *cand = NULL;
+    int ncand = -1;
+    if (g_corner_grid && search_radius <= 16.0 && isfinite(endpoint.x) && isfinite(endpoint.y)) {
+      int rings = (int)ceil(search_radius / g_corner_grid->cell) + 1;
+      ncand = orc_sgrid_gather(g_corner_grid, endpoint.x, endpoint.y, rings, NULL, 0);
+      cand = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ncand + 1));
+      orc_sgrid_gather(g_corner_grid, endpoint.x, endpoint.y, rings, cand, ncand);
+      orc_sort_i32(cand, ncand);
+    }
+    for (int ii = 0; ii < (ncand >= 0 ? ncand : M); ++ii) {
+      int i = ncand >= 0 ? cand[ii] : ii;
       double dx = nodes[i].x - endpoint.x, dy = nodes[i].y - endpoint.y;
       double dist = nrm(dx, dy);
       if (dist < min_distance || dist > search_radius) continue;
@@ -240,9 +297,38 @@ static v2 find_corner(const gridview *g, const v2 *nodes, int M, v2 endpoint, v2
       /* candidate; "closest among candidates", strict <, candidate order = node order */
       if (dist < best) { best = dist; best_i = i; }
     }
+    free(cand);
     if (best_i >= 0) return nodes[best_i];
   }
   return cast_ray(g, endpoint, other, target_angle_deg, min_distance);
+}
+
+/* nearest node of q by (distance, index): ring r of 5 cm cells is searched while a closer node could still be there
+ * (everything outside the (2r+1)^2 block is farther than r cells) */
+static int nearest_node_fast(const orc_sgrid *g, const v2 *bp, int M, v2 q) {
+  if (!isfinite(q.x) || !isfinite(q.y) || fabs(q.x) > 1e8 || fabs(q.y) > 1e8) {
+    int si = -1;
+    double md = DBL_MAX;
+    for (int i = 0; i < M; ++i) { double d = nrm(bp[i].x - q.x, bp[i].y - q.y); if (d < md) { md = d; si = i; } }
+    return si;
+  }
+  for (int rings = 1; rings <= 64; rings *= 2) {
+    int32_t cand[512];
+    int m = orc_sgrid_gather(g, q.x, q.y, rings, cand, 512);
+    if (m > 512) break;
+    double md = DBL_MAX;
+    int si = -1;
+    for (int k = 0; k < m; ++k) {
+      int i = cand[k];
+      double d = nrm(bp[i].x - q.x, bp[i].y - q.y);
+      if (d < md || (d == md && i < si)) { md = d; si = i; }
+    }
+    if (si >= 0 && md < (double)rings * 0.05) return si;   /* nothing outside the block can be closer or equal */
+  }
+  int si = -1;
+  double md = DBL_MAX;
+  for (int i = 0; i < M; ++i) { double d = nrm(bp[i].x - q.x, bp[i].y - q.y); if (d < md) { md = d; si = i; } }
+  return si;
 }
 
 int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
@@ -278,6 +364,10 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
   i64set keys;
   set_init(&keys, (size_t)ne + 16);
   const double threshold = 0.05;
+  const int fast = orc_fast_enabled();
+  orc_sgrid bpgrid;
+  memset(&bpgrid, 0, sizeof(bpgrid));
+  if (fast) orc_sgrid_init(&bpgrid, 0.05005, ne + 16);
   for (int e = 0; e < ne; ++e) {
     for (int side = 0; side < 2; ++side) {
       v2 q = side == 0 ? es[e] : ee[e];
@@ -285,11 +375,25 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
       int64_t key = ((int64_t)ix << 32) ^ (uint32_t)iy;
       if (set_has(&keys, key)) continue;
       int too_close = 0;
+      if (fast) { /* existence of an accepted point closer than 5 cm: the 3x3 block of 5 cm cells holds them all */
+        int32_t cand[64];
+        int m = orc_sgrid_gather(&bpgrid, q.x, q.y, 1, cand, 64);
+        if (m > 64) m = -1;
+        for (int k = 0; k < m; ++k) {
+          double dx = bp[cand[k]].x - q.x, dy = bp[cand[k]].y - q.y;
+          if (dx * dx + dy * dy < threshold * threshold) { too_close = 1; break; }
+        }
+        if (m < 0)
+          for (int i = 0; i < M; ++i) {
+            double dx = bp[i].x - q.x, dy = bp[i].y - q.y;
+            if (dx * dx + dy * dy < threshold * threshold) { too_close = 1; break; }
+          }
+      } else
       for (int i = 0; i < M; ++i) {
         double dx = bp[i].x - q.x, dy = bp[i].y - q.y;
         if (dx * dx + dy * dy < threshold * threshold) { too_close = 1; break; }
       }
-      if (!too_close) { set_add(&keys, key); bp[M++] = q; }
+      if (!too_close) { set_add(&keys, key); bp[M++] = q; if (fast) orc_sgrid_add(&bpgrid, q.x, q.y); }
     }
   }
   free(keys.k); free(keys.u);
@@ -304,9 +408,14 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
     for (int e = 0; e < ne; ++e) {
       int si = -1, ei = -1;
       double md = DBL_MAX;
+      if (fast) {
+        si = nearest_node_fast(&bpgrid, bp, M, es[e]);
+        ei = nearest_node_fast(&bpgrid, bp, M, ee[e]);
+      } else {
       for (int i = 0; i < M; ++i) { double d = nrm(bp[i].x - es[e].x, bp[i].y - es[e].y); if (d < md) { md = d; si = i; } }
       md = DBL_MAX;
       for (int i = 0; i < M; ++i) { double d = nrm(bp[i].x - ee[e].x, bp[i].y - ee[e].y); if (d < md) { md = d; ei = i; } }
+      }
       if (si >= 0 && ei >= 0 && si != ei) {
         int a = si, b = ei;
         if (a > b) { int t = a; a = b; b = t; }
@@ -323,8 +432,22 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
       }
     }
     const double nearby = 0.5;
-    for (int i = 0; i < M; ++i)
-      for (int j = i + 1; j < M; ++j) {
+    orc_sgrid pgrid;
+    memset(&pgrid, 0, sizeof(pgrid));
+    int32_t *pc = NULL;
+    if (fast) {
+      orc_sgrid_init(&pgrid, 0.5005, M + 16);
+      for (int i = 0; i < M; ++i) orc_sgrid_add(&pgrid, bp[i].x, bp[i].y);
+      pc = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M + 1));
+    }
+    for (int i = 0; i < M; ++i) {
+      /* fast mode: the j > i within 0.5 m all sit in the 3x3 block of 0.5 m cells; visited in ascending j as the
+         double loop does (the order decides the order of the appended edges) */
+      int nj = fast ? orc_sgrid_gather(&pgrid, bp[i].x, bp[i].y, 1, pc, M) : M - (i + 1);
+      if (fast) orc_sort_i32(pc, nj);
+      for (int jj = 0; jj < nj; ++jj) {
+        int j = fast ? pc[jj] : i + 1 + jj;
+        if (j <= i) continue;
         double dist = nrm(bp[i].x - bp[j].x, bp[i].y - bp[j].y);
         if (dist <= nearby && dist > 1e-6) {
           int64_t key = ((int64_t)i << 32) ^ (uint32_t)j;
@@ -337,7 +460,10 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
           }
         }
       }
+    }
+    if (fast) { orc_sgrid_free(&pgrid); free(pc); }
   }
+  if (fast) orc_sgrid_free(&bpgrid);
   free(added.k); free(added.u);
   free(es); free(ee);
 
@@ -370,6 +496,13 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
    * swapped so that ep1.x <= ep2.x (gvd:135-146) */
   out->corner_points = (double *)malloc(sizeof(double) * 8 * (size_t)(n_rows + 1));
   int have_corners = N > 0;
+  orc_sgrid cgrid;
+  memset(&cgrid, 0, sizeof(cgrid));
+  if (fast && N > 0) {
+    orc_sgrid_init(&cgrid, 1.0, N + 16);
+    for (int i = 0; i < N; ++i) orc_sgrid_add(&cgrid, nodes[i].x, nodes[i].y);
+    g_corner_grid = &cgrid;
+  }
   for (int r = 0; r < n_rows && have_corners; ++r) {
     v2 s = {rows_info[4 * r], rows_info[4 * r + 1]}, e = {rows_info[4 * r + 2], rows_info[4 * r + 3]};
     if (s.x > e.x) { v2 t = s; s = e; e = t; }
@@ -381,6 +514,16 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
     for (int k = 0; k < 4; ++k) { out->corner_points[8 * r + 2 * k] = c[k].x; out->corner_points[8 * r + 2 * k + 1] = c[k].y; }
   }
   int n_corner_rows = have_corners ? n_rows : 0;
+  if (g_corner_grid) { g_corner_grid = NULL; orc_sgrid_free(&cgrid); }
+  /* fast mode: corner points in a 0.1 m hash grid, index = 4 * row + corner, so ascending index = the (row, corner)
+     order of the double loop below */
+  orc_sgrid lgrid;
+  memset(&lgrid, 0, sizeof(lgrid));
+  if (fast) {
+    orc_sgrid_init(&lgrid, 0.1001, 4 * n_corner_rows + 16);
+    for (int r = 0; r < n_corner_rows; ++r)
+      for (int k = 0; k < 4; ++k) orc_sgrid_add(&lgrid, out->corner_points[8 * r + 2 * k], out->corner_points[8 * r + 2 * k + 1]);
+  }
 
   /* publishGraph, gvd:897-1010 */
   out->n_nodes = N;
@@ -396,8 +539,14 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
     out->nodes[2 * i] = nodes[i].x;
     out->nodes[2 * i + 1] = nodes[i].y;
     int mask = 0, cidx = -1, cnt = 0;
-    for (int r = 0; r < n_corner_rows; ++r)
-      for (int k = 0; k < 4; ++k) {
+    int32_t lc[64];
+    int nlc = fast ? orc_sgrid_gather(&lgrid, nodes[i].x, nodes[i].y, 1, lc, 64) : 4 * n_corner_rows;
+    int use_lc = fast && nlc <= 64;
+    if (use_lc) orc_sort_i32(lc, nlc);
+    else nlc = 4 * n_corner_rows;
+    for (int q = 0; q < nlc; ++q) {
+      {
+        int r = (use_lc ? lc[q] : q) / 4, k = (use_lc ? lc[q] : q) % 4;
         double d = nrm(nodes[i].x - out->corner_points[8 * r + 2 * k], nodes[i].y - out->corner_points[8 * r + 2 * k + 1]);
         if (d < tol) {
           mask |= 1 << k;
@@ -413,10 +562,12 @@ int orc_gvd_graph(const float *facet_xy, const int32_t *facet_off, int n_facets,
           if (cidx == -1) cidx = r;
         }
       }
+    }
     out->node_labels[i] = mask;
     out->node_cluster_indices[i] = cidx;
     out->node_label_counts[i] = cnt;
   }
+  if (fast) orc_sgrid_free(&lgrid);
   out->n_label_entries = nl;
   out->n_edges = nf;
   out->edges = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(nf + 1));

@@ -5,6 +5,7 @@
  * Citations: /root/reference/src/aos_seed_gen_node.cpp (abbreviated "sg").
  */
 #include "aos_oracle.h"
+#include "aos_oracle_fast.h"
 
 #include <float.h>
 #include <math.h>
@@ -300,7 +301,8 @@ static void cluster_cells(const orc_seed_params *p, const int8_t *grid, int w, i
   const int use_poly = p->n_poly > 0;
   size_t n = (size_t)w * (size_t)h;
   uint8_t *visited = (uint8_t *)calloc(n, 1);
-  for (size_t k = 0; k < n; ++k) labels[k] = -1;
+  if (labels)
+    for (size_t k = 0; k < n; ++k) labels[k] = -1;
   static const int ddx[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
   static const int ddy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
   memset(cs, 0, sizeof(*cs));
@@ -354,7 +356,7 @@ static void cluster_cells(const orc_seed_params *p, const int8_t *grid, int w, i
         sum_y += gy;
         isx += gx;
         isy += gy;
-        labels[cs->cells[k]] = (int32_t)index;
+        if (labels) labels[cs->cells[k]] = (int32_t)index;
       }
       size_t cnt = (size_t)(end - beg);
       cs->first[c] = (int32_t)index;
@@ -366,7 +368,8 @@ static void cluster_cells(const orc_seed_params *p, const int8_t *grid, int w, i
       /* sg:1062-1074: max over pairs of float(sqrt(int d2) * res); monotone in d2 */
       int64_t maxd2 = 0;
       float max_distance = 0.0f;
-      for (int a = beg; a < end; ++a) {
+      if (orc_fast_enabled()) maxd2 = orc_fast_max_pair_d2(cs->cells + beg, end - beg, w); /* same maximum, via the hull */
+      else for (int a = beg; a < end; ++a) {
         int ax = cs->cells[a] % w, ay = cs->cells[a] / w;
         for (int b = a + 1; b < end; ++b) {
           int dx = ax - cs->cells[b] % w, dy = ay - cs->cells[b] / w;
@@ -390,8 +393,16 @@ static void cluster_cells(const orc_seed_params *p, const int8_t *grid, int w, i
 typedef struct {
   double *xy;
   int n, cap;
+  orc_sgrid *grid; /* fast mode: hash grid over the points pushed so far (cell slightly above the largest radius asked) */
 } ptlist;
 static void pl_push(ptlist *l, double x, double y) {
+  if (orc_fast_enabled()) {
+    if (!l->grid) {
+      l->grid = (orc_sgrid *)malloc(sizeof(orc_sgrid));
+      orc_sgrid_init(l->grid, 0.5005, 1024);
+    }
+    orc_sgrid_add(l->grid, x, y);
+  }
   if (l->n == l->cap) {
     l->cap = l->cap ? l->cap * 2 : 256;
     l->xy = (double *)realloc(l->xy, sizeof(double) * 2 * (size_t)l->cap);
@@ -402,6 +413,17 @@ static void pl_push(ptlist *l, double x, double y) {
 }
 /* first-come duplicate test used all over sg (dist < 0.5) */
 static int pl_has_within(const ptlist *l, double x, double y, double r) {
+  if (l->grid && r <= 0.5) { /* existence test: the order of the candidates does not matter */
+    int32_t cand[256];
+    int m = orc_sgrid_gather(l->grid, x, y, 1, cand, 256);
+    if (m <= 256) {
+      for (int k = 0; k < m; ++k) {
+        double ddx = l->xy[2 * cand[k]] - x, ddy = l->xy[2 * cand[k] + 1] - y;
+        if (sqrt(ddx * ddx + ddy * ddy) < r) return 1;
+      }
+      return 0;
+    }
+  }
   for (int i = 0; i < l->n; ++i) {
     double ddx = l->xy[2 * i] - x, ddy = l->xy[2 * i + 1] - y;
     double dist = sqrt(ddx * ddx + ddy * ddy); /* std::pow(.,2) == exact square */
@@ -541,15 +563,23 @@ int orc_seed_stage(const orc_seed_params *p, const float *points, size_t n_point
   out->opened = (int8_t *)malloc(n);
   out->skel = (int8_t *)malloc(n);
   out->skel_framed = (int8_t *)malloc(n);
-  out->labels = (int32_t *)malloc(sizeof(int32_t) * n);
+  out->labels = orc_fast_skip_labels() ? NULL : (int32_t *)malloc(sizeof(int32_t) * n);
 
-  orc_bin_points(p, points, n_points, stride_floats, w, h, out->origin_x, out->origin_y, out->occ_raw);
+  const int fast = orc_fast_enabled(); /* indexed / threaded variants with identical results (aos_oracle_fast.h) */
   int inflation_cells = (int)(p->inflation_radius / p->grid_resolution); /* sg:936 float division */
-  orc_inflate(out->occ_raw, w, h, inflation_cells, out->occ_inflated);
+  if (fast) {
+    orc_fast_bin_points(p, points, n_points, stride_floats, w, h, out->origin_x, out->origin_y, out->occ_raw);
+    orc_fast_inflate(out->occ_raw, w, h, inflation_cells, out->occ_inflated);
+  } else {
+    orc_bin_points(p, points, n_points, stride_floats, w, h, out->origin_x, out->origin_y, out->occ_raw);
+    orc_inflate(out->occ_raw, w, h, inflation_cells, out->occ_inflated);
+  }
   orc_mark_borders(out->occ_inflated, w, h, out->occ_border);
-  orc_open_cross(out->occ_inflated, w, h, out->opened); /* skeleton of the UN-bordered grid, sg:560 */
+  if (fast) orc_fast_open_cross(out->occ_inflated, w, h, out->opened);
+  else orc_open_cross(out->occ_inflated, w, h, out->opened); /* skeleton of the UN-bordered grid, sg:560 */
   memcpy(out->skel, out->opened, n);
-  orc_thin_zhangsuen(out->skel, w, h);
+  if (fast) orc_fast_thin_zhangsuen(out->skel, w, h);
+  else orc_thin_zhangsuen(out->skel, w, h);
 
   cluster_set cs;
   cluster_cells(p, out->skel, w, h, out->origin_x, out->origin_y, &cs, out->labels);
@@ -737,6 +767,11 @@ int orc_seed_stage(const orc_seed_params *p, const float *points, size_t n_point
   free(virt.xy);
   free(ray.xy);
   free(endp.xy);
+  {
+    ptlist *ls[3] = {&virt, &ray, &endp};
+    for (int k = 0; k < 3; ++k)
+      if (ls[k]->grid) { orc_sgrid_free(ls[k]->grid); free(ls[k]->grid); }
+  }
 
   /* Step 9: frame AFTER clustering, sg:572 */
   orc_frame_polygon_bbox(p, out->skel, w, h, out->origin_x, out->origin_y, out->skel_framed);

@@ -18,7 +18,8 @@ _SO = os.path.join(_HERE, "_build", "libaos_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("aos_oracle_seed.c", "aos_oracle_gvd.c", "aos_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("aos_oracle_seed.c", "aos_oracle_gvd.c", "aos_oracle_fast.c", "aos_oracle_fast.h",
+                                             "aos_oracle.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -87,6 +88,7 @@ def lib():
         _lib.orc_point_in_polygon.restype = C.c_int
         _lib.orc_thin_zhangsuen.argtypes = [_P8, C.c_int, C.c_int]
         _lib.orc_thin_zhangsuen.restype = C.c_int
+        _lib.orc_set_fast.argtypes = [C.c_int, C.c_int, C.c_int]
         for name in ("orc_inflate",):
             getattr(_lib, name).argtypes = [_P8, C.c_int, C.c_int, C.c_int, _P8]
         for name in ("orc_mark_borders", "orc_open_cross"):
@@ -120,6 +122,13 @@ class SeedParams:
         return p
 
 
+def set_fast(on: bool, threads: int = 0, skip_labels: bool = False) -> None:
+    """Switch the oracle to its indexed / multi-threaded loops (identical results; see aos_oracle_fast.h)."""
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    lib().orc_set_fast(int(on), int(threads), int(skip_labels))
+
+
 def _arr(ptr, n, dtype):
     if n == 0:
         return np.zeros(0, dtype)
@@ -138,7 +147,7 @@ def seed_stage(params: SeedParams, points: np.ndarray) -> dict:
     out = dict(w=r.w, h=r.h, origin_x=r.origin_x, origin_y=r.origin_y, res=np.float32(r.res))
     for k in ("occ_raw", "occ_inflated", "occ_border", "opened", "skel", "skel_framed"):
         out[k] = _arr(getattr(r, k), n, np.int8).reshape(r.h, r.w)
-    out["labels"] = _arr(r.labels, n, np.int32).reshape(r.h, r.w)
+    out["labels"] = _arr(r.labels, n, np.int32).reshape(r.h, r.w) if r.labels else None
     nc = r.n_clusters
     out["n_clusters"] = nc
     for k, dt in (("cl_first", np.int32), ("cl_size", np.int32), ("cl_sumx", np.int64), ("cl_sumy", np.int64),
@@ -237,3 +246,35 @@ def radius_outlier_removal(points: np.ndarray, radius: float = 0.2, min_neighbor
         cnt = (d2.astype(np.float64) <= r2).sum(axis=1) - 1   # minus the query itself
         keep[idx[a:a + 512]] = cnt >= min_neighbors
     return keep
+
+
+def _pack_bits(img: np.ndarray) -> np.ndarray:
+    """{0,100} int8 [H, W] -> uint32 [H, pitch]: 32 cells per word, LSB = lowest x, pitch padded to 4 words (the
+    bit-grid layout include/aos_gpu.h documents for AOS_FMT_BITS)."""
+    h, w = img.shape
+    pitch = (((w + 31) >> 5) + 3) & ~3
+    out = np.zeros((h, pitch * 4), np.uint8)
+    for r0 in range(0, h, 2048):   # in slabs: the unpacked pad of a 20000^2 grid would be 400 MB
+        blk = img[r0:r0 + 2048] == 100
+        out[r0:r0 + 2048, :(w + 7) // 8] = np.packbits(blk, axis=1, bitorder="little")
+    return out.view(np.uint32).reshape(h, pitch)
+
+
+def result_artefacts(r: dict, g: dict | None) -> dict:
+    """The oracle's results under the names aos_gpu.lib.digest_of() hashes (seed_stage dict r, gvd_stage dict g)."""
+    art = {"occupancy": _pack_bits(r["occ_border"]), "skeleton": _pack_bits(r["skel"]),
+           "skeleton_framed": _pack_bits(r["skel_framed"]),
+           "clusters.label": r["cl_first"], "clusters.size": r["cl_size"], "clusters.center_x": r["cl_cx"],
+           "clusters.center_y": r["cl_cy"], "clusters.length": r["cl_len"], "clusters.sum_x": r["cl_sumx"],
+           "clusters.sum_y": r["cl_sumy"], "clusters.max_d2": r["cl_maxd2"],
+           "rows.cluster": r["row_cluster"], "seeds": r["seeds"], "rows_info": r["rows_info"]}
+    for i, f in enumerate(("center_x", "center_y", "start_x", "start_y", "end_x", "end_y", "length")):
+        art["rows." + f] = r["rows"][:, i] if len(r["rows"]) else np.zeros(0)
+    have = g is not None and "nodes" in g
+    if have:
+        xyz = np.zeros((len(g["nodes"]), 3))
+        xyz[:, :2] = g["nodes"]
+    for k in ("nodes_xyz", "node_labels", "node_cluster_indices", "node_label_counts", "node_label_clusters", "node_label_types",
+              "edges", "edge_lengths", "edge_clearances"):
+        art["graph." + k] = None if not have else (xyz if k == "nodes_xyz" else g[k])
+    return art
