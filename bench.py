@@ -142,7 +142,6 @@ def bench_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
@@ -251,6 +250,8 @@ def bench_ours(args):
                 stage_acc[name] = stage_acc.get(name, 0.0) + ms / reps
         c0.set_profiling(False)
 
+    # digest of map 0's result (every published array) -- compared with the CPU oracle on the same cloud below
+    gpu_digest, gpu_parts = c0.result_digest(parts=True)
     dev_ms, total_cells = adist.reduce_stats(dev_ms, cells * args.steps * T, device=dev)   # MAX over ranks, SUM of cells
     e2e_ms, _ = adist.reduce_stats(e2e_ms, cells * args.steps * T, device=dev)
     ms_per_step = dev_ms / args.steps
@@ -260,50 +261,76 @@ def bench_ours(args):
     line = None
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        # dominant HBM kernel by algorithmic bytes: the point-binning pass reads 16 B per point once
-        bin_ms = stage_acc.get("bin", float("nan"))
-        bin_bytes = 16.0 * n_pts
-        achieved = bin_bytes / (bin_ms * 1e-3) / 1e9 if bin_ms == bin_ms and bin_ms > 0 else None
         b_alg = 16.0 * n_pts + 9.125 * cells  # compulsory bytes of one map
-        gpu_ms = sum(v for k, v in stage_acc.items() if k not in ("gvd_host_voronoi",))
+        host_stages = ("gvd_host_voronoi",)
+        gpu_ms = sum(v for k, v in stage_acc.items() if k not in host_stages)
+        plane = cells / 8.0
+        # algorithmic bytes per stage (each plane read / written once at 1 bit per cell)
+        stage_bytes = {"bin": 16.0 * n_pts, "inflate": 3 * plane, "open": 2 * plane, "thin": 2 * plane, "frame": 2 * plane,
+                       "cc_mask_scan": plane}
+        kernels = []
+        for k, ms in sorted(stage_acc.items(), key=lambda kv: -kv[1]):
+            if k in host_stages or ms <= 0:
+                continue
+            e = {"stage": k, "ms": round(ms, 4), "share_of_device_time": round(ms / gpu_ms, 4) if gpu_ms > 0 else None}
+            if k in stage_bytes:
+                gbs = stage_bytes[k] / (ms * 1e-3) / 1e9
+                e.update(algorithmic_bytes=int(stage_bytes[k]), gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+            kernels.append(e)
+        whole_gbs = b_alg / (gpu_ms * 1e-3) / 1e9 if gpu_ms > 0 else None
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec0.grid_resolution} m, "
-                                   f"{n_pts} points per map",
-                       "maps_in_flight": T, "device_gate": gate, "step": f"{T} independent maps per GPU, one per stream/host thread "
-                                                    "(the Subdiv2D replay of each map runs on its own host core)",
-                       "host_cores": ncpu, "e2e_source": "pinned host memory" if pinned else "pageable host memory (pinning failed)",
-                       "l2": "inputs (16 B x points per map) larger than L2; every map is re-read from HBM",
-                       "pipeline": info.get("pipeline"), "graph": info.get("graph")},
+            "config": workload_config(args, gi, spec0, n_pts, T=T, gate=gate, ncpu=ncpu, pinned=pinned,
+                                      pipeline=info.get("pipeline"), graph=info.get("graph")),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 3),
                     "h2d_bytes_per_step": int(n_pts * 16) * T, "d2h_bytes_per_step": int(info_h.get("d2h_bytes", 0)) * T},
             "single_map": {"ms_per_map": round(single_ms, 3), "value": round(cells / (single_ms * 1e-3) / 1e6, 1), "unit": UNIT,
                            "device_stages_ms": round(gpu_ms, 3), "host_voronoi_ms": round(stage_acc.get("gvd_host_voronoi", 0.0), 3)},
             "gpu_launches": int(round(launches)),
-            "roofline": {"bound": "hbm", "kernel": "bin_points_xyz16", "achieved": round(achieved, 1) if achieved else None,
-                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": 3280462840 if args.workload == "C3" and args.points is None else None,
-                         "traffic_source": "ncu --set full, profiles/r01_n_pipeline_c3.txt (dram__bytes_read.sum 3.241483 GB + dram__bytes_write.sum 38.98 MB per launch)",
+            # the map-level figure: SURVEY 8(d)'s algorithmic bytes of ONE map / the device time of ONE map (all stages,
+            # CUDA events on the library's stream, one map in flight); per-stage figures beside it
+            "roofline": {"bound": "hbm", "kernel": "whole map: all device stages of aos_map_to_graph",
+                         "achieved": round(whole_gbs, 1) if whole_gbs else None, "peak": peak, "unit": "GB/s",
+                         "frac": round(whole_gbs / peak, 4) if whole_gbs else None,
+                         "algorithmic_bytes": int(b_alg), "device_ms_per_map": round(gpu_ms, 4),
+                         "traffic": None, "traffic_note": "per-kernel dram__bytes from ncu --set full are under profiles/ (r02_*)",
                          "peak_source": peak_src,
-                         "whole_map": {"algorithmic_bytes": int(b_alg),
-                                       "device_stages_gbs": round(b_alg / (gpu_ms * 1e-3) / 1e9, 1) if gpu_ms > 0 else None,
-                                       "device_stages_frac": round(b_alg / (gpu_ms * 1e-3) / 1e9 / peak, 4) if gpu_ms > 0 else None}},
+                         "time_dominant_stage": kernels[0] if kernels else None,
+                         "largest_traffic_kernel": next((k for k in kernels if k["stage"] == "bin"), None),
+                         "stages": kernels},
             "stages_ms": {k: round(v, 4) for k, v in stage_acc.items()},
             "clocks": clk.summary(),
             "gen_s": round(gen_s, 2),
         }
         if not args.no_cpu_baseline and world == 1:   # reported beside the N = 1 line only
-            line["cpu_baseline"] = cpu_baseline(args, cores=1, budget_s=args.cpu_budget)
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            cb, parity = cpu_baseline_full(args, host_np, spec0, gpu_digest, gpu_parts)
+            line["cpu_baseline"] = cb
+            line["parity"] = parity
     pool.shutdown()
     for c in ctxs:
         c.close()
+    del maps
+    torch.cuda.empty_cache()
     return line
+
+
+def workload_config(args, gi, spec, n_pts, **kw):
+    """The `config` object; the reference arm prints the same workload string (same grid, same points per map)."""
+    cfg = {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec.grid_resolution} m, {spec.n_points} points per map "
+                       "(nominal; seeded synthetic orchard, SURVEY.md 8(d))",
+           "points_per_map_generated": int(n_pts)}
+    if "T" in kw:
+        T = kw["T"]
+        cfg.update({"maps_in_flight": T, "device_gate": kw["gate"],
+                    "step": f"{T} independent maps per GPU, one per stream/host thread (the Subdiv2D replay of each map runs on "
+                            "its own host core)",
+                    "host_cores": kw["ncpu"],
+                    "e2e_source": "pinned host memory" if kw["pinned"] else "pageable host memory (pinning failed)",
+                    "l2": "inputs (16 B x points per map) larger than L2; every map is re-read from HBM",
+                    "pipeline": kw["pipeline"], "graph": kw["graph"]})
+    return cfg
 
 
 def bench_sweep(args):
@@ -322,7 +349,6 @@ def bench_sweep(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
     n_maps = 256
     mine = adist.map_assignment(n_maps, world, rank)
     ncpu = os.cpu_count() or 1
@@ -403,18 +429,18 @@ def bench_sweep(args):
                         "ms_per_step": round(e2e_ms / args.steps, 3), "h2d_bytes_per_step": int(n_pts * 16),
                         "d2h_bytes_per_step": None},
                 "gpu_launches": int(round(launches)), "clocks": clk.summary()}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     pool.shutdown()
     for c in ctxs:
         c.close()
+    return line if rank == 0 else None
 
 
-def bench_bands(args):
-    """BASELINE config 4: ONE grid row-band sharded over the ranks (strong scaling of the raster stages; clusters,
-    seeds and graph finish on rank 0).  Not the default: `--shard bands`, normally with --workload C4."""
+def run_bands(args, workload, steps, warmup, halo):
+    """BASELINE config 4: ONE grid row-band sharded over the ranks (strong scaling of the raster stages; clusters, seeds and
+    graph finish on rank 0).  Every N works on the SAME global cloud (synth.make_orchard_strips_torch: fixed strips with
+    their own generator seeds; a rank generates the strips that touch its rows), so the result digest must equal the
+    single-GPU digest of that cloud, which rank 0 computes with aos_map_to_graph and compares.  Collective: call on every
+    rank with the process group up.  Returns the record on rank 0."""
     import torch
     import torch.distributed as dist
 
@@ -425,9 +451,7 @@ def bench_bands(args):
     rank, world, local = adist.env_rank_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    spec = synth.config(args.workload, seed=0, n_points=args.points)
+    spec = synth.config(workload, seed=0, n_points=args.points)
     params = make_params(lib, spec)
     gi = lib.grid_geometry(params)
     ctx = lib.Context(local)
@@ -435,7 +459,19 @@ def bench_bands(args):
     res = float(np.float32(spec.grid_resolution))
     ylo = gi.origin_y + band.first_global_row * res - 2 * res
     yhi = gi.origin_y + (band.first_global_row + band.local_rows) * res + 2 * res
-    pts = synth.make_orchard_torch(spec, dev, y_range=(ylo, yhi)) if world > 1 else synth.make_orchard_torch(spec, dev)
+    single = None
+    if rank == 0:   # the single-GPU answer on the whole cloud
+        full = synth.make_orchard_strips_torch(spec, dev)
+        ref = lib.Context(local)
+        ref.map_to_graph(params, full)
+        single = {"digest": ref.result_digest(), "points": int(full.shape[0])}
+        ref.close()
+        if world == 1:
+            pts = full
+        del full
+    if world > 1:
+        torch.cuda.empty_cache()
+        pts = synth.make_orchard_strips_torch(spec, dev, y_range=(ylo, yhi))
     torch.cuda.synchronize()
 
     def sync_all():
@@ -452,7 +488,7 @@ def bench_bands(args):
         t["raster"] = time.perf_counter() - t0
         be = bands.LibBackend(ctx)
         t0 = time.perf_counter()
-        if args.halo == "p2p":
+        if halo == "p2p":
             launches = bands.run_thinning_p2p(be, band, rank, world, dist, device=dev)
         else:
             launches = bands.run_thinning(be, band, rank, world, dist)
@@ -470,9 +506,12 @@ def bench_bands(args):
             seeds, counts, rows_info = ctx.select_seeds()
             g = ctx.gvd_stage(seeds, rows_info) if len(seeds) else None
             t["tail_rank0"] = time.perf_counter() - t0
+            t["tail_rank0_host_voronoi"] = dict(ctx.stage_times()).get("gvd_host_voronoi", 0.0) * 1e-3
         return t, launches, g
 
-    for _ in range(args.warmup):
+    if rank == 0:
+        ctx.set_profiling(True)
+    for _ in range(warmup):
         one()
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -480,10 +519,10 @@ def bench_bands(args):
     with ClockSampler(local) as clk:
         ev0.record()
         w0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             t, launches, g = one()
             for k, v in t.items():
-                acc[k] = acc.get(k, 0.0) + v * 1e3 / args.steps
+                acc[k] = acc.get(k, 0.0) + v * 1e3 / steps
         sync_all()
         ev1.record()
         ev1.synchronize()
@@ -493,126 +532,174 @@ def bench_bands(args):
     if world > 1:
         dist.all_reduce(n_local)
     cells = gi.width * gi.height
+    rec = None
     if rank == 0:
+        digest = ctx.result_digest()
         raster_ms = acc.get("raster", 0) + acc.get("thin+halo", 0) + acc.get("gather", 0)
-        line = {"metric": METRIC, "value": round(cells * args.steps / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: ONE {gi.width}x{gi.height} grid @ {spec.grid_resolution} m row-band "
-                                       f"sharded over {world} GPU(s), {int(n_local.item())} points in total (halo overlap "
-                                       f"included), halo {ctx.band_halo_rows(params)} rows, " +
-                                       ("8 edge rows per neighbour stored into its peer-mapped buffer by the thinning kernel "
-                                        "(NVLink P2P), flags all-reduced" if args.halo == "p2p" else
-                                        "NCCL send/recv of 8 rows per neighbour and thinning launch"),
-                           "shard": "bands", "halo": args.halo, "thin_launches": launches,
-                           "graph": None if g is None else {"nodes": int(g["n_nodes"]), "edges": int(g["n_edges"])}},
-                "stages_ms_rank0": {k: round(v, 3) for k, v in acc.items()},
-                "raster_stages": {"ms": round(raster_ms, 3), "value": round(cells / (raster_ms * 1e-3) / 1e6, 1), "unit": UNIT},
-                "clocks": clk.summary()}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        rec = {"workload": f"{workload}: ONE {gi.width}x{gi.height} grid @ {spec.grid_resolution} m row-band sharded over "
+                           f"{world} GPU(s); one global cloud of {single['points']} points for every N "
+                           f"({int(n_local.item())} generated incl. halo overlap)",
+               "shard": "bands", "halo": halo, "halo_rows": ctx.band_halo_rows(params), "thin_launches": launches,
+               "steps": steps, "warmup": warmup, "scaling": "strong",
+               "ms_per_map": round(ms / steps, 3), "value": round(cells * steps / (ms * 1e-3) / 1e6, 1), "unit": UNIT,
+               "stages_ms_rank0": {k: round(v, 3) for k, v in acc.items()},
+               "raster_stages": {"ms": round(raster_ms, 3), "value": round(cells / (raster_ms * 1e-3) / 1e6, 1), "unit": UNIT},
+               "graph": None if g is None else {"nodes": int(g["n_nodes"]), "edges": int(g["n_edges"])},
+               "digest": digest, "single_gpu_digest": single["digest"], "equals_single_gpu": digest == single["digest"],
+               "clocks": clk.summary()}
     ctx.close()
+    del pts
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_bands(args):
+    """`--shard bands`: the band run as the whole bench line (normally with --workload C4)."""
+    rec = run_bands(args, args.workload, args.steps, args.warmup, args.halo)
+    if rec is None:
+        return None
+    return {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_map"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
+            "config": {"workload": rec["workload"], "shard": "bands", "halo": rec["halo"], "thin_launches": rec["thin_launches"],
+                       "graph": rec["graph"]},
+            "stages_ms_rank0": rec["stages_ms_rank0"], "raster_stages": rec["raster_stages"],
+            "digest": rec["digest"], "single_gpu_digest": rec["single_gpu_digest"], "equals_single_gpu": rec["equals_single_gpu"],
+            "clocks": rec["clocks"]}
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (port of the reference's algorithms) on a bounded crop of the workload
+# CPU arms: the oracle (port of the reference's algorithms, pinned to the compiled reference by tests/test_ref_cpu.py) on
+# the SAME configuration as the GPU arm -- full-size maps.  The reference's literal loops are quadratic in the number of
+# graph nodes / cluster cells (O(E*M) node search, O(M^2) proximity pairs, O(n^2) cluster diameter: 1e11..1e12 steps at
+# config 3), so the full-size runs use the oracle's indexed loops (oracle/aos_oracle_fast.c: hash grids, convex hulls,
+# rows in parallel threads), which tests/test_oracle_fast_cpu.py proves bit-identical to the literal ones.
 # ---------------------------------------------------------------------------------------------------
-def crop_spec(workload: str, seed: int):
-    """A 200 m x 120 m window of the workload's orchard (same row pitch, tree model, point density): the largest
-    crop on which the reference's quadratic loops (O(E*M) node search, O(n^2) cluster diameter) still finish in
-    seconds per map; smaller crops flatter the CPU arm, the full 1 km^2 map would take hours."""
-    from aos_gpu import synth
-    full = synth.config(workload, seed=seed)
-    ex, ey = min(full.extent_x, 200.0), min(full.extent_y, 120.0)
-    density = full.n_points / (full.extent_x * full.extent_y)
-    s = synth.OrchardSpec(extent_x=ex, extent_y=ey, row_pitch=full.row_pitch, tree_spacing=full.tree_spacing,
-                          tree_radius=full.tree_radius, n_points=int(density * ex * ey), seed=seed,
-                          grid_resolution=full.grid_resolution, inflation_radius=full.inflation_radius)
-    return s
+def oracle_map(O, spec, pts):
+    """One map through the oracle; returns (seconds seed stage, seconds gvd stage, seed dict, graph dict)."""
+    p = O.SeedParams(grid_resolution=spec.grid_resolution, inflation_radius=spec.inflation_radius, polygon=spec.polygon,
+                     exclusion=spec.exclusion)
+    t0 = time.perf_counter()
+    r = O.seed_stage(p, pts)
+    t1 = time.perf_counter()
+    g = O.gvd_stage(r["seeds"], r["skel_framed"], r["origin_x"], r["origin_y"], r["res"], r["rows_info"])
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, r, g
 
 
-def _cpu_one(args_tuple):
-    workload, seed, reps = args_tuple
-    from aos_gpu import synth
-    from oracle import oracle as O
-    spec = crop_spec(workload, seed)
-    pts = synth.make_orchard(spec)
-    p = O.SeedParams(grid_resolution=spec.grid_resolution, inflation_radius=spec.inflation_radius, polygon=spec.polygon)
-    times = []
-    cells = 0
-    for _ in range(reps):
-        t = time.perf_counter()
-        r = O.seed_stage(p, pts)
-        O.gvd_stage(r["seeds"], r["skel_framed"], r["origin_x"], r["origin_y"], r["res"], r["rows_info"])
-        times.append(time.perf_counter() - t)
-        cells = r["w"] * r["h"]
-    return cells, times, len(pts)
+def reference_small_configs(budget_s=12.0):
+    """The reference's OWN compiled code (oracle/_ref, literal loops, one thread) timed end to end on BASELINE configs 1
+    and 2 -- the sizes it was written for.  Empty when the prebuilt library did not travel."""
+    out = {}
+    try:
+        from aos_gpu import synth
+        from oracle import oracle as O
+        from oracle import ref as R
+        if not R.available():
+            return {"unavailable": "oracle/_ref/libaos_ref.so not present"}
+        for name in ("C1", "C2"):
+            spec = synth.config(name, seed=0)
+            pts = synth.make_orchard(spec)
+            p = O.SeedParams(grid_resolution=spec.grid_resolution, inflation_radius=spec.inflation_radius, polygon=spec.polygon)
+            t0 = time.perf_counter()
+            n = 0
+            while n == 0 or (time.perf_counter() - t0) < budget_s / 2:
+                a = R.seed_stage(p, pts)
+                R.gvd_stage(a["seeds"], a["skel_framed"], a["origin_x"], a["origin_y"], a["res"], a["rows_info"])
+                n += 1
+            dt = (time.perf_counter() - t0) / n
+            out[name] = {"cells": a["w"] * a["h"], "points": int(len(pts)), "ms_per_map": round(dt * 1e3, 1),
+                         "value": round(a["w"] * a["h"] / dt / 1e6, 2), "unit": UNIT, "cores": 1, "kind": "reference",
+                         "note": "exclusion discs = the node's 11 hard-coded ones"}
+    except Exception as e:   # the CPU arm must never take the bench line down
+        out["error"] = repr(e)[:200]
+    return out
 
 
-def _sample_text(args, cells, npts, what):
-    spec = crop_spec(args.workload, 1000)
-    return (f"{spec.extent_x:g}x{spec.extent_y:g} m crop of {args.workload} ({cells} cells, {npts} points), oracle port "
-            f"(C, -O2) seed stage + gvd stage incl. cv2.Subdiv2D, {what}")
-
-
-def cpu_baseline(args, cores: int, budget_s: float):
-    """The oracle (port of the reference's algorithms) on ONE host core: maps of the bounded crop, back to back,
-    until `budget_s` seconds of CPU work are spent (at least one map)."""
+def cpu_baseline_full(args, host_np, spec, gpu_digest, gpu_parts):
+    """cpu_baseline of the N = 1 line: ONE full map of the bench workload (map 0's own cloud, as the GPU processed it)
+    through the oracle with every host core, timed; its result digest is then compared with the GPU's (the parity check
+    of this very run, outside the timed region)."""
+    from aos_gpu import lib
     from oracle import oracle as O
     O.build()
-    t0 = time.perf_counter()
-    total, n, cells, npts = 0.0, 0, 0, 0
-    while n == 0 or (total + total / n) < budget_s:
-        cells, times, npts = _cpu_one((args.workload, 1000 + n, 1))
-        total += times[0]
-        n += 1
-    value = cells * n / total / 1e6
-    return {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": _sample_text(args, cells, npts, f"{n} map(s) on one core"),
-            "ms_per_map": round(1e3 * total / n, 2), "wall_s": round(time.perf_counter() - t0, 1)}
+    cores = os.cpu_count() or 1
+    t_start = time.perf_counter()
+    O.set_fast(True, threads=cores, skip_labels=True)
+    try:
+        ts, tg, r, g = oracle_map(O, spec, host_np)
+    finally:
+        O.set_fast(False)
+    cells = r["w"] * r["h"]
+    total, per = lib.digest_of(O.result_artefacts(r, g), parts=True)
+    bad = sorted(k for k in per if per[k] != gpu_parts.get(k))
+    cb = {"value": round(cells / (ts + tg) / 1e6, 2), "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"1 full {args.workload} map ({cells} cells, {len(host_np)} points: map 0 of this run), oracle port with its "
+                    f"indexed loops on {cores} threads (seed stage {ts:.1f} s, gvd stage incl. cv2.Subdiv2D {tg:.1f} s); the "
+                    "reference's literal loops do not finish this size (O(E*M), O(M^2), O(n^2) per cluster)",
+          "ms_per_map": round(1e3 * (ts + tg), 1), "wall_s": None,
+          "reference_small_configs": reference_small_configs()}
+    cb["wall_s"] = round(time.perf_counter() - t_start, 1)
+    parity = {"checked": True, "against": "oracle (CPU) on the same cloud, sha256 per published array",
+              "equal": total == gpu_digest, "arrays": len(per), "differing": bad, "digest": gpu_digest}
+    return cb, parity
 
 
 def bench_reference(args):
-    """CPU arm: every host core runs one crop map per step (independent maps, like the GPU arm's maps in flight)."""
-    import multiprocessing as mp
+    """CPU arm on the GPU arm's configuration: every step is ONE full map of the workload through the oracle with all host
+    cores (kind "port": the reference's own loops are quadratic and do not finish this size; the port's results are
+    bit-identical to them wherever both run).  A fresh seeded cloud per step, generated outside the timed part."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from aos_gpu import synth
     from oracle import oracle as O
     O.build()
-    cores = max(1, min(os.cpu_count() or 1, 64))
-    vals, cells, npts, t_start = [], 0, 0, time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
+    cores = os.cpu_count() or 1
+    spec0 = synth.config(args.workload, seed=0, n_points=args.points)
+    t_start = time.perf_counter()
+    O.set_fast(True, threads=cores, skip_labels=True)
+    times, cells, npts = [], 0, 0
+    budget_s = args.reference_budget
+    done = 0
+    try:
         for i in range(args.warmup + args.steps):
-            t1 = time.perf_counter()
-            res = pool.map(_cpu_one, [(args.workload, 1000 + i * cores + k, 1) for k in range(cores)])
-            wall = time.perf_counter() - t1
-            cells, npts = res[0][0], res[0][2]
+            spec = synth.config(args.workload, seed=i % 4, n_points=args.points)
+            pts = synth.make_orchard_strips(spec)
+            ts, tg, r, g = oracle_map(O, spec, pts)
+            cells, npts = r["w"] * r["h"], len(pts)
+            del r, g
             if i >= args.warmup:
-                vals.append(cells * cores / wall / 1e6)
-            if time.perf_counter() - t_start > 240 and vals:   # keep the whole arm within minutes
+                times.append(ts + tg)
+            done = i + 1
+            # the whole arm has to end within minutes: stop early once the budget is spent (steps reports what ran)
+            if time.perf_counter() - t_start > budget_s and times:
                 break
-    value = float(np.mean(vals))
+    finally:
+        O.set_fast(False)
+    per_map = float(np.mean(times))
+    value = cells / per_map / 1e6
+    from types import SimpleNamespace
+    gi = SimpleNamespace(width=int(round(spec0.extent_x / spec0.grid_resolution)), height=int(round(spec0.extent_y / spec0.grid_resolution)))
+    try:
+        from aos_gpu import lib
+        g2 = lib.grid_geometry(make_params(lib, spec0))
+        gi = SimpleNamespace(width=g2.width, height=g2.height)
+    except Exception:
+        pass
+    n_nominal = npts
     cb = {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
-          "sample": _sample_text(args, cells, npts, f"one map per core and step, {cores} cores"),
-          "ms_per_map": round(1e3 * cells * cores / (value * 1e6), 2), "wall_s": round(time.perf_counter() - t_start, 1)}
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-            "steps": len(vals), "warmup": args.warmup, "ms_per_step": round(1e3 * cells * cores / (value * 1e6), 2),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8 grids / f32,f64 geometry",
-            "data": "synthetic", "config": {"workload": f"{args.workload} (bounded crop, see cpu_baseline.sample)",
-                                            "maps_in_flight": cores},
+          "sample": f"{len(times)} full {args.workload} map(s) ({cells} cells, {npts} points each), one per step, oracle port with "
+                    f"its indexed loops on {cores} threads; {done - len(times)} warm-up map(s)",
+          "ms_per_map": round(1e3 * per_map, 1), "wall_s": round(time.perf_counter() - t_start, 1)}
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(times), "warmup": min(args.warmup, done - len(times)),
+            "ms_per_step": round(1e3 * per_map, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i8 grids / f32,f64 geometry", "data": "synthetic",
+            "config": workload_config(args, gi, spec0, n_nominal),
             "cpu_baseline": cb,
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def crop_cells(args):
-    from aos_gpu import lib
-    spec = crop_spec(args.workload, 1000)
-    gi = lib.grid_geometry(make_params(lib, spec))
-    return gi.width * gi.height
 
 
 def main():
@@ -626,10 +713,15 @@ def main():
     ap.add_argument("--maps-in-flight", type=int, default=0,
                     help="independent maps processed concurrently per GPU (0 = min(16, host cores / ranks))")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
-                    help="--shard bands: p2p = halo rows stored into peer memory by the thinning kernel; nccl = send/recv")
+                    help="band runs: p2p = halo rows stored into peer memory by the thinning kernel; nccl = send/recv")
     ap.add_argument("--shard", default="maps", choices=["maps", "bands"],
-                    help="maps: independent maps per GPU (default, weak scaling); bands: one grid row-band sharded")
-    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+                    help="maps: independent maps per GPU (default, weak scaling) followed by the config-4 band run as the "
+                         "`bands` sub-record; bands: only the band run, as the bench line")
+    ap.add_argument("--no-bands", action="store_true", help="skip the config-4 band sub-record of the default run")
+    ap.add_argument("--bands-workload", default="C4")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="(kept for compatibility; the CPU leg runs one full map)")
+    ap.add_argument("--reference-budget", type=float, default=420.0,
+                    help="--impl reference: seconds after which no further step is started")
     ap.add_argument("--device-gate", type=int, default=-1,
                     help="maps admitted to the seed stage's kernel phase at a time per GPU (aos_set_device_gate); 0 = no limit; "
                          "default 2 when at least 4 maps are in flight")
@@ -637,12 +729,33 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
-    elif args.shard == "bands":
-        bench_bands(args)
+        return
+    import torch
+    from aos_gpu import dist as adist
+    rank, world, local = adist.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libaos_gpu has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.shard == "bands":
+        line = bench_bands(args)
     elif args.workload.upper() == "C5":
-        bench_sweep(args)
+        line = bench_sweep(args)
     else:
-        bench_ours(args)
+        line = bench_ours(args)
+        if not args.no_bands and args.workload.upper() == "C3" and args.points is None:
+            # BASELINE config 4 (the row-band sharded grid) measured in the same driver-visible run: one 40000^2 grid over
+            # the N ranks, digest-checked against the single-GPU result of the same cloud
+            rec = run_bands(args, args.bands_workload, max(1, min(args.steps, 5)), 2, args.halo)
+            if line is not None:
+                line["bands"] = rec
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
