@@ -302,7 +302,7 @@ def bench_ours(args):
                          "stages": kernels},
             "stages_ms": {k: round(v, 4) for k, v in stage_acc.items()},
             "clocks": clk.summary(),
-            "gen_s": round(gen_s, 2),
+            "gen_s": round(gen_s, 2), "points_per_map": int(n_pts),
         }
         if not args.no_cpu_baseline and world == 1:   # reported beside the N = 1 line only
             cb, parity = cpu_baseline_full(args, host_np, spec0, gpu_digest, gpu_parts)
@@ -319,8 +319,7 @@ def bench_ours(args):
 def workload_config(args, gi, spec, n_pts, **kw):
     """The `config` object; the reference arm prints the same workload string (same grid, same points per map)."""
     cfg = {"workload": f"{args.workload}: {gi.width}x{gi.height} cells @ {spec.grid_resolution} m, {spec.n_points} points per map "
-                       "(nominal; seeded synthetic orchard, SURVEY.md 8(d))",
-           "points_per_map_generated": int(n_pts)}
+                       "(nominal; seeded synthetic orchard, SURVEY.md 8(d))"}
     if "T" in kw:
         T = kw["T"]
         cfg.update({"maps_in_flight": T, "device_gate": kw["gate"],
@@ -697,7 +696,7 @@ def bench_reference(args):
             "ms_per_step": round(1e3 * per_map, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i8 grids / f32,f64 geometry", "data": "synthetic",
             "config": workload_config(args, gi, spec0, n_nominal),
-            "cpu_baseline": cb,
+            "cpu_baseline": cb, "points_per_map": int(npts),
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
