@@ -712,15 +712,24 @@ struct ReplayJob {
 };
 
 // Cells travel through the ring as bounding-box-relative packed coordinates  rx | ry << 20.
+// SMEM = true (the default path): the CTA builds, from the cluster's OWN cell list, a BANDED bitmap in shared memory that
+// keeps for every 32-cell word column only the rows between that column's lowest and highest cell (colmin = first row,
+// coloff = word offset, heights by difference): at most one word per cell for a thin connected curve whatever its
+// direction, where the full bounding-box bitmap of a 1 km row is 12 k words for a few thousand cells and limits an SM to
+// one replay at a time.  With the band, every flagged cluster of a map is resident at once and the stage costs what its
+// longest cluster costs.  A cluster whose band does not fit the launch's budget raises its fallback flag and is replayed
+// by the SMEM = false instantiation on the global bitmap (launched over all jobs; the others exit at once).
 template <bool SMEM>
 __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ SeedDeviceParams P,
                                                         const ReplayJob *__restrict__ jobs,
                                                         const ClusterAcc *__restrict__ acc,
                                                         const uint32_t *__restrict__ offsets,
-                                                        const int *__restrict__ root_cellpos,
-                                                        const uint32_t *__restrict__ mask, uint32_t *gvisited,
+                                                        const int *__restrict__ grouped,
+                                                        const int *__restrict__ root_cellpos, int budget_words,
+                                                        uint32_t *gvisited, int *__restrict__ fallback,
                                                         int *__restrict__ queue, float *__restrict__ centre_out) {
-  extern __shared__ uint32_t sm[];  // ring[kRingN] | bitmap ww*hh words (SMEM only)
+  extern __shared__ uint32_t sm[];  // ring[kRingN] | colmin[ww] | coloff[ww + 1] | band words   (the last three: SMEM)
+  if (!SMEM && !fallback[blockIdx.x]) return;  // the banded instantiation already replayed this cluster
   const int lane = threadIdx.x;
   const ReplayJob job = jobs[blockIdx.x];
   const int c = job.cluster;
@@ -728,18 +737,60 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
   int *q = queue + offsets[c];
   const int w = P.w, pitch = P.pitch;
   uint32_t *ring = sm;
-  uint32_t *bm = sm + kRingN;
   const int ww = job.ww, hh = job.hh, bx0 = job.wx0 << 5, by0 = job.y0;
   const unsigned wlim = min(ww << 5, w - bx0);  // cells of the box that exist in the image
+  int *colmin = reinterpret_cast<int *>(sm + kRingN);
+  int *coloff = colmin + ww;  // first used as the per-column maximum
+  uint32_t *band = reinterpret_cast<uint32_t *>(coloff + ww + 1);
   if (SMEM) {
-    const uint32_t *src = mask + (size_t)by0 * pitch + job.wx0;
-    for (int ry = 0; ry < hh; ++ry)
-      for (int rx = lane; rx < ww; rx += 32) bm[ry * ww + rx] = src[(size_t)ry * pitch + rx];
+    const int *cells = grouped + offsets[c];
+    for (int i = lane; i < ww; i += 32) {
+      colmin[i] = 0x7fffffff;
+      coloff[i] = -1;
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      int pos = cells[k];
+      int y = pos / w, x = pos - y * w;
+      int col = (x - bx0) >> 5;
+      atomicMin(&colmin[col], y - by0);
+      atomicMax(&coloff[col], y - by0);
+    }
+    __syncwarp();
+    int running = 0;
+    for (int base = 0; base < ww; base += 32) {
+      int i = base + lane;
+      int h = 0;
+      if (i < ww && coloff[i] >= 0) h = coloff[i] - colmin[i] + 1;
+      int inc = (int)warp_incl_scan((uint32_t)h, lane);
+      if (i < ww) coloff[i] = running + inc - h;
+      running += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) coloff[ww] = running;
+    __syncwarp();
+    if (running > budget_words - kRingN - 2 * ww - 1) {  // does not fit this launch's shared memory
+      if (lane == 0) fallback[blockIdx.x] = 1;
+      return;
+    }
+    for (int i = lane; i < running; i += 32) band[i] = 0u;
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      int pos = cells[k];
+      int y = pos / w, x = pos - y * w;
+      int col = (x - bx0) >> 5;
+      atomicOr(&band[coloff[col] + (y - by0) - colmin[col]], 1u << (x & 31));
+    }
     __syncwarp();
   }
-  // the not-yet-visited bitmap: shared copy of the box, or the global scratch copy of the whole mask
+  // the not-yet-visited bitmap word of box cell (rx, ry): the band (null where the column has no such row), or the
+  // global scratch copy of the whole mask
   auto word_ptr = [&](int rx, int ry) -> uint32_t * {
-    return SMEM ? bm + ry * ww + (rx >> 5) : gvisited + (size_t)(ry + by0) * pitch + job.wx0 + (rx >> 5);
+    if (SMEM) {
+      const int col = rx >> 5;
+      const int o = coloff[col], r = ry - colmin[col];
+      return (unsigned)r < (unsigned)(coloff[col + 1] - o) ? band + o + r : nullptr;
+    }
+    return gvisited + (size_t)(ry + by0) * pitch + job.wx0 + (rx >> 5);
   };
   // neighbour k of the reference's tables dx = {-1,-1,-1,0,0,1,1,1}, dy = {-1,0,1,-1,1,-1,0,1}
   const int sub = lane >> 3, k8 = lane & 7;
@@ -754,7 +805,8 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
     if (lane == 0) {
       q[0] = start;
       ring[0] = (uint32_t)(x - bx0) | ((uint32_t)(y - by0) << 20);
-      atomicAnd(word_ptr(x - bx0, y - by0), ~(1u << (x & 31)));
+      uint32_t *wp = word_ptr(x - bx0, y - by0);
+      if (wp) atomicAnd(wp, ~(1u << (x & 31)));
     }
     __syncwarp();
   }
@@ -773,8 +825,10 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
     }
     const int rx = (int)(cur & 0xfffffu) + mydx, ry = (int)(cur >> 20) + mydy;
     bool take = false;
+    uint32_t *wp = nullptr;
     if (sub < avail && (unsigned)rx < wlim && (unsigned)ry < (unsigned)hh) {
-      uint32_t word = SMEM ? *word_ptr(rx, ry) : __ldcg(word_ptr(rx, ry));
+      wp = word_ptr(rx, ry);
+      uint32_t word = SMEM ? (wp ? *wp : 0u) : __ldcg(wp);
       take = (word >> (rx & 31)) & 1u;
     }
     // cells popped earlier in this step claim shared neighbours first (what sequential expansion does)
@@ -789,7 +843,7 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
       int slot = tail + __popc(m & lt);
       ring[slot & (kRingN - 1)] = (uint32_t)rx | ((uint32_t)ry << 20);
       q[slot] = (ry + by0) * w + rx + bx0;
-      atomicAnd(word_ptr(rx, ry), ~(1u << (rx & 31)));
+      atomicAnd(wp, ~(1u << (rx & 31)));
     }
     head += avail;
     tail += __popc(m);
@@ -949,8 +1003,10 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     const ClusterAcc *h_acc = reinterpret_cast<const ClusterAcc *>(c->pin_c.data());
     AOS_CUDA_OK(c, cudaMemcpyAsync(c->pin_c.data(), acc, sizeof(ClusterAcc) * (size_t)nc, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-    // shared-memory classes: bitmap words <= 2K (8 KB), <= 12K (48 KB), <= 50K (200 KB), else global bitmap
-    const size_t class_words[3] = {2048, 12288, 51200};
+    // shared-memory classes of the banded replay: ring + column tables + band bitmap (at most one word per cell for a
+    // thin connected curve) <= 4 K words (16 KB), <= 12 K (48 KB), <= 54 K (216 KB); larger ones go straight to the
+    // global-bitmap kernel, as does any cluster whose band turns out not to fit its class
+    const size_t class_words[3] = {4096, 12288, 55296};
     std::vector<ReplayJob> jobs[4];
     for (int i : need) {
       const ClusterAcc &a = h_acc[i];
@@ -963,7 +1019,8 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
       j.ww = (x1 >> 5) - j.wx0 + 1;
       j.y0 = y0;
       j.hh = y1 - y0 + 1;
-      size_t words = (size_t)j.ww * j.hh;
+      size_t band = std::min((size_t)j.ww * j.hh, (size_t)a.size);
+      size_t words = (size_t)kRingN + 2 * (size_t)j.ww + 1 + band;
       int cls = words <= class_words[0] ? 0 : words <= class_words[1] ? 1 : words <= class_words[2] ? 2 : 3;
       if (j.ww >= 32768 || j.hh >= 4096) {
         set_error(c, "cluster bounding box exceeds the replay packing limits");
@@ -983,28 +1040,31 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
       fprintf(stderr, "[aos] replay classes: %zu/%zu/%zu/%zu jobs, max cells %zu/%zu/%zu/%zu\n", jobs[0].size(), jobs[1].size(),
               jobs[2].size(), jobs[3].size(), mx[0], mx[1], mx[2], mx[3]);
     }
-    AOS_CUDA_OK(c, c->cl_stats.reserve(sizeof(ReplayJob) * total_jobs + sizeof(int) * total_jobs));
+    AOS_CUDA_OK(c, c->cl_stats.reserve((sizeof(ReplayJob) + 2 * sizeof(int)) * total_jobs));
     ReplayJob *d_jobs = c->cl_stats.as<ReplayJob>();
     int *d_flagged = reinterpret_cast<int *>(d_jobs + total_jobs);
-    // jobs | cluster ids, staged in page-locked memory (pin_a is free again: h_clusters holds its copy)
-    if (!c->pin_a.resize((sizeof(ReplayJob) + sizeof(int)) * total_jobs)) {
+    int *d_fallback = d_flagged + total_jobs;
+    // jobs | cluster ids | fallback flags, staged in page-locked memory (pin_a is free again: h_clusters holds its copy)
+    if (!c->pin_a.resize((sizeof(ReplayJob) + 2 * sizeof(int)) * total_jobs)) {
       set_error(c, "cudaHostAlloc failed (replay jobs)");
       return AOS_ERR_CUDA;
     }
     ReplayJob *all = reinterpret_cast<ReplayJob *>(c->pin_a.data());
     int *order = reinterpret_cast<int *>(all + total_jobs);
+    int *fb = order + total_jobs;
     {
       size_t q = 0;
       for (int k = 0; k < 4; ++k)
         for (const ReplayJob &j : jobs[k]) {
           all[q] = j;
+          fb[q] = k == 3;
           order[q++] = j.cluster;
         }
     }
-    s = h2d_small(c, d_jobs, all, (sizeof(ReplayJob) + sizeof(int)) * total_jobs, true);  // jobs | ids, contiguous on both sides
+    s = h2d_small(c, d_jobs, all, (sizeof(ReplayJob) + 2 * sizeof(int)) * total_jobs, true);  // contiguous on both sides
     if (s != AOS_OK) return s;
     uint32_t *gvisited = prefix;  // compact indices are no longer needed: reuse as the global "unvisited" bitmap
-    if (!jobs[3].empty()) AOS_CUDA_OK(c, cudaMemcpyAsync(gvisited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(gvisited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
     c->mark("replay_prep");
     // the size classes are independent launches: class 0 stays on the context stream, the others fork onto side
     // streams so that a few very long rows do not serialise behind the many short ones
@@ -1012,25 +1072,18 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     size_t done = 0;
     int side = 0;
     bool forked[3] = {false, false, false};
-    for (int k = 0; k < 4; ++k) {
+    AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(class_words[2] * 4)));
+    for (int k = 0; k < 3; ++k) {
       if (jobs[k].empty()) continue;
-      size_t smem = kRingN * 4 + (k < 3 ? class_words[k] * 4 : 0);
       cudaStream_t ls = st;
       if (k > 0 && side < 3) {
         ls = c->aux[side];
         AOS_CUDA_OK(c, cudaStreamWaitEvent(ls, c->ev_fork, 0));
         forked[side++] = true;
       }
-      if (k < 3) {
-        // per-function attribute shared by every context: always ask for the largest class
-        AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(kRingN * 4 + class_words[2] * 4)));
-        bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, smem, ls>>>(P, d_jobs + done, acc, offsets, root_cellpos,
-                                                                            mask, gvisited, queue, centre);
-      } else {
-        bfs_replay_kernel<false><<<(unsigned)jobs[k].size(), 32, smem, ls>>>(P, d_jobs + done, acc, offsets, root_cellpos,
-                                                                             mask, gvisited, queue, centre);
-      }
+      bfs_replay_kernel<true><<<(unsigned)jobs[k].size(), 32, class_words[k] * 4, ls>>>(
+          P, d_jobs + done, acc, offsets, grouped, root_cellpos, (int)class_words[k], nullptr, d_fallback + done, queue, centre);
       ++c->launches;
       done += jobs[k].size();
     }
@@ -1040,6 +1093,11 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
         AOS_CUDA_OK(c, cudaEventRecord(c->ev_join[k], c->aux[k]));
         AOS_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join[k], 0));
       }
+    // whatever did not fit (and class 3): the warp-per-cluster kernel on the global bitmap; everyone else exits at once
+    bfs_replay_kernel<false><<<(unsigned)total_jobs, 32, kRingN * 4, st>>>(P, d_jobs, acc, offsets, grouped, root_cellpos, 0,
+                                                                           gvisited, d_fallback, queue, centre);
+    ++c->launches;
+    AOS_CUDA_OK(c, cudaGetLastError());
     c->mark("replay_bfs");
     cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length,
                                                                          d_flagged, queue, centre, d_clusters, d_rows);
