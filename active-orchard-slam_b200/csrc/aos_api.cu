@@ -22,7 +22,7 @@ namespace {
 // threads) are serialised through one process-wide gate: concurrent copies would only share the PCIe link and
 // finish together, which keeps the threads in lockstep (all uploading, then all computing); one copy at a time runs
 // at the full link rate and staggers the threads, so the upload of one map overlaps the host/GPU stages of the others.
-std::mutex g_upload_gate;
+std::mutex g_upload_gates[64];  // one per device: uploads to different GPUs use different links
 
 // Kernel-phase gate (aos_set_device_gate): a counting semaphore per device.  Identical maps in flight on one GPU (one
 // context + host thread each) run in lockstep: all of them in their kernel phase at once -- the GPU time-slices 16
@@ -69,7 +69,7 @@ aos_status upload_points(aos_ctx *c, const void *points, size_t bytes, const voi
   if (bytes >= ((size_t)64 << 20)) {
     static const bool dbg = getenv("AOS_DEBUG") != nullptr;
     const auto t_wait = std::chrono::steady_clock::now();
-    std::lock_guard<std::mutex> lock(g_upload_gate);
+    std::lock_guard<std::mutex> lock(g_upload_gates[c->device & 63]);
     const auto t0 = std::chrono::steady_clock::now();
     // One copy: cutting it into pieces (even with only two queued at a time) neither frees the copy engine for other
     // streams' transfers -- it stays with this stream until it runs dry -- nor is it free (59.9 vs 57.7 ms per 3.2 GB).
@@ -236,6 +236,8 @@ aos_status aos_set_device_gate(int32_t max_concurrent) {
   for (auto &g : g_device_gates) g.cv.notify_all();
   return AOS_OK;
 }
+
+int32_t aos_get_device_gate(void) { return g_device_gate_cap.load(); }
 
 aos_status aos_set_profiling(aos_ctx *c, int enabled) {
   if (!c) return AOS_ERR_INVALID;
@@ -491,6 +493,13 @@ aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band 
   const size_t gbytes = (size_t)P.pitch * P.h * 4;
   DevBuf *grids[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_scratch};
   for (DevBuf *g : grids) AOS_CUDA_OK(c, g->reserve(gbytes));
+  // the two thinning planes may be mapped by the neighbouring ranks (CUDA IPC): growing them would free memory a peer
+  // still has open, so a larger map needs aos_band_ipc_release on every rank (and a barrier) first
+  if (c->band_exported && (gbytes > c->band_thin[0].cap || gbytes > c->band_thin[1].cap)) {
+    set_error(c, "band planes are exported over CUDA IPC and too small for this map: call aos_band_ipc_release on every rank "
+                 "(then a barrier) before a larger map");
+    return AOS_ERR_STATE;
+  }
   AOS_CUDA_OK(c, c->band_thin[0].reserve(gbytes));
   AOS_CUDA_OK(c, c->band_thin[1].reserve(gbytes));
   AOS_CUDA_OK(c, c->misc.reserve(4096));
@@ -556,6 +565,20 @@ aos_status aos_band_ipc_export(aos_ctx *c, int32_t buffer, unsigned char *handle
   cudaIpcMemHandle_t h;
   AOS_CUDA_OK(c, cudaIpcGetMemHandle(&h, c->band_thin[buffer].p));
   memcpy(handle, &h, sizeof(h));
+  c->band_exported = true;
+  return AOS_OK;
+}
+
+aos_status aos_band_ipc_release(aos_ctx *c) {
+  if (!c) return AOS_ERR_INVALID;
+  AOS_CUDA_OK(c, cudaSetDevice(c->device));
+  for (int s = 0; s < 2; ++s)
+    for (int b = 0; b < 2; ++b)
+      if (c->band_peer[s][b]) {
+        cudaIpcCloseMemHandle(c->band_peer[s][b]);
+        c->band_peer[s][b] = nullptr;
+      }
+  c->band_exported = false;  // the caller's barrier guarantees that the peers have closed their mappings too
   return AOS_OK;
 }
 

@@ -331,6 +331,7 @@ struct Ctx {
   int band_cur = 0;                       // which of band_thin[] holds the current thinning image
   bool band_p2p = false;                  // a p2p launch has run since aos_band_raster
   void *band_peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [lo/hi neighbour][buffer 0/1], IPC-mapped
+  bool band_exported = false;  // handles of band_thin[] were given out: the planes must not be re-allocated
   int band_peer_first_row[2] = {0, 0};    // neighbour's global row of its local row 0
   bool partial_grids = false, have_occ = false;  // after aos_seed_stage_tail only some grids exist
 

@@ -417,7 +417,9 @@ aos_status aos_map_to_graph_batch(aos_batch_item *items, int32_t n_items, int32_
       if (items[j].ctx == items[i].ctx && max_threads != 1) return AOS_ERR_INVALID;  // a context is not thread-safe
   }
   int nt = max_threads > 0 ? std::min(max_threads, n_items) : n_items;
-  if (nt >= 4) aos_set_device_gate(2);  // stagger the kernel phases of the maps in flight (see aos_set_device_gate)
+  // stagger the kernel phases of the maps in flight (see aos_set_device_gate) for the duration of this call only
+  const int32_t gate_before = aos_get_device_gate();
+  if (nt >= 4 && gate_before == 0) aos_set_device_gate(2);
   std::atomic<int> next{0};
   auto work = [&]() {
     for (int i = next.fetch_add(1); i < n_items; i = next.fetch_add(1)) {
@@ -434,6 +436,7 @@ aos_status aos_map_to_graph_batch(aos_batch_item *items, int32_t n_items, int32_
     for (int t = 0; t < nt; ++t) pool.emplace_back(work);
     for (auto &t : pool) t.join();
   }
+  aos_set_device_gate(gate_before);
   for (int i = 0; i < n_items; ++i)
     if (items[i].status != AOS_OK && items[i].status != AOS_ERR_STATE) return items[i].status;
   return AOS_OK;

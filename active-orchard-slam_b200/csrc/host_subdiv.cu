@@ -50,7 +50,7 @@ inline double tri_area(float ax, float ay, float bx, float by, float cx, float c
 // tri_area and a dead zone of FLT_EPSILON / 8; evaluated inline in flip_around (its only caller).
 }  // namespace
 
-float g_outer_factor = 6.f;  // see aos_set_subdiv_outer_factor
+float g_outer_factor = 3.f;  // OpenCV <= 4.5.x (the reference's platform); see aos_set_subdiv_outer_factor
 bool g_literal_splices = false;  // see aos_set_subdiv_literal_splices (tests: take swapEdges' literal splice sequence)
 
 void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
@@ -58,7 +58,7 @@ void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   next_.clear();
   pt_.clear();
   valid_geometry_ = false;
-  // initDelaunay: the three outer vertices sit big_coord away (3 x max side up to OpenCV 4.5.x, 6 x in 4.13)
+  // initDelaunay: the three outer vertices sit big_coord away (3 x max side up to OpenCV 4.5.x -- the default --, 6 x in 4.13)
   const float big = g_outer_factor * (float)(rw > rh ? rw : rh);
   const float rx = (float)rx_i, ry = (float)ry_i;
   tlx_ = rx;

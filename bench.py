@@ -156,6 +156,10 @@ def bench_ours(args):
         free_b, _ = torch.cuda.mem_get_info(local)
         T = max(1, min(T, int(0.85 * free_b / per_map)))
     gate = (2 if T >= 4 else 0) if args.device_gate < 0 else args.device_gate
+    if not args.no_cpu_baseline:   # the parity leg compares with the oracle, whose Subdiv2D is this image's cv2
+        import ctypes
+        from oracle import subdiv as _sd
+        lib.load().aos_set_subdiv_outer_factor(ctypes.c_float(_sd.outer_factor()))
     lib.load().aos_set_device_gate(gate)   # maps admitted to the seed stage's kernel phase at a time (0 = no limit)
     spec0 = synth.config(args.workload, seed=rank * 64, n_points=args.points)
     params = make_params(lib, spec0)

@@ -231,11 +231,18 @@ AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, cons
                                     aos_mem points_mem);
 
 /* cv::Subdiv2D::initDelaunay places its three outer vertices big_coord = factor * max(rect.width, rect.height)
- * away.  factor is 6 in the OpenCV this library is validated against bit-for-bit (4.13, tests/test_subdiv_cpu.py)
- * and, to the best of our knowledge, 3 up to OpenCV 4.5.x (ROS 2 Humble's libopencv-dev, package.xml:48); it
- * only moves the far-away Voronoi vertices of hull cells, which filterNodesAndEdgesOutsideGrid crops.
- * Process-wide; default 6. */
+ * away: factor 3 up to OpenCV 4.5.x (ROS 2 Humble's libopencv-dev = 4.5.4, the reference's platform, package.xml:48),
+ * 6 in OpenCV 4.13 (the cv2 this library is validated against bit for bit, tests/test_subdiv_cpu.py).
+ * The factor is NOT cosmetic: the far vertices change the flip history, hence which quad-edge pair each Voronoi
+ * vertex is computed from; on orchard seed sets the graph topology stays the same but about 5 % of the node
+ * coordinates move by a few float32 ulps (up to 2.3e-5 m at 60 m; tests/test_subdiv_cpu.py::test_outer_factor_...).
+ * A node that wants the graph of ITS OpenCV bit for bit sets the factor it links against -- one line, version-agnostic:
+ *     cv::Subdiv2D probe(cv::Rect(0, 0, 100, 100));
+ *     aos_set_subdiv_outer_factor(probe.getVertex(1).x / 100.f);
+ * (INTEGRATION.md section 3).  Process-wide; default 3 = the reference's platform. */
 AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
+/* Current kernel-phase gate (aos_set_device_gate); aos_map_to_graph_batch restores it when it returns. */
+AOS_API int32_t aos_get_device_gate(void);
 /* Test switch (process-wide): make every Lawson flip of the replay run swapEdges' four literal splices instead of
  * the fused read-once / write-once update of the twelve `next` slots.  Same result; off by default. */
 AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
@@ -331,6 +338,10 @@ AOS_API aos_status aos_band_ipc_export(aos_ctx *ctx, int32_t buffer, unsigned ch
 AOS_API aos_status aos_band_ipc_import(aos_ctx *ctx, int32_t side, int32_t buffer, const unsigned char *handle,
                                        int32_t peer_first_global_row);
 AOS_API aos_status aos_band_thin_launch_p2p(aos_ctx *ctx, int32_t *deleted);
+/* Close this context's mappings of its neighbours' planes and forget that its own were exported.  The exported planes
+ * are never re-allocated while a peer may have them open: aos_band_raster refuses (AOS_ERR_STATE) a map that needs
+ * larger planes until EVERY rank has called this and passed a barrier; the next map then exports / imports again. */
+AOS_API aos_status aos_band_ipc_release(aos_ctx *ctx);
 /* Device pointer of a LOCAL grid (AOS_GRID_RAW .. AOS_GRID_SKELETON; the skeleton is the current thinning image): local row r is global row row0 - halo_lo + r. */
 AOS_API aos_status aos_band_grid_device(aos_ctx *ctx, aos_grid_id which, uint32_t **bits, int32_t *pitch_words,
                                         int32_t *local_rows);

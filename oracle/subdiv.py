@@ -56,3 +56,12 @@ def voronoi_facets(seeds: np.ndarray, minx: float, maxx: float, miny: float, max
         off[i + 1] = off[i] + len(f)
     xy = np.concatenate([np.asarray(f, np.float32).reshape(-1, 2) for f in facets]) if facets else np.zeros((0, 2), np.float32)
     return np.ascontiguousarray(xy, np.float32), off, np.asarray(inserted, np.float32).reshape(-1, 2)
+
+
+def outer_factor() -> float:
+    """big_coord / max(side) of THIS image's cv::Subdiv2D::initDelaunay, probed from the real cv2 (3 up to OpenCV 4.5.x,
+    6 in 4.13).  Tests, smoke() and bench.py pass it to aos_set_subdiv_outer_factor so that the library replays the
+    Subdiv2D the oracle runs; the library's own default is the reference platform's 3."""
+    import cv2
+    sd = cv2.Subdiv2D((0, 0, 100, 100))
+    return float(sd.getVertex(1)[0][0]) / 100.0

@@ -152,3 +152,50 @@ def test_replay_matches_cv2_at_c3_size(oracle):
     gx, go = lib.voronoi_facets(s, *b)
     assert len(go) - 1 == len(s) and len(gx) > 1_300_000
     assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32))
+
+
+def test_outer_factor_changes_vertex_bits_not_topology(oracle):
+    """cv::Subdiv2D::initDelaunay's outer triangle sits 3 x (OpenCV <= 4.5.x, the reference's platform and the library's
+    default) or 6 x (4.13, this image) the rectangle away.  The far vertices change the flip history, so the factor is
+    part of the arithmetic: on an orchard seed set the graph topology is the same, but a few per cent of the node
+    coordinates move by float32 ulps.  (Hence aos_set_subdiv_outer_factor and the one-line probe a node runs against
+    the OpenCV it links; conftest.py does the same with cv2.)"""
+    import ctypes as C
+    from aos_gpu import synth
+    from oracle import subdiv
+    L = lib.load()
+    assert subdiv.outer_factor() in (3.0, 6.0)
+    spec = synth.config("C2", seed=0, n_points=600_000)
+    p = oracle.SeedParams(grid_resolution=spec.grid_resolution, inflation_radius=spec.inflation_radius, polygon=spec.polygon)
+    oracle.set_fast(True)
+    try:
+        a = oracle.seed_stage(p, synth.make_orchard(spec))
+        merged = oracle.merge_seeds(a["seeds"])
+        minx, miny = float(a["origin_x"]), float(a["origin_y"])
+        maxx = minx + float(np.float32(np.float32(a["w"]) * a["res"]))
+        maxy = miny + float(np.float32(np.float32(a["h"]) * a["res"]))
+        skel = np.ascontiguousarray(a["skel_framed"])
+        rows = np.ascontiguousarray(a["rows_info"], np.float64)
+        out = {}
+        for f in (3.0, 6.0):
+            L.aos_set_subdiv_outer_factor(C.c_float(f))
+            xy, off = lib.voronoi_facets(merged, minx, maxx, miny, maxy)
+            gr = oracle._Graph()
+            rc = oracle.lib().orc_gvd_graph(xy.ctypes.data_as(oracle._PF), off.ctypes.data_as(oracle._P32), len(off) - 1,
+                                            skel.ctypes.data_as(oracle._P8), skel.shape[1], skel.shape[0], minx, miny,
+                                            C.c_float(float(a["res"])), rows.ctypes.data_as(oracle._PD), len(rows), C.byref(gr))
+            assert rc == 0
+            out[f] = (oracle._arr(gr.nodes, 2 * gr.n_nodes, np.float64).reshape(-1, 2),
+                      oracle._arr(gr.edges, 2 * gr.n_edges, np.int32).reshape(-1, 2),
+                      oracle._arr(gr.node_labels, gr.n_nodes, np.int32))
+            oracle.lib().orc_graph_free(C.byref(gr))
+            if f == subdiv.outer_factor():   # the factor of this image's cv2 reproduces the real Subdiv2D bit for bit
+                fx, fo, _ = subdiv.voronoi_facets(merged, minx, maxx, miny, maxy)
+                assert np.array_equal(fo, off) and np.array_equal(fx, xy)
+    finally:
+        oracle.set_fast(False)
+        L.aos_set_subdiv_outer_factor(C.c_float(subdiv.outer_factor()))
+    (n3, e3, l3), (n6, e6, l6) = out[3.0], out[6.0]
+    assert n3.shape == n6.shape and np.array_equal(e3, e6) and np.array_equal(l3, l6)      # same graph ...
+    d = np.abs(n3 - n6).max(axis=1)
+    assert 0 < (d > 0).sum() < 0.2 * len(n3) and d.max() < 1e-4                              # ... different low bits
