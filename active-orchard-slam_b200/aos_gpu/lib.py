@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "aos_select_seeds", "aos_get_seeds", "aos_get_rows_info", "aos_get_launch_count",
     "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_voronoi_facets_device", "aos_merge_seeds_device", "aos_trim_path", "aos_set_subdiv_outer_factor", "aos_set_subdiv_literal_splices", "aos_set_device_gate",
     "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_ipc_export", "aos_band_ipc_import",
-    "aos_band_thin_launch_p2p", "aos_band_grid_device", "aos_seed_stage_tail", "aos_band_ipc_release", "aos_get_device_gate",
+    "aos_band_thin_launch_p2p", "aos_band_grid_device", "aos_seed_stage_tail", "aos_band_ipc_release", "aos_get_device_gate", "aos_set_voronoi_mode",
 ]
 
 
@@ -159,6 +159,7 @@ def load() -> C.CDLL:
     L.aos_band_ipc_import.argtypes = [vp, i32, i32, vp, i32]
     L.aos_band_thin_launch_p2p.argtypes = [vp, C.POINTER(i32)]
     L.aos_band_ipc_release.argtypes = [vp]
+    L.aos_set_voronoi_mode.argtypes = [vp, i32]
     L.aos_get_device_gate.restype = i32
     L.aos_band_grid_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.aos_seed_stage_tail.argtypes = [vp, C.POINTER(CSeedParams), vp, vp]
@@ -433,6 +434,10 @@ class Context:
         cache.pop((side, buffer), None)
         self._check(self.L.aos_band_ipc_import(self.h, side, buffer, h, peer_first_global_row), "aos_band_ipc_import")
         cache[(side, buffer)] = (handle, peer_first_global_row)
+
+    def set_voronoi_mode(self, device: bool):
+        """False: Subdiv2D insertion replay (bit-exact, default).  True: parallel Voronoi cells on the device (opt-in)."""
+        self._check(self.L.aos_set_voronoi_mode(self.h, 1 if device else 0), "aos_set_voronoi_mode")
 
     def band_ipc_release(self):
         self._check(self.L.aos_band_ipc_release(self.h), "aos_band_ipc_release")

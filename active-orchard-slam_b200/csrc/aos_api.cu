@@ -194,7 +194,7 @@ void aos_destroy(aos_ctx *c) {
       if (c->band_peer[s][b]) cudaIpcCloseMemHandle(c->band_peer[s][b]);
   c->band_thin[0].release();
   c->band_thin[1].release();
-  DevBuf *sdb[] = {&c->sd_quads, &c->sd_verts, &c->sd_vor, &c->sd_base};
+  DevBuf *sdb[] = {&c->sd_quads, &c->sd_verts, &c->sd_vor, &c->sd_base, &c->vc_cells};
   for (DevBuf *b : sdb) b->release();
   subdiv_release_pins(c);
   c->graph.release();
@@ -238,6 +238,12 @@ aos_status aos_set_device_gate(int32_t max_concurrent) {
 }
 
 int32_t aos_get_device_gate(void) { return g_device_gate_cap.load(); }
+
+aos_status aos_set_voronoi_mode(aos_ctx *c, int32_t mode) {
+  if (!c || (mode != AOS_VORONOI_REPLAY && mode != AOS_VORONOI_DEVICE)) return AOS_ERR_INVALID;
+  c->voronoi_mode = mode;
+  return AOS_OK;
+}
 
 aos_status aos_set_profiling(aos_ctx *c, int enabled) {
   if (!c) return AOS_ERR_INVALID;

@@ -217,6 +217,10 @@ aos_status run_ror(Ctx *c, const void *dpoints, size_t n, uint32_t step, uint32_
                    int min_neighbors, size_t *n_out);
 aos_status facets_prepare(Ctx *c, const Subdiv &sd, int *n_slots);  // *n_slots = -1: structure is not a triangulation
 aos_status facets_fill(Ctx *c, float2 *d_fxy, int *d_enext);
+// k_vcells.cu: the opt-in device Voronoi (one thread per seed clips its cell); *n_slots = -1: a cell overflowed
+aos_status vcells_prepare(Ctx *c, const double *seeds, int n_seeds, double min_x, double max_x, double min_y, double max_y,
+                          int *n_slots);
+aos_status vcells_fill(Ctx *c, float2 *d_fxy, int *d_enext);
 void subdiv_release_pins(Ctx *c);  // host_gvd.cu
 
 // RAII hold of one slot of the per-device kernel-phase gate (aos_api.cu; a no-op unless aos_set_device_gate(n > 0))
@@ -262,6 +266,7 @@ struct GraphInputs {
   const float *facet_xy = nullptr;  // pinned host: one x,y per facet-vertex slot; slot e also is Voronoi edge e (vd:97-114)
   const int *enext = nullptr;       // pinned host: slot of the edge's end point (next vertex of the same facet)
   bool device_facets = false;       // slots and links come from facets_fill (k_facets.cu) instead of the two host arrays
+  bool device_cells = false;        // ... or from vcells_fill (k_vcells.cu, aos_set_voronoi_mode(AOS_VORONOI_DEVICE))
   int n_slots = 0;
   const double *rows_info = nullptr;  // host, 4 per row
   int n_rows = 0;
@@ -368,7 +373,10 @@ struct Ctx {
   PinVec<double> pin_seed_in;    // caller-owned seeds staged for the merge
   PinVec<char> pin_a, pin_b, pin_c;  // staging of the small per-map tables (rows, replay jobs, cluster tables)
   Subdiv subdiv;                                    // lives in the context so its arrays are allocated (and pinned) once
-  DevBuf sd_quads, sd_verts, sd_vor, sd_base;       // k_facets.cu
+  DevBuf sd_quads, sd_verts, sd_vor, sd_base;       // k_facets.cu (and k_vcells.cu in device-Voronoi mode)
+  DevBuf vc_cells;                                  // k_vcells.cu: neighbour grid offsets + cursors
+  int vc_n = 0;
+  int voronoi_mode = 0;                             // aos_set_voronoi_mode: 0 = Subdiv2D replay (bit-exact), 1 = device cells
   int sd_nv = 0, sd_nq = 0;
   void *sd_pinned[3] = {nullptr, nullptr, nullptr};  // cudaHostRegister'ed storage of subdiv's three arrays
   size_t sd_pinned_bytes[3] = {0, 0, 0};

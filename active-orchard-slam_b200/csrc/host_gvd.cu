@@ -289,11 +289,6 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   const double miny = in.oy, maxy = in.oy + (double)(float)((float)(unsigned)in.h * in.res);
   // VoronoiDiagram::compute: the Delaunay insertions are a sequential replay on the host (host_subdiv.cu); the
   // circumcentres and the facet walks are data-parallel and run on the device (k_facets.cu)
-  Subdiv &sd = c->subdiv;
-  const bool built = host_subdiv_build(sd, c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy,
-                                       [c, &sd](size_t n) { sd_unpin_if_growing(c, sd, n); });
-  c->mark("gvd_host_voronoi");
-  const double tg2 = dbg ? wall() : 0;
   if (!c->pin_rows.resize(4 * (size_t)n_rows)) {
     set_error(c, "cudaHostAlloc failed for the row staging buffer");
     return AOS_ERR_CUDA;
@@ -301,6 +296,29 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
   if (n_rows) memcpy(c->pin_rows.data(), rows_info, sizeof(double) * 4 * (size_t)n_rows);
   in.rows_info = c->pin_rows.data();
   in.n_rows = n_rows;
+  if (c->voronoi_mode == AOS_VORONOI_DEVICE) {
+    // opt-in: the Voronoi cells of the same point set, one thread per seed, no insertion replay (k_vcells.cu).  Same
+    // diagram; vertex low bits and facet starts are not Subdiv2D's, so the graph is not bit-identical to the reference's.
+    int cell_slots = 0;
+    aos_status vs = vcells_prepare(c, c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy, &cell_slots);
+    if (vs != AOS_OK) return vs;
+    c->mark("gvd_device_voronoi");
+    if (cell_slots >= 0) {
+      in.device_facets = true;
+      in.device_cells = true;
+      in.n_slots = cell_slots;
+      aos_status s = run_graph(c, in);
+      if (s != AOS_OK) return s;
+      c->have_graph = true;
+      return AOS_OK;
+    }
+    // a cell overflowed the fixed-size polygons (never seen): fall through to the replay
+  }
+  Subdiv &sd = c->subdiv;
+  const bool built = host_subdiv_build(sd, c->h_merged.data(), (int)(c->h_merged.size() / 2), minx, maxx, miny, maxy,
+                                       [c, &sd](size_t n) { sd_unpin_if_growing(c, sd, n); });
+  c->mark("gvd_host_voronoi");
+  const double tg2 = dbg ? wall() : 0;
   int dev_slots = -1;
   if (built) {
     sd_pin_all(c, sd);

@@ -767,7 +767,7 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   uint32_t *d_tot = reinterpret_cast<uint32_t *>(d_cnt + 8);  // scan totals
 
   if (in.device_facets) {
-    aos_status fs = facets_fill(c, d_fxy, d_enext);
+    aos_status fs = in.device_cells ? vcells_fill(c, d_fxy, d_enext) : facets_fill(c, d_fxy, d_enext);
     if (fs != AOS_OK) return fs;
   } else {
     AOS_CUDA_OK(c, cudaMemcpyAsync(d_fxy, in.facet_xy, sizeof(float2) * K, cudaMemcpyHostToDevice, st));

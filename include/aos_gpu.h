@@ -241,6 +241,18 @@ AOS_API aos_status aos_map_to_graph(aos_ctx *ctx, const aos_seed_params *p, cons
  *     aos_set_subdiv_outer_factor(probe.getVertex(1).x / 100.f);
  * (INTEGRATION.md section 3).  Process-wide; default 3 = the reference's platform. */
 AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
+/* How VoronoiDiagram::compute (vd:16-114) is carried out on this context.
+ *   AOS_VORONOI_REPLAY (default): cv::Subdiv2D's incremental insertion replayed step for step on the host
+ *       (csrc/host_subdiv.cu), circumcentres and facet walks on the device: the graph is the reference's bit for bit.
+ *   AOS_VORONOI_DEVICE (opt-in): the Voronoi cells of the same point set (seeds + Subdiv2D's outer triangle) built in
+ *       parallel, one thread per seed clipping its cell by its neighbours' bisectors (csrc/k_vcells.cu).  Same diagram,
+ *       no sequential step (0.27 s -> about 1 ms per 240 k seeds); but which edge pair a circumcentre is computed from
+ *       and where a facet starts are products of Subdiv2D's flip history, so vertex low bits and the winners of the
+ *       5 cm first-come merge (vd:149-207) can differ: the graph equals the reference's up to those choices (measured
+ *       in tests/test_vcells_gpu.py and DESIGN.md), not bit for bit. */
+#define AOS_VORONOI_REPLAY 0
+#define AOS_VORONOI_DEVICE 1
+AOS_API aos_status aos_set_voronoi_mode(aos_ctx *ctx, int32_t mode);
 /* Current kernel-phase gate (aos_set_device_gate); aos_map_to_graph_batch restores it when it returns. */
 AOS_API int32_t aos_get_device_gate(void);
 /* Test switch (process-wide): make every Lawson flip of the replay run swapEdges' four literal splices instead of
