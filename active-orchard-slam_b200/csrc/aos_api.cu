@@ -381,6 +381,7 @@ extern "C" {
 
 aos_status aos_seed_stage(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points,
                           uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  NvtxRange nvtx_range("aos_seed_stage");
   if (!c) return AOS_ERR_INVALID;
   aos_status s = check_params(c, p);
   if (s != AOS_OK) return s;
@@ -462,6 +463,7 @@ int32_t aos_band_halo_rows(const aos_seed_params *p) {
 
 aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band *band, const void *points, size_t n_points,
                            uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  NvtxRange nvtx_range("aos_band_raster");
   if (!c) return AOS_ERR_INVALID;
   aos_status s = check_params(c, p);
   if (s != AOS_OK) return s;
@@ -542,6 +544,7 @@ aos_status aos_band_raster(aos_ctx *c, const aos_seed_params *p, const aos_band 
 }
 
 aos_status aos_band_thin_launch(aos_ctx *c, int32_t *deleted) {
+  NvtxRange nvtx_range("aos_band_thin_launch");
   if (!c) return AOS_ERR_INVALID;
   if (!c->have_band) {
     set_error(c, "aos_band_raster has not completed");
@@ -605,6 +608,7 @@ aos_status aos_band_ipc_import(aos_ctx *c, int32_t side, int32_t buffer, const u
 }
 
 aos_status aos_band_thin_launch_p2p(aos_ctx *c, int32_t *deleted) {
+  NvtxRange nvtx_range("aos_band_thin_launch_p2p");
   if (!c) return AOS_ERR_INVALID;
   if (!c->have_band) {
     set_error(c, "aos_band_raster has not completed");
@@ -657,6 +661,7 @@ aos_status aos_band_grid_device(aos_ctx *c, aos_grid_id which, uint32_t **bits, 
 }
 
 aos_status aos_seed_stage_tail(aos_ctx *c, const aos_seed_params *p, const uint32_t *skeleton_bits, const uint32_t *occupancy_bits) {
+  NvtxRange nvtx_range("aos_seed_stage_tail");
   if (!c || !skeleton_bits) return AOS_ERR_INVALID;
   aos_status s = check_params(c, p);
   if (s != AOS_OK) return s;
@@ -801,6 +806,7 @@ aos_status aos_get_launch_count(aos_ctx *c, int64_t *out) {
 }
 
 aos_status aos_select_seeds(aos_ctx *c, int32_t *n_seeds, int32_t counts[3]) {
+  NvtxRange nvtx_range("aos_select_seeds");
   if (!c) return AOS_ERR_INVALID;
   if (!c->have_seed) {
     set_error(c, "aos_seed_stage has not completed");
@@ -872,6 +878,7 @@ aos_status aos_thin_bits(aos_ctx *c, uint32_t *inout, int32_t w, int32_t h, int3
 aos_status aos_radius_outlier_removal(aos_ctx *c, const void *points, size_t n_points, uint32_t point_step, uint32_t off_x,
                                       uint32_t off_y, uint32_t off_z, aos_mem points_mem, float radius, int32_t min_neighbors,
                                       const void **out_points, size_t *n_out) {
+  NvtxRange nvtx_range("aos_radius_outlier_removal");
   if (!c || !out_points || !n_out) return AOS_ERR_INVALID;
   aos_status s = check_points(c, points, n_points, point_step, off_x, off_y, off_z);
   if (s != AOS_OK) return s;

@@ -17,6 +17,8 @@
 #ifndef __CUDA_ARCH_LIST__
 #endif
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler injects itself
+
 namespace aos {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
@@ -224,6 +226,14 @@ aos_status vcells_fill(Ctx *c, float2 *d_fxy, int *d_enext);
 void subdiv_release_pins(Ctx *c);  // host_gvd.cu
 
 // RAII hold of one slot of the per-device kernel-phase gate (aos_api.cu; a no-op unless aos_set_device_gate(n > 0))
+// NVTX range over one C-ABI call (tracing): "aos_seed_stage", "aos_gvd_stage", ...
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 struct DeviceGate {
   int dev = -1;
   explicit DeviceGate(const Ctx *c);
@@ -307,6 +317,7 @@ struct Ctx {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<std::string, int>> marks;  // (stage that ENDS at this event, event index)
   void mark(const char *name) {
+    nvtxMarkA(name);  // NVTX marker where each stage's launches end on the host timeline (ranges: NvtxRange per C-ABI call)
     if (!profile) return;
     int i = (int)marks.size();
     if (i >= (int)ev_pool.size()) {

@@ -207,11 +207,13 @@ static aos_status gvd_stage_impl(aos_ctx *c, const double *seeds_xy, int32_t n_s
 
 aos_status aos_gvd_stage(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
                          const int8_t *skeleton, const aos_grid_info *info) {
+  NvtxRange nvtx_range("aos_gvd_stage");
   return gvd_stage_impl(c, seeds_xy, n_seeds, rows_info, n_rows, skeleton, false, AOS_MEM_HOST, info);
 }
 
 aos_status aos_gvd_stage_bits(aos_ctx *c, const double *seeds_xy, int32_t n_seeds, const double *rows_info, int32_t n_rows,
                               const uint32_t *skeleton_bits, aos_mem skeleton_mem, const aos_grid_info *info) {
+  NvtxRange nvtx_range("aos_gvd_stage_bits");
   if (!skeleton_bits || !info) return AOS_ERR_INVALID;
   return gvd_stage_impl(c, seeds_xy, n_seeds, rows_info, n_rows, skeleton_bits, true, skeleton_mem, info);
 }
@@ -403,6 +405,7 @@ aos_status aos_get_graph(aos_ctx *c, aos_gvd_graph *out) {
 
 aos_status aos_map_to_graph(aos_ctx *c, const aos_seed_params *p, const void *points, size_t n_points, uint32_t point_step,
                             uint32_t off_x, uint32_t off_y, uint32_t off_z, aos_mem points_mem) {
+  NvtxRange nvtx_range("aos_map_to_graph");
   if (!c) return AOS_ERR_INVALID;
   static const bool dbg = getenv("AOS_DEBUG") != nullptr;
   static const auto t_proc = std::chrono::steady_clock::now();
