@@ -256,6 +256,39 @@ def bench_ours(args):
 
     # digest of map 0's result (every published array) -- compared with the CPU oracle on the same cloud below
     gpu_digest, gpu_parts = c0.result_digest(parts=True)
+    device_voronoi = None
+    if not args.no_device_voronoi:
+        # the opt-in parallel Voronoi (aos_set_voronoi_mode(AOS_VORONOI_DEVICE)): same maps, no host insertion replay; NOT
+        # bit-identical to the reference, so it is reported beside the headline, never as it
+        from aos_gpu.compare import compare_graphs
+        g_replay = c0.graph()
+        for c in ctxs:
+            c.set_voronoi_mode(True)
+        run_batch(2)
+        dv_ms, _ = timed(args.steps)
+        with torch.cuda.stream(stream):
+            c0.set_profiling(True)
+            c0.map_to_graph(params, maps[0])
+            dv_stages = dict(c0.stage_times())
+            c0.set_profiling(False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                c0.map_to_graph(params, maps[0])
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dv_single = e0.elapsed_time(e1) / 3
+        g_dev = c0.graph()
+        for c in ctxs:
+            c.set_voronoi_mode(False)
+        dv_ms, dv_cells = adist.reduce_stats(dv_ms, cells * args.steps * T, device=dev)
+        device_voronoi = {"value": round(adist.throughput_mcells(dv_cells, dv_ms), 1), "unit": UNIT,
+                          "ms_per_step": round(dv_ms / args.steps, 3), "single_map_ms": round(dv_single, 3),
+                          "device_stages_ms": round(sum(dv_stages.values()), 3),
+                          "voronoi_stage_ms": round(dv_stages.get("gvd_device_voronoi", 0.0), 3),
+                          "bit_exact": False, "agreement_with_replay_map0": compare_graphs(g_replay, g_dev),
+                          "note": "opt-in aos_set_voronoi_mode(AOS_VORONOI_DEVICE); the headline value/e2e use the bit-exact replay"}
     dev_ms, total_cells = adist.reduce_stats(dev_ms, cells * args.steps * T, device=dev)   # MAX over ranks, SUM of cells
     e2e_ms, _ = adist.reduce_stats(e2e_ms, cells * args.steps * T, device=dev)
     ms_per_step = dev_ms / args.steps
@@ -308,6 +341,8 @@ def bench_ours(args):
             "clocks": clk.summary(),
             "gen_s": round(gen_s, 2), "points_per_map": int(n_pts),
         }
+        if device_voronoi is not None:
+            line["device_voronoi"] = device_voronoi
         if not args.no_cpu_baseline and world == 1:   # reported beside the N = 1 line only
             cb, parity = cpu_baseline_full(args, host_np, spec0, gpu_digest, gpu_parts)
             line["cpu_baseline"] = cb
@@ -729,6 +764,7 @@ def main():
                     help="maps admitted to the seed stage's kernel phase at a time per GPU (aos_set_device_gate); 0 = no limit; "
                          "default 2 when at least 4 maps are in flight")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-device-voronoi", action="store_true", help="skip the opt-in device-Voronoi sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
