@@ -32,7 +32,7 @@ namespace {
 constexpr int kMaxPoly = 40;        // vertices of a cell while it is being clipped
 constexpr int kMaxOut = 24;         // vertices of a finished cell (slot stride of the scratch polygons)
 constexpr double kGridCell = 2.0;   // metres; merged seeds are at least 0.5 m apart
-constexpr double kClipMargin = 12.0;
+constexpr double kClipMargin = 3.0;   // beyond Subdiv2D's rectangle (= grid + 1 m): outside the grid either way
 constexpr int kOuter = 3;           // sites 0..2 are Subdiv2D's outer triangle
 
 struct VcParams {
@@ -227,10 +227,18 @@ __global__ void __launch_bounds__(64) vc_cell_kernel(VcParams P, const double2 *
     return;
   }
   if (poly.m < 2) return;
-  // start at the edge with the smallest neighbour id (any fixed rule; Subdiv2D's start is a product of its history)
-  int start = 0;
-  for (int k = 1; k < poly.m; ++k)
+  // Where Subdiv2D starts the facet: at rot(vtx.firstEdge), and firstEdge is the edge most recently (re)assigned at the
+  // vertex.  An edge to a LATER-inserted neighbour w is assigned when w is inserted and survives (flipping it away would
+  // need a still later neighbour), so firstEdge = the edge to the highest-index neighbour whenever that index exceeds the
+  // seed's own, and the facet starts at the vertex that begins the bisector edge of that neighbour (verified against
+  // cv2 on every facet of the C2 maps).  A seed whose neighbours are all earlier (about 3 %) keeps the edge last assigned
+  // during its own insertion, which depends on the flip order: those start at the smallest neighbour id instead.
+  int start = 0, hi = 0;
+  for (int k = 1; k < poly.m; ++k) {
     if (poly.id[k] < poly.id[start]) start = k;
+    if (poly.id[k] > poly.id[hi]) hi = k;
+  }
+  if (poly.id[hi] > i) start = hi;
   for (int t = 0; t < poly.m; ++t) {
     const int k = (start + t) % poly.m, kp = k == 0 ? poly.m - 1 : k - 1;
     const int a = poly.id[kp], b = poly.id[k];  // vertex k is where the bisectors of (i, a) and (i, b) meet

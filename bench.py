@@ -570,9 +570,29 @@ def run_bands(args, workload, steps, warmup, halo):
     if world > 1:
         dist.all_reduce(n_local)
     cells = gi.width * gi.height
+    digest = ctx.result_digest() if rank == 0 else None
+    # the same band run with the opt-in device Voronoi on rank 0 (no host insertion replay in the tail): timing only
+    dv = None
+    if not getattr(args, "no_device_voronoi", False):
+        if rank == 0:
+            ctx.set_voronoi_mode(True)
+        one()
+        sync_all()
+        acc2 = {}
+        w1 = time.perf_counter()
+        for _ in range(steps):
+            t2, _, g2 = one()
+            for k, v in t2.items():
+                acc2[k] = acc2.get(k, 0.0) + v * 1e3 / steps
+        sync_all()
+        ms2, _ = adist.reduce_stats((time.perf_counter() - w1) * 1e3, 0, device=dev)
+        if rank == 0:
+            ctx.set_voronoi_mode(False)
+            dv = {"ms_per_map": round(ms2 / steps, 3), "value": round(cells * steps / (ms2 * 1e-3) / 1e6, 1), "unit": UNIT,
+                  "stages_ms_rank0": {k: round(v, 3) for k, v in acc2.items() if k != "tail_rank0_host_voronoi"},
+                  "graph": None if g2 is None else {"nodes": int(g2["n_nodes"]), "edges": int(g2["n_edges"])}, "bit_exact": False}
     rec = None
     if rank == 0:
-        digest = ctx.result_digest()
         raster_ms = acc.get("raster", 0) + acc.get("thin+halo", 0) + acc.get("gather", 0)
         rec = {"workload": f"{workload}: ONE {gi.width}x{gi.height} grid @ {spec.grid_resolution} m row-band sharded over "
                            f"{world} GPU(s); one global cloud of {single['points']} points for every N "
@@ -584,7 +604,7 @@ def run_bands(args, workload, steps, warmup, halo):
                "raster_stages": {"ms": round(raster_ms, 3), "value": round(cells / (raster_ms * 1e-3) / 1e6, 1), "unit": UNIT},
                "graph": None if g is None else {"nodes": int(g["n_nodes"]), "edges": int(g["n_edges"])},
                "digest": digest, "single_gpu_digest": single["digest"], "equals_single_gpu": digest == single["digest"],
-               "clocks": clk.summary()}
+               "device_voronoi": dv, "clocks": clk.summary()}
     ctx.close()
     del pts
     torch.cuda.empty_cache()
