@@ -9,7 +9,7 @@ timeout 300 $B > $O/plain.json 2> $O/plain.err || { echo "plain run failed"; tai
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches.csv $B > $O/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
   -k regex:"bfs_replay_kernel|cc_link_kernel|edge_test_kernel|vs_generate_kernel|ray_points_kernel|thin_kernel|bin_points|inflate_kernel|corner_kernel|mask_count_kernel" \
-  -s 60 -c 40 -o $O/prof_r02 -f $B > $O/ncu_full.log 2>&1
+  -s 16 -c 16 -o $O/prof_r02 -f $B > $O/ncu_full.log 2>&1
 # the opt-in device Voronoi kernel
 cat > $O/vc.py <<'PY'
 import sys, os
@@ -27,4 +27,11 @@ print("ok", ctx.graph()["n_nodes"])
 PY
 timeout 300 python $O/vc.py > $O/vc_plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:"vc_cell_kernel" -c 2 -o $O/prof_vc -f python $O/vc.py > $O/ncu_vc.log 2>&1
 python scripts/ncu_summary.py $O/launches.csv $O/prof_r02.ncu-rep $O/prof_vc.ncu-rep > $O/summary.txt 2>&1
+# gpurun copies back at most 64 MiB: keep the text exports, drop the reports
+for r in prof_r02 prof_vc; do
+  [ -f $O/$r.ncu-rep ] && ncu -i $O/$r.ncu-rep --page raw --csv 2>/dev/null | gzip > $O/$r.raw.csv.gz
+  rm -f $O/$r.ncu-rep
+done
+rm -f gpurun_out/*.ncu-rep
+du -sh gpurun_out
 tail -5 $O/summary.txt

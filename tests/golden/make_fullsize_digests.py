@@ -19,6 +19,7 @@ from oracle import oracle as O  # noqa: E402
 CASES = {   # name -> (workload, seed, points)
     "C3": ("C3", 0, None),
     "C3_40M": ("C3", 3, 40_000_000),
+    "C4": ("C4", 0, None),          # 40000 x 40000 cells @ 0.025 m, R = 32 (about 20 GB and 2 minutes)
 }
 
 
