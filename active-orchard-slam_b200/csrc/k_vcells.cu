@@ -29,7 +29,7 @@
 namespace aos {
 
 namespace {
-constexpr int kMaxPoly = 40;        // vertices of a cell while it is being clipped
+constexpr int kMaxPoly = 32;        // vertices of a cell while it is being clipped
 constexpr int kMaxOut = 24;         // vertices of a finished cell (slot stride of the scratch polygons)
 constexpr double kGridCell = 2.0;   // metres; merged seeds are at least 0.5 m apart
 constexpr double kClipMargin = 3.0;   // beyond Subdiv2D's rectangle (= grid + 1 m): outside the grid either way
@@ -113,57 +113,96 @@ __global__ void vc_sort_kernel(const uint32_t *__restrict__ cell_off, int ncell,
   }
 }
 
-struct Poly {
-  double2 v[kMaxPoly];  // vertex k = start of edge k
-  int id[kMaxPoly];     // edge k lies on the bisector of (site, id[k]); -1..-4 = clip rectangle sides
+// A cell polygon lives in SHARED memory, one column per thread (element k of thread t at [k * kCellThreads + t]: no bank
+// conflicts), and is clipped in place: as thread-local arrays the polygons spilled to local memory and the kernel moved
+// 9 GB through DRAM per 240 k seeds (ncu, profiles/r02_c_*): 2.2 ms; in shared memory it is arithmetic only.
+constexpr int kCellThreads = 64;
+struct PolyRef {
+  double2 *v;  // vertex k = start of edge k
+  int *id;     // edge k lies on the bisector of (site, id[k]); -1..-4 = clip rectangle sides
   int m;
+  __device__ __forceinline__ double2 &V(int k) { return v[k * kCellThreads]; }
+  __device__ __forceinline__ int &I(int k) { return id[k * kCellThreads]; }
 };
 
-// clip by the half plane of points at least as close to p as to q; returns false on overflow
-__device__ bool clip(Poly &poly, double2 p, double2 q, int qid) {
-  // signed value: > 0 outside (closer to q).  |x - p|^2 - |x - q|^2 = 2 x.(q - p) + |p|^2 - |q|^2
+// clip by the half plane of points at least as close to p as to q; returns false on overflow.  The outside vertices of a
+// convex polygon form one cyclic run [a, b]: it is replaced by the two crossing points (the first keeps edge a-1's
+// label... i.e. the crossing on edge a-1 starts the new edge along the bisector of q, the crossing on edge b continues edge b).
+__device__ bool clip(PolyRef &poly, double2 p, double2 q, int qid) {
   const double nx = q.x - p.x, ny = q.y - p.y;
   const double mx = 0.5 * (p.x + q.x), my = 0.5 * (p.y + q.y);
-  double s[kMaxPoly];
-  bool any_out = false, any_in = false;
-  for (int k = 0; k < poly.m; ++k) {
-    s[k] = (poly.v[k].x - mx) * nx + (poly.v[k].y - my) * ny;
-    any_out |= s[k] > 0;
-    any_in |= s[k] <= 0;
-  }
-  if (!any_out) return true;
-  if (!any_in) {  // cannot happen for a site's own cell (p itself is inside every half plane); keep the cell
-    return true;
-  }
-  Poly out;
-  out.m = 0;
-  for (int k = 0; k < poly.m; ++k) {
-    const int k1 = k + 1 == poly.m ? 0 : k + 1;
-    const bool in0 = s[k] <= 0, in1 = s[k1] <= 0;
-    if (in0) {
-      if (out.m >= kMaxPoly) return false;
-      out.v[out.m] = poly.v[k];
-      out.id[out.m] = poly.id[k];
-      ++out.m;
+  const int m = poly.m;
+  auto side = [&](int k) {  // > 0: outside (closer to q)
+    const double2 v = poly.V(k);
+    return (v.x - mx) * nx + (v.y - my) * ny;
+  };
+  // first outside vertex whose predecessor is inside, and the length of the outside run
+  int a = -1, n_out = 0;
+  bool prev_in = side(m - 1) <= 0;
+  for (int k = 0; k < m; ++k) {
+    const bool in = side(k) <= 0;
+    if (!in) {
+      ++n_out;
+      if (prev_in) a = k;
     }
-    if (in0 != in1) {
-      const double t = s[k] / (s[k] - s[k1]);
-      const double2 x = make_double2(poly.v[k].x + t * (poly.v[k1].x - poly.v[k].x), poly.v[k].y + t * (poly.v[k1].y - poly.v[k].y));
-      if (out.m >= kMaxPoly) return false;
-      out.v[out.m] = x;
-      // leaving the half plane: the new edge runs along the bisector of q; entering: the old edge k continues
-      out.id[out.m] = in0 ? qid : poly.id[k];
-      ++out.m;
-    }
+    prev_in = in;
   }
-  poly = out;
+  if (n_out == 0) return true;
+  if (n_out == m || a < 0) return true;  // cannot happen for a site's own cell (p is inside every half plane); keep the cell
+  const int b = (a + n_out - 1) % m;     // last outside vertex of the run
+  const int ap = a == 0 ? m - 1 : a - 1, bn = b + 1 == m ? 0 : b + 1;
+  // crossing on edge ap -> a (leaving) and on edge b -> bn (entering)
+  const double s0 = side(ap), s1 = side(a), s2 = side(b), s3 = side(bn);
+  const double t0 = s0 / (s0 - s1), t1 = s2 / (s2 - s3);
+  const double2 va = poly.V(ap), vb = poly.V(a), vc = poly.V(b), vd = poly.V(bn);
+  const double2 x0 = make_double2(va.x + t0 * (vb.x - va.x), va.y + t0 * (vb.y - va.y));
+  const double2 x1 = make_double2(vc.x + t1 * (vd.x - vc.x), vc.y + t1 * (vd.y - vc.y));
+  const int id_b = poly.I(b);  // the edge that continues after the entering crossing
+  const int new_m = m - n_out + 2;
+  if (new_m > kMaxPoly) return false;
+  // rotate so that the run starts at index a with a <= b (no wrap): if it wraps, rotate the kept part to the front
+  if (a + n_out > m) {
+    // outside run wraps: kept vertices are (b+1 .. a-1), contiguous.  Move them to the front, then append x0, x1.
+    const int keep = m - n_out, first = bn;
+    for (int k = 0; k < keep; ++k) {
+      poly.V(k) = poly.V(first + k);
+      poly.I(k) = poly.I(first + k);
+    }
+    poly.V(keep) = x0;
+    poly.I(keep) = qid;
+    poly.V(keep + 1) = x1;
+    poly.I(keep + 1) = id_b;
+  } else {
+    // [0 .. a-1] kept, [a .. b] replaced by x0, x1, [b+1 .. m-1] kept and shifted
+    const int shift = 2 - n_out;
+    if (shift > 0) {
+      for (int k = m - 1; k > b; --k) {
+        poly.V(k + shift) = poly.V(k);
+        poly.I(k + shift) = poly.I(k);
+      }
+    } else if (shift < 0) {
+      for (int k = b + 1; k < m; ++k) {
+        poly.V(k + shift) = poly.V(k);
+        poly.I(k + shift) = poly.I(k);
+      }
+    }
+    poly.V(a) = x0;
+    poly.I(a) = qid;
+    poly.V(a + 1) = x1;
+    poly.I(a + 1) = id_b;
+  }
+  poly.m = new_m;
   return true;
 }
 
 // One thread per site: the cell polygon, written as up to kMaxOut float2 at scratch[i * kMaxOut], count in cnt[i]
-__global__ void __launch_bounds__(64) vc_cell_kernel(VcParams P, const double2 *__restrict__ sites, const int *__restrict__ site_cell,
-                                                     const uint32_t *__restrict__ cell_off, const int *__restrict__ items,
-                                                     float2 *__restrict__ scratch, uint32_t *__restrict__ cnt, int *__restrict__ err) {
+__global__ void __launch_bounds__(kCellThreads) vc_cell_kernel(VcParams P, const double2 *__restrict__ sites,
+                                                               const int *__restrict__ site_cell,
+                                                               const uint32_t *__restrict__ cell_off, const int *__restrict__ items,
+                                                               float2 *__restrict__ scratch, uint32_t *__restrict__ cnt,
+                                                               int *__restrict__ err) {
+  __shared__ double2 s_v[kMaxPoly * kCellThreads];
+  __shared__ int s_id[kMaxPoly * kCellThreads];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > P.n) return;
   if (i == P.n) {
@@ -181,16 +220,15 @@ __global__ void __launch_bounds__(64) vc_cell_kernel(VcParams P, const double2 *
     const int j = items[k];
     if (j < i && sites[j].x == p.x && sites[j].y == p.y) return;
   }
-  Poly poly;
-  poly.m = 4;  // counter-clockwise, as getVoronoiFacetList's polygons
-  poly.v[0] = make_double2(P.cx0, P.cy0);
-  poly.v[1] = make_double2(P.cx1, P.cy0);
-  poly.v[2] = make_double2(P.cx1, P.cy1);
-  poly.v[3] = make_double2(P.cx0, P.cy1);
-  poly.id[0] = -1;
-  poly.id[1] = -2;
-  poly.id[2] = -3;
-  poly.id[3] = -4;
+  PolyRef poly{s_v + threadIdx.x, s_id + threadIdx.x, 4};  // counter-clockwise, as getVoronoiFacetList's polygons
+  poly.V(0) = make_double2(P.cx0, P.cy0);
+  poly.V(1) = make_double2(P.cx1, P.cy0);
+  poly.V(2) = make_double2(P.cx1, P.cy1);
+  poly.V(3) = make_double2(P.cx0, P.cy1);
+  poly.I(0) = -1;
+  poly.I(1) = -2;
+  poly.I(2) = -3;
+  poly.I(3) = -4;
   bool ok = true;
   for (int o = 0; o < kOuter && ok; ++o) ok = clip(poly, p, sites[o], o);
   const int max_ring = max(P.gnx, P.gny);
@@ -216,7 +254,8 @@ __global__ void __launch_bounds__(64) vc_cell_kernel(VcParams P, const double2 *
     // every unseen seed is farther than r * kGridCell: it can only cut a cell whose radius exceeds half of that
     double rad2 = 0;
     for (int k = 0; k < poly.m; ++k) {
-      const double ddx = poly.v[k].x - p.x, ddy = poly.v[k].y - p.y;
+      const double2 v = poly.V(k);
+      const double ddx = v.x - p.x, ddy = v.y - p.y;
       rad2 = fmax(rad2, ddx * ddx + ddy * ddy);
     }
     const double reach = (double)r * kGridCell;
@@ -235,13 +274,14 @@ __global__ void __launch_bounds__(64) vc_cell_kernel(VcParams P, const double2 *
   // during its own insertion, which depends on the flip order: those start at the smallest neighbour id instead.
   int start = 0, hi = 0;
   for (int k = 1; k < poly.m; ++k) {
-    if (poly.id[k] < poly.id[start]) start = k;
-    if (poly.id[k] > poly.id[hi]) hi = k;
+    if (poly.I(k) < poly.I(start)) start = k;
+    if (poly.I(k) > poly.I(hi)) hi = k;
   }
-  if (poly.id[hi] > i) start = hi;
+  if (poly.I(hi) > i) start = hi;
   for (int t = 0; t < poly.m; ++t) {
     const int k = (start + t) % poly.m, kp = k == 0 ? poly.m - 1 : k - 1;
-    const int a = poly.id[kp], b = poly.id[k];  // vertex k is where the bisectors of (i, a) and (i, b) meet
+    const int a = poly.I(kp), b = poly.I(k);  // vertex k is where the bisectors of (i, a) and (i, b) meet
+    const double2 vk = poly.V(k);
     float2 out;
     if (a >= 0 && b >= 0 && a != b) {
       int t0 = i, t1 = a, t2 = b;  // ascending site order: the same bits from all three cells
@@ -249,9 +289,9 @@ __global__ void __launch_bounds__(64) vc_cell_kernel(VcParams P, const double2 *
       if (t1 > t2) { int s = t1; t1 = t2; t2 = s; }
       if (t0 > t1) { int s = t0; t0 = t1; t1 = s; }
       out = circumcentre_cv(sites[t0], sites[t1], sites[t2]);
-      if (!(fabsf(out.x) < FLT_MAX * 0.5f) || !(fabsf(out.y) < FLT_MAX * 0.5f)) out = make_float2((float)poly.v[k].x, (float)poly.v[k].y);
+      if (!(fabsf(out.x) < FLT_MAX * 0.5f) || !(fabsf(out.y) < FLT_MAX * 0.5f)) out = make_float2((float)vk.x, (float)vk.y);
     } else {
-      out = make_float2((float)poly.v[k].x, (float)poly.v[k].y);  // on the clip rectangle: outside the grid, cropped later
+      out = make_float2((float)vk.x, (float)vk.y);  // on the clip rectangle: outside the grid, cropped later
     }
     scratch[(size_t)i * kMaxOut + t] = out;
   }
@@ -338,7 +378,7 @@ aos_status vcells_prepare(Ctx *c, const double *seeds, int n_seeds, double min_x
   ++c->launches;
   vc_sort_kernel<<<(unsigned)((ncell + tb - 1) / tb), tb, 0, st>>>(cell_off, (int)ncell, items);
   ++c->launches;
-  vc_cell_kernel<<<(P.n + 1 + 63) / 64, 64, 0, st>>>(P, sites, site_cell, cell_off, items, c->sd_vor.as<float2>(),
+  vc_cell_kernel<<<(P.n + 1 + kCellThreads - 1) / kCellThreads, kCellThreads, 0, st>>>(P, sites, site_cell, cell_off, items, c->sd_vor.as<float2>(),
                                                      c->sd_base.as<uint32_t>(), d_err);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
