@@ -366,6 +366,8 @@ struct Ctx {
   DevBuf cl_table;   // aos_cluster[n_clusters]
   DevBuf cl_aux;     // per-cluster extreme points, candidate lists ...
   DevBuf cand_buf;
+  DevBuf bfs_buf;         // chain-compressed BFS order (k_cluster.cu, BfsBufs)
+  int bfs_fallbacks = 0;  // clusters of the last map that took the literal replay instead
   int n_skel_cells = 0;
   int *d_cell_cluster = nullptr;  // compact cell -> cluster ordinal (inside cand_buf)
   int *d_root_cellpos = nullptr;  // cluster ordinal -> canonical label (inside cl_aux)

@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
     const __grid_constant__ SeedDeviceParams P, const ClusterAcc *__restrict__ acc, const uint32_t *__restrict__ offsets,
     const int *__restrict__ grouped, const int *__restrict__ root_cellpos, float min_length,
     const int *__restrict__ flagged /* null: all clusters; else the replayed ones */,
+    const int *__restrict__ skip /* per entry of flagged: 1 = the replay gave up on it, leave its rows as they are */,
     const int *__restrict__ bfs_cells /* BFS-ordered cells of replayed clusters (same offsets) */,
     const float *__restrict__ replay_centre /* 2 per cluster, valid for replayed clusters */,
     aos_cluster *__restrict__ out_clusters, RowOut *__restrict__ out_rows) {
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(kClThreads) cluster_finalize_kernel(
   __shared__ long long s_i64[kClThreads / 32];
   __shared__ int s_int[kClThreads / 32];
   const bool replayed = flagged != nullptr;
+  if (skip && skip[blockIdx.x]) return;
   const int c = replayed ? flagged[blockIdx.x] : (int)blockIdx.x;
   const ClusterAcc a = acc[c];
   const int n = (int)a.size;
@@ -869,6 +871,311 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// BFS order without visiting the cells one by one (the default path; bfs_replay_kernel above is its fallback).
+// A thinned skeleton is almost everywhere a CHAIN: 97 % of its cells have exactly two neighbours that do not touch
+// each other.  Once the FIFO has entered a maximal run of such cells from one end it can only walk it cell by cell, one
+// cell per BFS level, and nothing else can interfere before the run's other end (a chain cell has no other neighbours).
+// So while every cell of the current level is such a walker the next levels are known in advance: level l + t holds each
+// walker's t-th successor, in the same order.  The replay therefore
+//   1. finds every cell's neighbours and the chain cells (bfs_prepare_kernel; the BFS root is never a chain cell),
+//   2. ranks the runs by pointer jumping along both directions at once (bfs_link_init / bfs_jump: log2(longest run)
+//      rounds), which gives each chain cell its run, its position in it and the run's length, and lays the runs out as
+//      arrays (bfs_runs / bfs_scatter),
+//   3. walks the component with one warp (bfs_chain_kernel): a level that contains an irregular cell (junction, corner,
+//      end, blob) or a walker at the end of its run is expanded literally -- eight lanes per cell test the neighbours in
+//      the reference's order, four cells at a time, equal claims resolved in lane order -- and a level of walkers is
+//      fast-forwarded by as many levels as the nearest event allows (end of a run; two walkers that entered one run from
+//      both ends meet in its middle), the skipped cells written by all lanes at once.
+// For the longest row of a config-3 map (9823 cells) that is ~300 sequential steps instead of 9823.  A visited chain cell
+// is not flagged: of a run only the prefix [0, lo) and the suffix [hi, L) can have been visited.
+// scripts/dev/chain_bfs_proto.py is the same algorithm in Python, checked against the plain FIFO on random images.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kItemCap = 64;  // cells of one BFS level the warp keeps in shared memory; wider levels -> fallback kernel
+
+struct BfsBufs {
+  int *nbr;                // 8 per cell: compact index of the neighbour in the reference's order, -1 = none
+  int2 *link;              // chain cell: its two neighbours (in that order); (-1,-1) irregular; (-2,-2) cluster not flagged
+  uint2 *state;            // 2 per cell (one per link): x = state index of the farthest known chain cell that way, y = steps
+  int4 *cinfo;             // x = first slot of the cell's run in run_cells (-1: irregular), y = position, z = run length
+  int *run_cells;          // the runs as arrays of compact cell indices
+  int2 *lohi;              // per run (at its first slot): positions [lo, hi) are not visited yet
+  int *headbase;           // per head cell: first slot of its run
+  unsigned char *vis;      // irregular cells: visited
+  int *ctr;                // [0] run slots handed out, [1] clusters left to the fallback, [2] broken ranking, [4 + r] round r changed
+};
+
+__global__ void bfs_prepare_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix, int pitch, int h, int w,
+                                   const int *__restrict__ cellpos, const int *__restrict__ cell_cluster,
+                                   const int *__restrict__ root_cellpos, const RowOut *__restrict__ rows, int n, BfsBufs B) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = cell_cluster[i];
+    if (!(rows[c].flags & (kFlagNeedsOrder | kFlagTie))) {
+      B.link[i] = make_int2(-2, -2);
+      continue;
+    }
+    const int pos = cellpos[i];
+    const int y = pos / w, x = pos - y * w;
+    int ids[8];
+    int deg = 0, n0 = -1, n1 = -1, k0 = 0, k1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int kk = k + (k >= 4);
+      const int nx = x + kk / 3 - 1, ny = y + kk % 3 - 1;
+      int id = -1;
+      if ((unsigned)nx < (unsigned)w && (unsigned)ny < (unsigned)h) id = compact_index(mask, prefix, pitch, nx, ny);
+      ids[k] = id;
+      if (id >= 0) {
+        if (deg == 0) n0 = id, k0 = kk;
+        else if (deg == 1) n1 = id, k1 = kk;
+        ++deg;
+      }
+    }
+    int4 *dst = reinterpret_cast<int4 *>(B.nbr + 8 * (size_t)i);
+    dst[0] = make_int4(ids[0], ids[1], ids[2], ids[3]);
+    dst[1] = make_int4(ids[4], ids[5], ids[6], ids[7]);
+    // a chain cell: two neighbours that are not neighbours of each other; the root starts the FIFO and stays irregular
+    const bool apart = abs(k0 / 3 - k1 / 3) > 1 || abs(k0 % 3 - k1 % 3) > 1;
+    const bool chain = deg == 2 && apart && pos != root_cellpos[c];
+    B.link[i] = chain ? make_int2(n0, n1) : make_int2(-1, -1);
+    B.cinfo[i] = make_int4(-1, 0, 0, 0);
+  }
+}
+
+__global__ void bfs_link_init_kernel(int n, BfsBufs B) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 l = B.link[i];
+    if (l.x < 0) continue;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int t = s ? l.y : l.x;
+      const int2 lt = B.link[t];
+      // the neighbour continues the run through its OTHER link; an irregular neighbour ends the run at this cell
+      B.state[2 * (size_t)i + s] = lt.x >= 0 ? make_uint2(2u * (unsigned)t + (lt.x == i ? 1u : 0u), 1u) : make_uint2(2u * (unsigned)i + s, 0u);
+    }
+  }
+}
+
+// One round of pointer jumping, in place: an entry that reads its target before or after the target's own update composes
+// two true statements either way (8-byte entries are loaded and stored whole).
+__global__ void bfs_jump_kernel(int n, BfsBufs B, int round) {
+  if (round > 0 && B.ctr[4 + round - 1] == 0) return;  // the previous round changed nothing
+  bool changed = false;
+  const unsigned total = 2u * (unsigned)n;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    if (B.link[idx >> 1].x < 0) continue;
+    const uint2 st = __ldcg(B.state + idx);
+    if (st.x == idx) continue;  // the run ends here
+    const uint2 st2 = __ldcg(B.state + st.x);
+    if (st2.x == st.x) continue;  // already at the end of the run
+    __stcg(B.state + idx, make_uint2(st2.x, st.y + st2.y));
+    changed = true;
+  }
+  if (changed) B.ctr[4 + round] = 1;
+}
+
+__global__ void bfs_runs_kernel(int n, BfsBufs B) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (B.link[i].x < 0) continue;
+    const uint2 e0 = B.state[2 * (size_t)i], e1 = B.state[2 * (size_t)i + 1];
+    const int E0 = (int)(e0.x >> 1), E1 = (int)(e1.x >> 1), L = (int)(e0.y + e1.y) + 1;
+    int head, pos;
+    if (E0 == E1) {  // a run of one cell (a closed ring of chain cells cannot exist: every component has its root)
+      head = i;
+      pos = 0;
+      if (L != 1) B.ctr[2] = 1;
+    } else if (E0 < E1) {
+      head = E0;
+      pos = (int)e0.y;
+    } else {
+      head = E1;
+      pos = (int)e1.y;
+    }
+    if (head == i) {
+      const int rb = atomicAdd(&B.ctr[0], L);
+      B.headbase[i] = rb;
+      B.lohi[rb] = make_int2(0, L);
+    }
+    B.cinfo[i] = make_int4(head, pos, L, 0);
+  }
+}
+
+__global__ void bfs_scatter_kernel(int n, BfsBufs B) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (B.link[i].x < 0) continue;
+    int4 ci = B.cinfo[i];
+    ci.x = B.headbase[ci.x];
+    B.cinfo[i] = ci;
+    B.run_cells[ci.x + ci.y] = i;
+  }
+}
+
+// float32 running sums in FIFO order (seed_gen:1053-1057) over a finished BFS-order cell list: lanes fetch 32 cells at a
+// time, the additions themselves stay strictly sequential (every lane keeps the same copy)
+__device__ __forceinline__ void ordered_centre(const int *q, int n, int w, int lane, float *cx, float *cy) {
+  float sum_x = 0.f, sum_y = 0.f;
+  for (int base = 0; base < n; base += 32) {
+    int pos = base + lane < n ? __ldcg(q + base + lane) : 0;
+    int y = pos / w;
+    float xf = (float)(pos - y * w), yf = (float)y;
+    if (n - base >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sum_x = __fadd_rn(sum_x, __shfl_sync(0xffffffffu, xf, j));
+        sum_y = __fadd_rn(sum_y, __shfl_sync(0xffffffffu, yf, j));
+      }
+    } else {
+      const int cnt = n - base;
+      for (int j = 0; j < cnt; ++j) {
+        sum_x = __fadd_rn(sum_x, __shfl_sync(0xffffffffu, xf, j));
+        sum_y = __fadd_rn(sum_y, __shfl_sync(0xffffffffu, yf, j));
+      }
+    }
+  }
+  *cx = __fdiv_rn(sum_x, (float)(unsigned long long)n);
+  *cy = __fdiv_rn(sum_y, (float)(unsigned long long)n);
+}
+
+// One warp per flagged cluster.  items: x = compact cell, y = run slot (-1 irregular), z = position, w = L << 2 | dir + 1
+__global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ flagged, const ClusterAcc *__restrict__ acc,
+                                                       const uint32_t *__restrict__ offsets, const int *__restrict__ root_cellpos,
+                                                       const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix,
+                                                       int pitch, int w, const int *__restrict__ cellpos, BfsBufs B,
+                                                       int *__restrict__ fallback, int *__restrict__ queue,
+                                                       float *__restrict__ centre_out) {
+  __shared__ int4 s_items[2][kItemCap];
+  const int lane = threadIdx.x;
+  const int c = flagged[blockIdx.x];
+  const int n = (int)acc[c].size;
+  int *q = queue + offsets[c];
+  const unsigned lt = (1u << lane) - 1u;
+  auto give_up = [&]() {
+    if (lane == 0) {
+      fallback[blockIdx.x] = 1;
+      atomicAdd(&B.ctr[1], 1);
+    }
+  };
+  if (lane == 0) fallback[blockIdx.x] = 0;
+  if (__ldcg(&B.ctr[2])) {  // the ranking found something it does not understand: every cluster takes the literal replay
+    give_up();
+    return;
+  }
+  int cur = 0, cnt = 1, out = 1;
+  {
+    const int rpos = root_cellpos[c];
+    const int ry = rpos / w, rx = rpos - ry * w;
+    const int root = compact_index(mask, prefix, pitch, rx, ry);
+    if (lane == 0) {
+      q[0] = rpos;
+      B.vis[root] = 1;
+      s_items[0][0] = make_int4(root, -1, 0, 1);
+    }
+    __syncwarp();
+  }
+  const int sub = lane >> 3, k8 = lane & 7;
+  while (cnt > 0) {
+    // ---- how many levels can the whole list be fast-forwarded? ----
+    int f = 0x7fffffff;
+    for (int base = 0; base < cnt; base += 32) {
+      if (base + lane < cnt) {
+        const int4 it = s_items[cur][base + lane];
+        int fi = 0;
+        if (it.y >= 0) {
+          const int2 lh = __ldcg(B.lohi + it.y);
+          const int L = it.w >> 2, gap = lh.y - lh.x;
+          fi = L == 1 ? 0 : (lh.x > 0 && lh.y < L) ? gap >> 1 : gap;  // entered from both ends: the walkers share what is left
+        }
+        f = min(f, fi);
+      }
+    }
+    f = __reduce_min_sync(0xffffffffu, f);
+    if (f >= 1) {
+      if (out + (long long)f * cnt > n) break;  // cannot happen; the check after the loop reports it
+      const int total = f * cnt;
+      for (int idx = lane; idx < total; idx += 32) {
+        const int t = idx / cnt, i = idx - t * cnt;
+        const int4 it = s_items[cur][i];
+        const int dir = (it.w & 3) - 1;
+        q[out + idx] = cellpos[B.run_cells[it.y + it.z + dir * (t + 1)]];
+      }
+      __syncwarp();
+      for (int i = lane; i < cnt; i += 32) {
+        int4 it = s_items[cur][i];
+        const int dir = (it.w & 3) - 1;
+        it.z += dir * f;
+        it.x = B.run_cells[it.y + it.z];
+        if (dir > 0) __stcg(&B.lohi[it.y].x, it.z + 1);
+        else __stcg(&B.lohi[it.y].y, it.z);
+        s_items[cur][i] = it;
+      }
+      out += total;
+      __syncwarp();
+      continue;
+    }
+    // ---- one literal level: four cells per step, lanes 8 s .. 8 s + 7 test the neighbours of the s-th one ----
+    int ncnt = 0;
+    bool overflow = false;
+    for (int base = 0; base < cnt; base += 4) {
+      const bool valid = base + sub < cnt;
+      const int4 it = valid ? s_items[cur][base + sub] : make_int4(0, -1, 0, 0);
+      const int j = valid ? __ldg(B.nbr + 8 * (size_t)it.x + k8) : -1;
+      bool take = false;
+      int4 ci = make_int4(-1, 0, 0, 0);
+      if (j >= 0) {
+        ci = B.cinfo[j];
+        if (ci.x < 0) take = __ldcg(B.vis + j) == 0;
+        else {
+          const int2 lh = __ldcg(B.lohi + ci.x);
+          take = lh.x <= ci.y && ci.y < lh.y;
+        }
+      }
+      // a cell claimed by two lanes of this step goes to the lower lane: the cell popped earlier, as in the FIFO
+      const unsigned same = __match_any_sync(0xffffffffu, take ? j : -2 - lane);
+      take = take && (__ffs(same) - 1 == lane);
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (ncnt + __popc(m) > kItemCap || out + ncnt + __popc(m) > n) {
+        overflow = true;
+        break;
+      }
+      if (take) {
+        const int slot = ncnt + __popc(m & lt);
+        int dir = 0;
+        if (ci.x >= 0) {
+          // pushed by its predecessor in the run, or entered from outside at one of the run's ends
+          dir = it.y == ci.x ? (it.z == ci.y - 1 ? 1 : -1) : (ci.y == 0 ? 1 : -1);
+          if (dir > 0) __stcg(&B.lohi[ci.x].x, ci.y + 1);
+          else __stcg(&B.lohi[ci.x].y, ci.y);
+        } else {
+          B.vis[j] = 1;
+        }
+        s_items[cur ^ 1][slot] = make_int4(j, ci.x, ci.y, (ci.z << 2) | (dir + 1));
+        q[out + slot] = cellpos[j];
+      }
+      ncnt += __popc(m);
+      __syncwarp();
+    }
+    if (overflow) {
+      give_up();
+      return;
+    }
+    out += ncnt;
+    cnt = ncnt;
+    cur ^= 1;
+    __syncwarp();
+  }
+  if (out != n) {  // defensive: the literal replay recomputes the cluster
+    give_up();
+    return;
+  }
+  __syncwarp();
+  float cx, cy;
+  ordered_centre(q, n, w, lane, &cx, &cy);
+  if (lane == 0) {
+    centre_out[2 * c] = cx;
+    centre_out[2 * c + 1] = cy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------
 static inline int grid_for(size_t n, int threads, int cap_mult = 16) {
@@ -966,7 +1273,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   AOS_CUDA_OK(c, c->cl_table.reserve(sizeof(aos_cluster) * (size_t)nc + sizeof(RowOut) * (size_t)nc));
   aos_cluster *d_clusters = c->cl_table.as<aos_cluster>();
   RowOut *d_rows = reinterpret_cast<RowOut *>(d_clusters + nc);
-  cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, nullptr,
+  cluster_finalize_kernel<<<nc, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, nullptr, nullptr,
                                                      nullptr, nullptr, d_clusters, d_rows);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
@@ -989,13 +1296,88 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   if (s != AOS_OK) return s;
 
   c->mark("cc_finalize");
-  // ---- order-dependent clusters: replay the reference's BFS and finalise again --------------------
+  // ---- order-dependent clusters: the reference's BFS order, then finalise again ------------------------
   // needed when a float32 partial sum can round (sum >= 2^24) or an arg-max tie must be broken by BFS order
   std::vector<int> need;
+  unsigned max_need = 0;
   for (int i = 0; i < nc; ++i)
-    if (h_rows[i].flags & (kFlagNeedsOrder | kFlagTie)) need.push_back(i);
+    if (h_rows[i].flags & (kFlagNeedsOrder | kFlagTie)) {
+      need.push_back(i);
+      max_need = std::max(max_need, (unsigned)c->h_clusters[i].size);
+    }
+  if (!need.empty() && !getenv("AOS_LITERAL_BFS")) {
+    const size_t nn = (size_t)n, total_jobs = need.size();
+    // nbr int[8n] | state uint2[2n] | cinfo int4[n] | link int2[n] | lohi int2[n] | run_cells int[n] | headbase int[n] |
+    // flagged int[jobs] | fallback int[jobs] | ctr int[64] | vis u8[n]
+    const size_t jobs4 = (total_jobs + 3) & ~(size_t)3;
+    AOS_CUDA_OK(c, c->bfs_buf.reserve(nn * (32 + 16 + 16 + 8 + 8 + 4 + 4 + 1) + (2 * jobs4 + 64) * 4 + 16 * 12));
+    BfsBufs B;
+    char *p = c->bfs_buf.as<char>();
+    auto carve = [&p](size_t bytes) {
+      char *r = p;
+      p += (bytes + 15) & ~(size_t)15;
+      return r;
+    };
+    B.nbr = reinterpret_cast<int *>(carve(nn * 32));
+    B.state = reinterpret_cast<uint2 *>(carve(nn * 16));
+    B.cinfo = reinterpret_cast<int4 *>(carve(nn * 16));
+    B.link = reinterpret_cast<int2 *>(carve(nn * 8));
+    B.lohi = reinterpret_cast<int2 *>(carve(nn * 8));
+    B.run_cells = reinterpret_cast<int *>(carve(nn * 4));
+    B.headbase = reinterpret_cast<int *>(carve(nn * 4));
+    int *d_flagged = reinterpret_cast<int *>(carve(jobs4 * 4));
+    int *d_fallback = reinterpret_cast<int *>(carve(jobs4 * 4));
+    B.ctr = reinterpret_cast<int *>(carve(64 * 4));
+    B.vis = reinterpret_cast<unsigned char *>(carve(nn));
+    if (!c->pin_a.resize(sizeof(int) * jobs4)) {  // pin_a is free again: h_clusters holds its copy
+      set_error(c, "cudaHostAlloc failed (replay jobs)");
+      return AOS_ERR_CUDA;
+    }
+    // longest first: CTAs are dispatched in index order
+    std::sort(need.begin(), need.end(), [&](int a, int b) {
+      return c->h_clusters[a].size != c->h_clusters[b].size ? c->h_clusters[a].size > c->h_clusters[b].size : a < b;
+    });
+    memcpy(c->pin_a.data(), need.data(), sizeof(int) * total_jobs);
+    s = h2d_small(c, d_flagged, c->pin_a.data(), sizeof(int) * jobs4, true);
+    if (s != AOS_OK) return s;
+    AOS_CUDA_OK(c, cudaMemsetAsync(B.ctr, 0, 64 * 4 + nn, st));  // counters and the visited bytes behind them
+    const int gb = grid_for(nn, 256);
+    bfs_prepare_kernel<<<gb, 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, cellpos, cell_cluster, root_cellpos, d_rows, n, B);
+    bfs_link_init_kernel<<<gb, 256, 0, st>>>(n, B);
+    c->launches += 2;
+    int rounds = 1;
+    while ((1u << rounds) < max_need && rounds < 31) ++rounds;  // a run is shorter than its cluster
+    ++rounds;  // the last round finds nothing to change
+    if (rounds > 56) rounds = 56;
+    for (int r = 0; r < rounds; ++r) bfs_jump_kernel<<<grid_for(2 * nn, 256), 256, 0, st>>>(n, B, r);
+    bfs_runs_kernel<<<gb, 256, 0, st>>>(n, B);
+    bfs_scatter_kernel<<<gb, 256, 0, st>>>(n, B);
+    c->launches += rounds + 2;
+    AOS_CUDA_OK(c, cudaGetLastError());
+    c->mark("replay_prep");
+    bfs_chain_kernel<<<(unsigned)total_jobs, 32, 0, st>>>(d_flagged, acc, offsets, root_cellpos, mask, prefix, P.pitch, P.w, cellpos, B,
+                                                         d_fallback, queue, centre);
+    ++c->launches;
+    AOS_CUDA_OK(c, cudaGetLastError());
+    c->mark("replay_bfs");
+    cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, d_flagged,
+                                                                         d_fallback, queue, centre, d_clusters, d_rows);
+    ++c->launches;
+    AOS_CUDA_OK(c, cudaGetLastError());
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, B.ctr, 16, cudaMemcpyDeviceToHost, st));
+    s = fetch_tables();  // one synchronisation for the tables and the fallback counter
+    if (s != AOS_OK) return s;
+    c->bfs_fallbacks = c->h_flag[1];
+    if (getenv("AOS_DEBUG"))
+      fprintf(stderr, "[aos] BFS order: %zu clusters (longest %u cells), %d jump rounds, %d run slots, %d left to the literal replay%s\n",
+              total_jobs, max_need, rounds, c->h_flag[0], c->h_flag[1], c->h_flag[2] ? " (ranking broken)" : "");
+    // clusters the warp gave up on (a level wider than its list) kept their flags: the literal replay below takes them
+    need.clear();
+    if (c->h_flag[1] > 0)
+      for (int i = 0; i < nc; ++i)
+        if (h_rows[i].flags & (kFlagNeedsOrder | kFlagTie)) need.push_back(i);
+  }
   if (!need.empty()) {
-    // bounding boxes come from the directional extremes already on the host-side? no: take them from acc
     if (!c->pin_c.resize(sizeof(ClusterAcc) * (size_t)nc)) {
       set_error(c, "cudaHostAlloc failed (cluster accumulators)");
       return AOS_ERR_CUDA;
@@ -1037,8 +1419,8 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
       size_t mx[4] = {0, 0, 0, 0};
       for (int k = 0; k < 4; ++k)
         for (const ReplayJob &j : jobs[k]) mx[k] = std::max(mx[k], (size_t)h_acc[j.cluster].size);
-      fprintf(stderr, "[aos] replay classes: %zu/%zu/%zu/%zu jobs, max cells %zu/%zu/%zu/%zu\n", jobs[0].size(), jobs[1].size(),
-              jobs[2].size(), jobs[3].size(), mx[0], mx[1], mx[2], mx[3]);
+      fprintf(stderr, "[aos] literal replay classes: %zu/%zu/%zu/%zu jobs, max cells %zu/%zu/%zu/%zu\n", jobs[0].size(),
+              jobs[1].size(), jobs[2].size(), jobs[3].size(), mx[0], mx[1], mx[2], mx[3]);
     }
     AOS_CUDA_OK(c, c->cl_stats.reserve((sizeof(ReplayJob) + 2 * sizeof(int)) * total_jobs));
     ReplayJob *d_jobs = c->cl_stats.as<ReplayJob>();
@@ -1065,7 +1447,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     if (s != AOS_OK) return s;
     uint32_t *gvisited = prefix;  // compact indices are no longer needed: reuse as the global "unvisited" bitmap
     AOS_CUDA_OK(c, cudaMemcpyAsync(gvisited, mask, words * 4, cudaMemcpyDeviceToDevice, st));
-    c->mark("replay_prep");
+    c->mark("literal_replay_prep");
     // the size classes are independent launches: class 0 stays on the context stream, the others fork onto side
     // streams so that a few very long rows do not serialise behind the many short ones
     AOS_CUDA_OK(c, cudaEventRecord(c->ev_fork, st));
@@ -1098,10 +1480,10 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
                                                                            gvisited, d_fallback, queue, centre);
     ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
-    c->mark("replay_bfs");
+    c->mark("literal_replay_bfs");
     cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length,
-                                                                         d_flagged, queue, centre, d_clusters, d_rows);
-  ++c->launches;
+                                                                         d_flagged, nullptr, queue, centre, d_clusters, d_rows);
+    ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
     s = fetch_tables();  // after the replay kernels consumed the job list: the copy engine has read pin_a by now
     if (s != AOS_OK) return s;
