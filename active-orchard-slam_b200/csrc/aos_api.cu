@@ -186,7 +186,7 @@ void aos_destroy(aos_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->g_raw, &c->g_infl, &c->g_occ, &c->g_open, &c->g_skel, &c->g_framed, &c->g_scratch,
                     &c->points_stage, &c->misc, &c->cc_mask, &c->cc_prefix, &c->cc_blocksum, &c->cc_parent,
-                    &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf, &c->bfs_buf,
+                    &c->cc_cellpos, &c->cc_rootrank, &c->cl_stats, &c->cl_table, &c->cl_aux, &c->cand_buf, &c->bfs_buf, &c->ray_table, &c->corner_fb,
                     &c->gvd_buf, &c->gvd_buf2, &c->gvd_buf3, &c->gvd_skel, &c->seed_buf, &c->seed_buf2, &c->edt_buf, &c->edt_out, &c->ror_buf, &c->ror_out};
   for (DevBuf *b : bufs) b->release();
   for (int s = 0; s < 2; ++s)

@@ -366,6 +366,7 @@ struct Ctx {
   DevBuf cl_table;   // aos_cluster[n_clusters]
   DevBuf cl_aux;     // per-cluster extreme points, candidate lists ...
   DevBuf cand_buf;
+  DevBuf corner_fb;       // k_graph.cu: corners left to corner_far_kernel
   DevBuf bfs_buf;         // chain-compressed BFS order (k_cluster.cu, BfsBufs)
   int bfs_fallbacks = 0;  // clusters of the last map that took the literal replay instead
   int n_skel_cells = 0;
@@ -402,6 +403,9 @@ struct Ctx {
   PinVec<double> h_seeds;
   int seed_counts[3] = {0, 0, 0};     // virtual, ray, endpoint
   std::vector<double> h_rows_info;    // /exploration_tree_rows_info: start x,y,end x,y per row, sorted
+  std::vector<double> ray_steps;      // k_seeds.cu: castRayFromEndpoint's accumulated ray parameter, step by step
+  DevBuf ray_table;                   // ... its device copy (ray_steps_dev entries)
+  size_t ray_steps_dev = 0;
 };
 
 }  // namespace aos

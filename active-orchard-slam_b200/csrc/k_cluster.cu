@@ -144,26 +144,51 @@ __device__ __forceinline__ float cell_world(double origin, int idx, float res) {
   return (float)(origin + (double)__fmul_rn((float)idx, res));
 }
 
-__global__ void mask_count_kernel(const __grid_constant__ SeedDeviceParams P, const uint32_t *__restrict__ skel,
-                                  uint32_t *__restrict__ mask, uint32_t *__restrict__ counts) {
-  size_t total = (size_t)P.pitch * P.h;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    uint32_t v = skel[i];
-    if (v && P.n_poly > 0) {  // use_polygon_filter (seed_gen:979-982)
-      int y = (int)(i / (size_t)P.pitch), cw = (int)(i - (size_t)y * P.pitch);
-      float wy = cell_world(P.oy, y, P.res);
-      uint32_t keep = 0, rem = v;
-      while (rem) {
-        int b = __ffs(rem) - 1;
-        rem &= rem - 1;
-        float wx = cell_world(P.ox, (cw << 5) + b, P.res);
-        if (point_in_polygon(P, (double)wx, (double)wy)) keep |= 1u << b;
+// The polygon test (seed_gen:979-982) runs only on set bits, and set bits are rare (a skeleton): a warp pools the set bits
+// of its 32 words and tests them one per lane, instead of every lane walking its own word's bits while the others wait.
+__global__ void __launch_bounds__(256) mask_count_kernel(const __grid_constant__ SeedDeviceParams P,
+                                                         const uint32_t *__restrict__ skel, uint32_t *__restrict__ mask,
+                                                         uint32_t *__restrict__ counts) {
+  __shared__ uint32_t s_keep[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t total = (size_t)P.pitch * P.h;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x + warp * 32; base < total; base += stride) {
+    const size_t i = base + lane;
+    uint32_t v = i < total ? skel[i] : 0u;
+    if (P.n_poly > 0 && __any_sync(0xffffffffu, v != 0u)) {  // use_polygon_filter
+      const uint32_t cnt = __popc(v);
+      const uint32_t incl = warp_incl_scan(cnt, lane);
+      const uint32_t all = __shfl_sync(0xffffffffu, incl, 31);
+      s_keep[warp][lane] = 0u;
+      __syncwarp();
+      for (uint32_t t0 = 0; t0 < all; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        // owner = first lane whose inclusive count exceeds t
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const uint32_t probe = __shfl_sync(0xffffffffu, incl, (owner + step - 1) & 31);
+          if (owner + step <= 31 && probe <= t) owner += step;
+        }
+        const uint32_t ov = __shfl_sync(0xffffffffu, v, owner), oincl = __shfl_sync(0xffffffffu, incl, owner);
+        if (t < all) {
+          const uint32_t nth = t - (oincl - __popc(ov));  // 0-based rank of the bit inside the owner's word
+          const int b = __fns(ov, 0, (int)nth + 1);
+          const size_t wi = base + owner;
+          const int y = (int)(wi / (size_t)P.pitch), cw = (int)(wi - (size_t)y * P.pitch);
+          const float wy = cell_world(P.oy, y, P.res), wx = cell_world(P.ox, (cw << 5) + b, P.res);
+          if (point_in_polygon(P, (double)wx, (double)wy)) atomicOr(&s_keep[warp][owner], 1u << b);
+        }
       }
-      v = keep;
+      __syncwarp();
+      v = s_keep[warp][lane];
+      __syncwarp();
     }
-    mask[i] = v;
-    counts[i] = __popc(v);
+    if (i < total) {
+      mask[i] = v;
+      counts[i] = __popc(v);
+    }
   }
 }
 
@@ -232,37 +257,29 @@ __device__ __forceinline__ int compact_index(const uint32_t *mask, const uint32_
   return (int)prefix[wi] + __popc(m & (bit - 1u));
 }
 
-__global__ void cc_link_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix, int pitch, int h,
-                               int w, int *parent) {
-  size_t total = (size_t)pitch * h;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    uint32_t v = mask[i];
-    if (!v) continue;
-    int y = (int)(i / (size_t)pitch), cw = (int)(i - (size_t)y * pitch);
-    int idx = (int)prefix[i];
-    while (v) {
-      int b = __ffs(v) - 1;
-      v &= v - 1;
-      int x = (cw << 5) + b;
-      // raster-earlier half of the 8-neighbourhood: W, NW, N, NE  (N = row y-1)
+// one thread per skeleton cell (dense: every lane has a cell), hooking it to the raster-earlier half of its neighbourhood
+__global__ void cc_link_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix, int pitch, int w,
+                               const int *__restrict__ cellpos, int n, int *parent) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int pos = cellpos[idx];
+    const int y = pos / w, x = pos - y * w;
+    // W, NW, N, NE  (N = row y-1)
+    if (x > 0) {
+      // the west neighbour is the previous compact index when its bit is set
+      const uint32_t m = mask[(size_t)y * pitch + ((x - 1) >> 5)];
+      if ((m >> ((x - 1) & 31)) & 1u) uf_union(parent, idx, idx - 1);
+    }
+    if (y > 0) {
       if (x > 0) {
-        int n = compact_index(mask, prefix, pitch, x - 1, y);
+        int n = compact_index(mask, prefix, pitch, x - 1, y - 1);
         if (n >= 0) uf_union(parent, idx, n);
       }
-      if (y > 0) {
-        if (x > 0) {
-          int n = compact_index(mask, prefix, pitch, x - 1, y - 1);
-          if (n >= 0) uf_union(parent, idx, n);
-        }
-        int n = compact_index(mask, prefix, pitch, x, y - 1);
+      int n = compact_index(mask, prefix, pitch, x, y - 1);
+      if (n >= 0) uf_union(parent, idx, n);
+      if (x + 1 < w) {
+        n = compact_index(mask, prefix, pitch, x + 1, y - 1);
         if (n >= 0) uf_union(parent, idx, n);
-        if (x + 1 < w) {
-          n = compact_index(mask, prefix, pitch, x + 1, y - 1);
-          if (n >= 0) uf_union(parent, idx, n);
-        }
       }
-      ++idx;
     }
   }
 }
@@ -1220,7 +1237,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   uint32_t *rootrank = c->cc_rootrank.as<uint32_t>();
   cc_init_kernel<<<grid_for(words, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, parent, cellpos);
   ++c->launches;
-  cc_link_kernel<<<grid_for(words, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, parent);
+  cc_link_kernel<<<grid_for(n, 256), 256, 0, st>>>(mask, prefix, P.pitch, P.w, cellpos, n, parent);
   ++c->launches;
   cc_flatten_kernel<<<grid_for(n, 256), 256, 0, st>>>(parent, rootrank, n);
   ++c->launches;

@@ -533,44 +533,61 @@ __device__ __forceinline__ void warp_argmin(double &d, int &i) {
 // The radius ladder 5, 7, 9, 2*diagonal (gvd:716-722) returns the nearest admissible node of the first
 // non-empty rung, which is the nearest admissible node overall: searched here as a 9 m block of 0.5 m cells
 // first and the whole node array if that block has none.
+struct CornerJob {
+  double2 endpoint, other;
+  double outx, outy, perpx, perpy, angle;
+  bool neg, pos;
+};
+
+__device__ __forceinline__ CornerJob corner_job(const double *__restrict__ rows, int job) {
+  const int r = job >> 2, k = job & 3;
+  double2 s = make_double2(rows[4 * r], rows[4 * r + 1]), e = make_double2(rows[4 * r + 2], rows[4 * r + 3]);
+  if (s.x > e.x) {  // gvd:140-145
+    double2 t = s;
+    s = e;
+    e = t;
+  }
+  CornerJob J;
+  J.endpoint = k < 2 ? s : e;
+  J.other = k < 2 ? e : s;
+  J.angle = (k & 1) ? 90.0 : -90.0;  // TL -90, TR +90, BL -90, BR +90
+  double mx = J.other.x - J.endpoint.x, my = J.other.y - J.endpoint.y;
+  if (sqrt(mx * mx + my * my) < 1e-6) {
+    mx = 1.0;
+    my = 0.0;
+  } else {
+    normalize2(mx, my);
+  }
+  J.outx = -mx, J.outy = -my, J.perpx = -my, J.perpy = mx;
+  J.neg = fabs(J.angle - (-90.0)) < 1e-6;
+  J.pos = fabs(J.angle - 90.0) < 1e-6;
+  return J;
+}
+
+// fb[0] counts the corners without an admissible node within 9 m, fb[1 ...] lists them: corner_far_kernel finishes those
+// (a whole-array scan by one warp took as long as all other corners together)
 __global__ void corner_kernel(const double *__restrict__ rows, CornerParams P, const double2 *__restrict__ nodes, PointGrid g,
-                              double *__restrict__ corners) {
+                              double *__restrict__ corners, int *__restrict__ fb) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const double min_distance = 0.5;
   const double last_radius = sqrt(P.gw * P.gw + P.gh * P.gh) * 2.0;
   for (int job = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; job < 4 * P.n_rows; job += warps) {
     const int r = job >> 2, k = job & 3;
-    double2 s = make_double2(rows[4 * r], rows[4 * r + 1]), e = make_double2(rows[4 * r + 2], rows[4 * r + 3]);
-    if (s.x > e.x) {  // gvd:140-145
-      double2 t = s;
-      s = e;
-      e = t;
-    }
-    const double2 endpoint = k < 2 ? s : e, other = k < 2 ? e : s;
-    const double angle = (k & 1) ? 90.0 : -90.0;  // TL -90, TR +90, BL -90, BR +90
-    double mx = other.x - endpoint.x, my = other.y - endpoint.y;
-    if (sqrt(mx * mx + my * my) < 1e-6) {
-      mx = 1.0;
-      my = 0.0;
-    } else {
-      normalize2(mx, my);
-    }
-    const double outx = -mx, outy = -my, perpx = -my, perpy = mx;
-    const bool neg = fabs(angle - (-90.0)) < 1e-6, pos = fabs(angle - 90.0) < 1e-6;
+    const CornerJob J = corner_job(rows, job);
     double best = DBL_MAX;
     int best_i = -1;
     // block of cells covering radius 9 m around the endpoint
     {
       const double R = 9.0;  // rungs 5, 7, 9 apply even on grids whose diagonal is shorter
-      const long long cx0 = cell_coord(endpoint.x - R, g.inv), cx1 = cell_coord(endpoint.x + R, g.inv);
-      const long long cy0 = cell_coord(endpoint.y - R, g.inv), cy1 = cell_coord(endpoint.y + R, g.inv);
+      const long long cx0 = cell_coord(J.endpoint.x - R, g.inv), cx1 = cell_coord(J.endpoint.x + R, g.inv);
+      const long long cy0 = cell_coord(J.endpoint.y - R, g.inv), cy1 = cell_coord(J.endpoint.y + R, g.inv);
       const long long nx = cx1 - cx0 + 1, total = nx * (cy1 - cy0 + 1);
       for (long long c = lane; c < total; c += 32) {
         int slot = hash_find(g.h, cell_key(cx0 + c % nx, cy0 + c / nx));
         if (slot < 0) continue;
         for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
-          double d = corner_candidate(nodes[u], endpoint, outx, outy, perpx, perpy, neg, pos, min_distance, R);
+          double d = corner_candidate(nodes[u], J.endpoint, J.outx, J.outy, J.perpx, J.perpy, J.neg, J.pos, min_distance, R);
           if (d >= 0.0 && (d < best || (d == best && u < best_i))) {
             best = d;
             best_i = u;
@@ -579,20 +596,56 @@ __global__ void corner_kernel(const double *__restrict__ rows, CornerParams P, c
       }
       warp_argmin(best, best_i);
     }
-    if (best_i < 0 && last_radius > 9.0) {
-      for (int u = lane; u < P.n_nodes; u += 32) {
-        double d = corner_candidate(nodes[u], endpoint, outx, outy, perpx, perpy, neg, pos, min_distance, last_radius);
-        if (d >= 0.0 && (d < best || (d == best && u < best_i))) {
-          best = d;
-          best_i = u;
-        }
-      }
-      warp_argmin(best, best_i);
+    if (lane != 0) continue;
+    if (best_i < 0 && last_radius > 9.0) {  // last rung of the ladder (2 x diagonal): all nodes, by a whole CTA
+      fb[1 + atomicAdd(fb, 1)] = job;
+      continue;
     }
+    double2 c = best_i >= 0 ? nodes[best_i] : cast_ray_dev(P, J.endpoint, J.other, J.angle, min_distance);
+    corners[8 * (size_t)r + 2 * k] = c.x;
+    corners[8 * (size_t)r + 2 * k + 1] = c.y;
+  }
+}
+
+constexpr int kFarThreads = 1024;
+__global__ void __launch_bounds__(kFarThreads) corner_far_kernel(const double *__restrict__ rows, CornerParams P,
+                                                                 const double2 *__restrict__ nodes, double *__restrict__ corners,
+                                                                 const int *__restrict__ fb) {
+  __shared__ double s_d[kFarThreads / 32];
+  __shared__ int s_i[kFarThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double min_distance = 0.5;
+  const double last_radius = sqrt(P.gw * P.gw + P.gh * P.gh) * 2.0;
+  const int n_jobs = fb[0];
+  for (int q = blockIdx.x; q < n_jobs; q += gridDim.x) {
+    const int job = fb[1 + q];
+    const int r = job >> 2, k = job & 3;
+    const CornerJob J = corner_job(rows, job);
+    double best = DBL_MAX;
+    int best_i = -1;
+    for (int u = threadIdx.x; u < P.n_nodes; u += kFarThreads) {
+      double d = corner_candidate(nodes[u], J.endpoint, J.outx, J.outy, J.perpx, J.perpy, J.neg, J.pos, min_distance, last_radius);
+      if (d >= 0.0 && (d < best || (d == best && u < best_i))) {
+        best = d;
+        best_i = u;
+      }
+    }
+    warp_argmin(best, best_i);
+    __syncthreads();  // the previous job's readers are done with the scratch
     if (lane == 0) {
-      double2 c = best_i >= 0 ? nodes[best_i] : cast_ray_dev(P, endpoint, other, angle, min_distance);
-      corners[8 * (size_t)r + 2 * k] = c.x;
-      corners[8 * (size_t)r + 2 * k + 1] = c.y;
+      s_d[warp] = best;
+      s_i[warp] = best_i;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      best = s_d[lane];
+      best_i = s_i[lane];
+      warp_argmin(best, best_i);
+      if (lane == 0) {
+        double2 c = best_i >= 0 ? nodes[best_i] : cast_ray_dev(P, J.endpoint, J.other, J.angle, min_distance);
+        corners[8 * (size_t)r + 2 * k] = c.x;
+        corners[8 * (size_t)r + 2 * k + 1] = c.y;
+      }
     }
   }
 }
@@ -949,8 +1002,12 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
     CP.gh = gh;
     CP.n_rows = n_rows;
     CP.n_nodes = N;
-    corner_kernel<<<blocks_for((size_t)n_rows * 4 * 32), 256, 0, st>>>(d_rows, CP, d_cnodes, gn, d_corners);
-  ++c->launches;
+    AOS_CUDA_OK(c, c->corner_fb.reserve(sizeof(int) * (4 * (size_t)n_rows + 4)));
+    int *d_fb = c->corner_fb.as<int>();
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_fb, 0, sizeof(int), st));
+    corner_kernel<<<blocks_for((size_t)n_rows * 4 * 32), 256, 0, st>>>(d_rows, CP, d_cnodes, gn, d_corners, d_fb);
+    corner_far_kernel<<<std::min(4 * n_rows, 4 * kNumSMs), kFarThreads, 0, st>>>(d_rows, CP, d_cnodes, d_corners, d_fb);
+    c->launches += 2;
     label_scatter_kernel<0><<<blocks_for((size_t)n_rows * 4), 256, 0, st>>>(d_corners, n_rows, d_cnodes, gn, d_loff, nullptr,
                                                                            nullptr, nullptr);
   ++c->launches;

@@ -12,6 +12,8 @@
 
 #include <algorithm>
 
+#include <float.h>
+
 #include "aos_common.cuh"
 #include "dev_hash.cuh"
 
@@ -66,7 +68,9 @@ __device__ bool raycast_to_occupied_dev(const SeedGrid &g, double sx, double sy,
     cx += dx * step;
     cy += dy * step;
     double ex = cx - sx, ey = cy - sy;
-    if (sqrt(ex * ex + ey * ey) < 1.0) continue;
+    // the reference tests sqrt(z) < 1.0; a correctly rounded square root is below 1 exactly when z is (the largest
+    // double below 1 has a root below the midpoint to 1), so the root itself is not needed
+    if (ex * ex + ey * ey < 1.0) continue;
     int gx, gy;
     world_to_grid_dev(g, (float)cx, (float)cy, &gx, &gy);
     if (sg_occ(g, gx, gy)) {
@@ -94,11 +98,13 @@ struct RayConsts {
 
 // castRayFromEndpoint, seed_gen:1774-1891, one WARP per ray.  The reference advances `cur += 0.1` step by step
 // (a sequential floating-point accumulation) until the sample leaves the grid or lands on a skeleton cell; rays
-// along a row can run for 10^4 steps.  Every lane replays 32 of those additions (bit-identical values of `cur`),
-// keeps the one of its own step, evaluates that step, and the first lane whose step terminates the loop wins.
+// along a row can run for 10^4 steps.  Every ray starts at min_distance = 1.0, so the accumulated values are the same
+// sequence for all of them: T[k] = 1.0 + 0.1 + ... (k additions, rounded one by one), built once on the host
+// (ray_steps_table) and shared by every ray of every map.  Lane l evaluates step 32 i + l; the first lane whose step
+// terminates the loop wins.  Entries past the table are above abs_max by construction.
 __device__ double2 cast_ray_from_endpoint_warp(const SeedGrid &g, const RayConsts &K, double spx, double spy, double opx,
-                                               double opy, int ang /* 0: 0 deg, 1: -90, 2: +90 */, double min_distance,
-                                               int lane) {
+                                               double opy, int ang /* 0: 0 deg, 1: -90, 2: +90 */,
+                                               const double *__restrict__ T, int nT, int lane) {
   double ex = opx - spx, ey = opy - spy;
   if (sqrt(ex * ex + ey * ey) < 1e-6) {
     ex = 1.0;
@@ -119,14 +125,8 @@ __device__ double2 cast_ray_from_endpoint_warp(const SeedGrid &g, const RayConst
   const double minx = g.ox, maxx = g.ox + K.gw, miny = g.oy, maxy = g.oy + K.gh;
   const double resolution = (double)g.res;
   const double abs_max = sqrt(K.gw * K.gw + K.gh * K.gh) * 3.0;
-  double cur = min_distance;
-  for (;;) {
-    double c = cur, mine = cur;
-#pragma unroll 1
-    for (int j = 1; j < 32; ++j) {
-      c += 0.1;
-      if (j == lane) mine = c;
-    }
+  for (int k = lane;; k += 32) {
+    const double mine = k < nT ? T[k] : DBL_MAX;
     // status of this lane's step: 0 continue, 1 left the grid, 2 hit a cell, 3 past abs_max (loop condition fails)
     int status = 0;
     double px = 0.0, py = 0.0;
@@ -152,7 +152,6 @@ __device__ double2 cast_ray_from_endpoint_warp(const SeedGrid &g, const RayConst
       if (st == 2) return make_double2(px, py);
       break;
     }
-    cur = c + 0.1;
   }
   double fx = spx + rdx * abs_max, fy = spy + rdy * abs_max;
   if (!(fx >= minx && fx <= maxx && fy >= miny && fy <= maxy)) {
@@ -222,7 +221,8 @@ __global__ void vs_generate_kernel(const __grid_constant__ SeedDeviceParams P, S
 
 // ---- generateRayPointsFromEndpoints + endpoint seeds ---------------------------------------------------------
 __global__ void ray_points_kernel(const __grid_constant__ SeedDeviceParams P, SeedGrid g, RayConsts K,
-                                  const RowDev *__restrict__ rows, int n_rows, double2 *__restrict__ ray_pts,
+                                  const RowDev *__restrict__ rows, int n_rows, const double *__restrict__ T, int nT,
+                                  double2 *__restrict__ ray_pts,
                                   unsigned char *__restrict__ ray_state, double2 *__restrict__ end_pts,
                                   unsigned char *__restrict__ end_state) {
   const int lane = threadIdx.x & 31;
@@ -232,7 +232,7 @@ __global__ void ray_points_kernel(const __grid_constant__ SeedDeviceParams P, Se
     const RowDev R = rows[r];
     const bool from_start = k < 3;
     const double2 p = cast_ray_from_endpoint_warp(g, K, from_start ? R.sx : R.ex, from_start ? R.sy : R.ey,
-                                                  from_start ? R.ex : R.sx, from_start ? R.ey : R.sy, k % 3, 1.0, lane);
+                                                  from_start ? R.ex : R.sx, from_start ? R.ey : R.sy, k % 3, T, nT, lane);
     if (lane != 0) continue;
     const double minx = g.ox, maxx = g.ox + K.gw, miny = g.oy, maxy = g.oy + K.gh;
     bool valid = isfinite(p.x) && isfinite(p.y) && (p.x >= minx && p.x <= maxx && p.y >= miny && p.y <= maxy);
@@ -514,7 +514,27 @@ aos_status device_select_seeds(Ctx *c) {
     vs_generate_kernel<<<blocks_for(n_virt, 128), 128, 0, st>>>(P, sg, d_rows, n_rows, d_offs, n_virt, d_vpts, d_vst);
     ++c->launches;
   }
-  ray_points_kernel<<<blocks_for((size_t)n_ray * 32, 128), 128, 0, st>>>(P, sg, K, d_rows, n_rows, d_rpts, d_rst, d_epts, d_est);
+  // the accumulated ray parameter 1.0 + 0.1 + 0.1 + ... of castRayFromEndpoint (seed_gen:1840-1880), one addition at a time
+  // as the reference performs them; the same for every ray, so it is built once and only ever extended
+  {
+    const double abs_max = sqrt(K.gw * K.gw + K.gh * K.gh) * 3.0;
+    if (!(abs_max < 1e7)) {
+      set_error(c, "grid too large for the ray step table");
+      return AOS_ERR_CAPACITY;
+    }
+    std::vector<double> &T = c->ray_steps;
+    if (T.empty()) T.push_back(1.0);
+    const size_t before = T.size();
+    while (T.back() <= abs_max) T.push_back(T.back() + 0.1);
+    if (T.size() != before || c->ray_steps_dev != T.size()) {
+      AOS_CUDA_OK(c, c->ray_table.reserve(sizeof(double) * T.size()));
+      AOS_CUDA_OK(c, cudaMemcpyAsync(c->ray_table.as<double>(), T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, st));
+      AOS_CUDA_OK(c, cudaStreamSynchronize(st));  // pageable source: once per context (and per larger grid)
+      c->ray_steps_dev = T.size();
+    }
+  }
+  ray_points_kernel<<<blocks_for((size_t)n_ray * 32, 128), 128, 0, st>>>(P, sg, K, d_rows, n_rows, c->ray_table.as<double>(),
+                                                                         (int)c->ray_steps_dev, d_rpts, d_rst, d_epts, d_est);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
 
