@@ -907,18 +907,29 @@ __global__ void __launch_bounds__(32) bfs_replay_kernel(const __grid_constant__ 
 // is not flagged: of a run only the prefix [0, lo) and the suffix [hi, L) can have been visited.
 // scripts/dev/chain_bfs_proto.py is the same algorithm in Python, checked against the plain FIFO on random images.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kItemCap = 64;  // cells of one BFS level the warp keeps in shared memory; wider levels -> fallback kernel
+constexpr int kItemCap = 64;   // cells of one BFS level the warp keeps in shared memory; wider levels -> fallback kernel
+constexpr int kRunHdr = 8;     // ints in front of a run's cells: lo, hi, L, out0, out1 (irregular-table slots beyond either end)
+constexpr unsigned kDone = 0x80000000u;
+
+struct IrrRec {    // one per irregular cell of a flagged cluster (junctions, corners, ends, blobs, the root): 80 bytes
+  int2 nb[8];      // neighbour k in the reference's order: (run base, position) of a chain cell, (-1 - slot, 0) of an
+                   // irregular one, (INT_MIN, 0) = none.  While the table is being built nb[k].x is the compact index.
+  int cellpos;
+  int vis;
+  int pad[2];
+};
 
 struct BfsBufs {
-  int *nbr;                // 8 per cell: compact index of the neighbour in the reference's order, -1 = none
-  int2 *link;              // chain cell: its two neighbours (in that order); (-1,-1) irregular; (-2,-2) cluster not flagged
-  uint2 *state;            // 2 per cell (one per link): x = state index of the farthest known chain cell that way, y = steps
-  int4 *cinfo;             // x = first slot of the cell's run in run_cells (-1: irregular), y = position, z = run length
-  int *run_cells;          // the runs as arrays of compact cell indices
-  int2 *lohi;              // per run (at its first slot): positions [lo, hi) are not visited yet
-  int *headbase;           // per head cell: first slot of its run
-  unsigned char *vis;      // irregular cells: visited
-  int *ctr;                // [0] run slots handed out, [1] clusters left to the fallback, [2] broken ranking, [4 + r] round r changed
+  int2 *link;      // chain cell: its two neighbours (compact indices, reference order); irregular: (-1, slot in irr);
+                   // cell of a cluster that needs no order: (-2, -2)
+  uint2 *state;    // 2 per cell (one per link), pointer jumping: x = entry index of the farthest known chain cell that way,
+                   // y = steps | kDone once x is the end of the run
+  int4 *cinfo;     // ALIASES state (same 16 bytes per cell) once the runs are ranked: x = run base, y = position, z = L
+  int *runs;       // per run: kRunHdr header ints, then cellpos of its cells in run order
+  IrrRec *irr;
+  int *ctr;        // [0] ints of `runs` handed out, [1] clusters left to the fallback, [2] ranking broken / out of space,
+                   // [3] irregular cells, [4 + r] round r changed something
+  int run_cap, irr_cap;
 };
 
 __global__ void bfs_prepare_kernel(const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix, int pitch, int h, int w,
@@ -947,82 +958,151 @@ __global__ void bfs_prepare_kernel(const uint32_t *__restrict__ mask, const uint
         ++deg;
       }
     }
-    int4 *dst = reinterpret_cast<int4 *>(B.nbr + 8 * (size_t)i);
-    dst[0] = make_int4(ids[0], ids[1], ids[2], ids[3]);
-    dst[1] = make_int4(ids[4], ids[5], ids[6], ids[7]);
     // a chain cell: two neighbours that are not neighbours of each other; the root starts the FIFO and stays irregular
     const bool apart = abs(k0 / 3 - k1 / 3) > 1 || abs(k0 % 3 - k1 % 3) > 1;
-    const bool chain = deg == 2 && apart && pos != root_cellpos[c];
-    B.link[i] = chain ? make_int2(n0, n1) : make_int2(-1, -1);
-    B.cinfo[i] = make_int4(-1, 0, 0, 0);
+    if (deg == 2 && apart && pos != root_cellpos[c]) {
+      B.link[i] = make_int2(n0, n1);
+      continue;
+    }
+    const int slot = atomicAdd(&B.ctr[3], 1);
+    if (slot >= B.irr_cap) {
+      B.ctr[2] = 1;
+      B.link[i] = make_int2(-1, 0);
+      continue;
+    }
+    B.link[i] = make_int2(-1, slot);
+    IrrRec *r = B.irr + slot;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r->nb[k] = make_int2(ids[k], 0);
+    r->cellpos = pos;
+    r->vis = 0;
   }
 }
 
 __global__ void bfs_link_init_kernel(int n, BfsBufs B) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int2 l = B.link[i];
-    if (l.x < 0) continue;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int t = s ? l.y : l.x;
-      const int2 lt = B.link[t];
-      // the neighbour continues the run through its OTHER link; an irregular neighbour ends the run at this cell
-      B.state[2 * (size_t)i + s] = lt.x >= 0 ? make_uint2(2u * (unsigned)t + (lt.x == i ? 1u : 0u), 1u) : make_uint2(2u * (unsigned)i + s, 0u);
+      uint2 st = make_uint2(2u * (unsigned)i + s, kDone);  // not a chain cell: nothing to jump
+      if (l.x >= 0) {
+        const int t = s ? l.y : l.x;
+        const int2 lt = B.link[t];
+        // the neighbour continues the run through its OTHER link; an irregular neighbour ends the run at this cell
+        if (lt.x >= 0) st = make_uint2(2u * (unsigned)t + (lt.x == i ? 1u : 0u), 1u);
+      }
+      B.state[2 * (size_t)i + s] = st;
     }
   }
 }
 
 // One round of pointer jumping, in place: an entry that reads its target before or after the target's own update composes
-// two true statements either way (8-byte entries are loaded and stored whole).
+// two true statements either way (8-byte entries are loaded and stored whole).  Finished entries cost one 8-byte read.
 __global__ void bfs_jump_kernel(int n, BfsBufs B, int round) {
   if (round > 0 && B.ctr[4 + round - 1] == 0) return;  // the previous round changed nothing
-  bool changed = false;
+  bool unfinished = false;
   const unsigned total = 2u * (unsigned)n;
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    if (B.link[idx >> 1].x < 0) continue;
-    const uint2 st = __ldcg(B.state + idx);
-    if (st.x == idx) continue;  // the run ends here
-    const uint2 st2 = __ldcg(B.state + st.x);
-    if (st2.x == st.x) continue;  // already at the end of the run
-    __stcg(B.state + idx, make_uint2(st2.x, st.y + st2.y));
-    changed = true;
+    uint2 st = __ldcg(B.state + idx);
+    if (st.y & kDone) continue;
+#pragma unroll 1
+    for (int hop = 0; hop < 4 && !(st.y & kDone); ++hop) {  // a few hops per round: the chains shorten under way
+      const uint2 st2 = __ldcg(B.state + st.x);
+      st = make_uint2(st2.x, st.y + st2.y);  // the target's kDone bit carries over: its x is the run's end
+    }
+    __stcg(B.state + idx, st);
+    unfinished |= !(st.y & kDone);
   }
-  if (changed) B.ctr[4 + round] = 1;
+  if (__syncthreads_or(unfinished) && threadIdx.x == 0) B.ctr[4 + round] = 1;  // one store per CTA, not per entry
 }
 
 __global__ void bfs_runs_kernel(int n, BfsBufs B) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (B.link[i].x < 0) continue;
+    const int2 l = B.link[i];
+    if (l.x < 0) continue;
     const uint2 e0 = B.state[2 * (size_t)i], e1 = B.state[2 * (size_t)i + 1];
-    const int E0 = (int)(e0.x >> 1), E1 = (int)(e1.x >> 1), L = (int)(e0.y + e1.y) + 1;
-    int head, pos;
+    if (!(e0.y & e1.y & kDone)) {  // too few rounds (cannot happen: the host sizes them by the largest cluster)
+      B.ctr[2] = 1;
+      continue;
+    }
+    const int d0 = (int)(e0.y & ~kDone), d1 = (int)(e1.y & ~kDone);
+    const int E0 = (int)(e0.x >> 1), E1 = (int)(e1.x >> 1), L = d0 + d1 + 1;
+    int head, pos, rb = -1;
     if (E0 == E1) {  // a run of one cell (a closed ring of chain cells cannot exist: every component has its root)
       head = i;
       pos = 0;
       if (L != 1) B.ctr[2] = 1;
     } else if (E0 < E1) {
       head = E0;
-      pos = (int)e0.y;
+      pos = d0;
     } else {
       head = E1;
-      pos = (int)e1.y;
+      pos = d1;
     }
     if (head == i) {
-      const int rb = atomicAdd(&B.ctr[0], L);
-      B.headbase[i] = rb;
-      B.lohi[rb] = make_int2(0, L);
+      const int ints = (L + kRunHdr + 3) & ~3;  // headers are read as int4
+      rb = atomicAdd(&B.ctr[0], ints);
+      if (rb + ints > B.run_cap) {
+        B.ctr[2] = 1;
+        rb = -1;
+      } else {
+        // the irregular cells beyond either end: this cell's link on the side where the run ends at once, and the far
+        // end cell's link on the side its entry names
+        int out0, out1;
+        if (L == 1) {
+          out0 = l.x;
+          out1 = l.y;
+        } else {
+          const bool side0_ends_here = (int)(e0.x >> 1) == i;
+          out0 = side0_ends_here ? l.x : l.y;
+          const uint2 far = side0_ends_here ? e1 : e0;
+          const int2 lf = B.link[far.x >> 1];
+          out1 = (far.x & 1u) ? lf.y : lf.x;
+        }
+        int *hdr = B.runs + rb;
+        hdr[0] = 0;
+        hdr[1] = L;
+        hdr[2] = L;
+        hdr[3] = B.link[out0].y;
+        hdr[4] = B.link[out1].y;
+      }
     }
-    B.cinfo[i] = make_int4(head, pos, L, 0);
+    B.cinfo[i] = make_int4(head, pos, L, rb);  // over this cell's own two state entries: nobody else reads them here
   }
 }
 
-__global__ void bfs_scatter_kernel(int n, BfsBufs B) {
+__global__ void bfs_scatter_kernel(int n, const int *__restrict__ cellpos, BfsBufs B) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (B.link[i].x < 0) continue;
-    int4 ci = B.cinfo[i];
-    ci.x = B.headbase[ci.x];
-    B.cinfo[i] = ci;
-    B.run_cells[ci.x + ci.y] = i;
+    const int2 l = B.link[i];
+    if (l.x >= 0) {
+      const int4 ci = B.cinfo[i];
+      const int rb = B.cinfo[ci.x].w;  // the head's slot; only .x of a record changes in this kernel
+      B.cinfo[i].x = rb;
+      if (rb >= 0) B.runs[rb + kRunHdr + ci.y] = cellpos[i];
+    }
+  }
+}
+
+// neighbour ids of the irregular cells -> what the walk needs to know about each neighbour
+__global__ void bfs_irr_kernel(int n, BfsBufs B) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 l = B.link[i];
+    if (l.x != -1) continue;
+    IrrRec *r = B.irr + l.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = r->nb[k].x;
+      int2 v = make_int2(INT_MIN, 0);
+      if (j >= 0) {
+        const int2 lj = B.link[j];
+        if (lj.x < 0) v = make_int2(-1 - lj.y, 0);
+        else {
+          const int4 cj = B.cinfo[j];
+          v = make_int2(cj.x, cj.y);
+        }
+      }
+      r->nb[k] = v;
+    }
   }
 }
 
@@ -1030,8 +1110,10 @@ __global__ void bfs_scatter_kernel(int n, BfsBufs B) {
 // time, the additions themselves stay strictly sequential (every lane keeps the same copy)
 __device__ __forceinline__ void ordered_centre(const int *q, int n, int w, int lane, float *cx, float *cy) {
   float sum_x = 0.f, sum_y = 0.f;
+  int nxt = lane < n ? __ldcg(q + lane) : 0;
   for (int base = 0; base < n; base += 32) {
-    int pos = base + lane < n ? __ldcg(q + base + lane) : 0;
+    const int pos = nxt;
+    nxt = base + 32 + lane < n ? __ldcg(q + base + 32 + lane) : 0;  // in flight while this batch is added up
     int y = pos / w;
     float xf = (float)(pos - y * w), yf = (float)y;
     if (n - base >= 32) {
@@ -1052,13 +1134,12 @@ __device__ __forceinline__ void ordered_centre(const int *q, int n, int w, int l
   *cy = __fdiv_rn(sum_y, (float)(unsigned long long)n);
 }
 
-// One warp per flagged cluster.  items: x = compact cell, y = run slot (-1 irregular), z = position, w = L << 2 | dir + 1
+// One warp per flagged cluster.  items: x = run base (walker) or -1 (irregular), y = position / irregular slot, z = direction
 __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ flagged, const ClusterAcc *__restrict__ acc,
                                                        const uint32_t *__restrict__ offsets, const int *__restrict__ root_cellpos,
                                                        const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix,
-                                                       int pitch, int w, const int *__restrict__ cellpos, BfsBufs B,
-                                                       int *__restrict__ fallback, int *__restrict__ queue,
-                                                       float *__restrict__ centre_out) {
+                                                       int pitch, int w, BfsBufs B, int *__restrict__ fallback,
+                                                       int *__restrict__ queue, float *__restrict__ centre_out) {
   __shared__ int4 s_items[2][kItemCap];
   const int lane = threadIdx.x;
   const int c = flagged[blockIdx.x];
@@ -1081,72 +1162,102 @@ __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ f
     const int rpos = root_cellpos[c];
     const int ry = rpos / w, rx = rpos - ry * w;
     const int root = compact_index(mask, prefix, pitch, rx, ry);
+    const int slot = B.link[root].y;
     if (lane == 0) {
       q[0] = rpos;
-      B.vis[root] = 1;
-      s_items[0][0] = make_int4(root, -1, 0, 1);
+      B.irr[slot].vis = 1;
+      s_items[0][0] = make_int4(-1, slot, 0, 0);
     }
     __syncwarp();
   }
   const int sub = lane >> 3, k8 = lane & 7;
   while (cnt > 0) {
-    // ---- how many levels can the whole list be fast-forwarded? ----
-    int f = 0x7fffffff;
-    for (int base = 0; base < cnt; base += 32) {
-      if (base + lane < cnt) {
-        const int4 it = s_items[cur][base + lane];
-        int fi = 0;
-        if (it.y >= 0) {
-          const int2 lh = __ldcg(B.lohi + it.y);
-          const int L = it.w >> 2, gap = lh.y - lh.x;
-          fi = L == 1 ? 0 : (lh.x > 0 && lh.y < L) ? gap >> 1 : gap;  // entered from both ends: the walkers share what is left
+    // ---- how many levels can the whole list be fast-forwarded? (only a list of walkers can) ----
+    bool walkers_only = true;
+    for (int base = 0; base < cnt; base += 32)
+      if (base + lane < cnt && s_items[cur][base + lane].x < 0) walkers_only = false;
+    int f = 0;
+    if (__all_sync(0xffffffffu, walkers_only)) {
+      f = 0x7fffffff;
+      for (int base = 0; base < cnt; base += 32) {
+        if (base + lane < cnt) {
+          const int4 it = s_items[cur][base + lane];
+          const int4 hd = __ldcg(reinterpret_cast<const int4 *>(B.runs + it.x));  // lo, hi, L, out0
+          const int gap = hd.y - hd.x;
+          f = min(f, (hd.x > 0 && hd.y < hd.z) ? gap >> 1 : gap);  // entered from both ends: the walkers share what is left
         }
-        f = min(f, fi);
       }
+      f = __reduce_min_sync(0xffffffffu, f);
     }
-    f = __reduce_min_sync(0xffffffffu, f);
     if (f >= 1) {
       if (out + (long long)f * cnt > n) break;  // cannot happen; the check after the loop reports it
       const int total = f * cnt;
       for (int idx = lane; idx < total; idx += 32) {
         const int t = idx / cnt, i = idx - t * cnt;
         const int4 it = s_items[cur][i];
-        const int dir = (it.w & 3) - 1;
-        q[out + idx] = cellpos[B.run_cells[it.y + it.z + dir * (t + 1)]];
+        q[out + idx] = B.runs[it.x + kRunHdr + it.y + it.z * (t + 1)];
       }
       __syncwarp();
       for (int i = lane; i < cnt; i += 32) {
         int4 it = s_items[cur][i];
-        const int dir = (it.w & 3) - 1;
-        it.z += dir * f;
-        it.x = B.run_cells[it.y + it.z];
-        if (dir > 0) __stcg(&B.lohi[it.y].x, it.z + 1);
-        else __stcg(&B.lohi[it.y].y, it.z);
+        it.y += it.z * f;
+        if (it.z > 0) __stcg(B.runs + it.x, it.y + 1);
+        else __stcg(B.runs + it.x + 1, it.y);
         s_items[cur][i] = it;
       }
       out += total;
       __syncwarp();
       continue;
     }
-    // ---- one literal level: four cells per step, lanes 8 s .. 8 s + 7 test the neighbours of the s-th one ----
+    // ---- one literal level: four cells per step.  Lanes 8 s .. 8 s + 7 test the neighbours of the s-th one if it is
+    // irregular; a walker has one way to go (lane 8 s): the next cell of its run, or the irregular cell beyond its end ----
     int ncnt = 0;
     bool overflow = false;
     for (int base = 0; base < cnt; base += 4) {
       const bool valid = base + sub < cnt;
-      const int4 it = valid ? s_items[cur][base + sub] : make_int4(0, -1, 0, 0);
-      const int j = valid ? __ldg(B.nbr + 8 * (size_t)it.x + k8) : -1;
+      const int4 it = valid ? s_items[cur][base + sub] : make_int4(-1, -1, 0, 0);
+      // target: tx >= 0: chain cell (run tx, position ty), direction tz; tx < 0: irregular slot -1 - tx; tcp = its cellpos.
+      // What decides (run header / visited flag) and what is stored (cellpos) are loaded side by side: a step costs two
+      // memory latencies (neighbour record, then these), not three.
+      int tx = INT_MIN, ty = 0, tz = 0, tcp = 0;
       bool take = false;
-      int4 ci = make_int4(-1, 0, 0, 0);
-      if (j >= 0) {
-        ci = B.cinfo[j];
-        if (ci.x < 0) take = __ldcg(B.vis + j) == 0;
-        else {
-          const int2 lh = __ldcg(B.lohi + ci.x);
-          take = lh.x <= ci.y && ci.y < lh.y;
+      if (valid && it.x < 0) {
+        const int2 nb = __ldg(&B.irr[it.y].nb[k8]);
+        tx = nb.x;
+        ty = nb.y;
+        if (tx >= 0) {
+          const int4 hd = __ldcg(reinterpret_cast<const int4 *>(B.runs + tx));
+          tcp = __ldg(B.runs + tx + kRunHdr + ty);
+          take = hd.x <= ty && ty < hd.y;
+          // entered from outside at one of the run's ends; a run of one cell is entered "forwards" from its out0 side
+          tz = hd.z == 1 ? (hd.w == it.y ? 1 : -1) : (ty == 0 ? 1 : -1);
+        } else if (tx != INT_MIN) {
+          const int2 cv = __ldcg(reinterpret_cast<const int2 *>(&B.irr[-1 - tx].cellpos));  // cellpos, vis
+          tcp = cv.x;
+          take = cv.y == 0;
+        }
+      } else if (valid && k8 == 0) {
+        const int4 hd = __ldcg(reinterpret_cast<const int4 *>(B.runs + it.x));
+        const int o1 = __ldg(B.runs + it.x + 4);
+        const int ncp = __ldg(B.runs + it.x + kRunHdr + it.y + it.z);  // next cell of the run (a pad / header int beyond its ends)
+        const int gap = hd.y - hd.x;
+        if (gap >= 1) {
+          tx = it.x;
+          ty = it.y + it.z;
+          tz = it.z;
+          tcp = ncp;
+          take = true;
+        } else if (!(hd.x > 0 && hd.y < hd.z)) {  // walked to the end: the irregular cell beyond it
+          const int o = it.z > 0 ? o1 : hd.w;
+          const int2 cv = __ldcg(reinterpret_cast<const int2 *>(&B.irr[o].cellpos));
+          tx = -1 - o;
+          tcp = cv.x;
+          take = cv.y == 0;
         }
       }
       // a cell claimed by two lanes of this step goes to the lower lane: the cell popped earlier, as in the FIFO
-      const unsigned same = __match_any_sync(0xffffffffu, take ? j : -2 - lane);
+      const int key = tx >= 0 ? tx + kRunHdr + ty : tx;
+      const unsigned same = __match_any_sync(0xffffffffu, take ? key : INT_MIN + 1 + lane);
       take = take && (__ffs(same) - 1 == lane);
       const unsigned m = __ballot_sync(0xffffffffu, take);
       if (ncnt + __popc(m) > kItemCap || out + ncnt + __popc(m) > n) {
@@ -1155,17 +1266,15 @@ __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ f
       }
       if (take) {
         const int slot = ncnt + __popc(m & lt);
-        int dir = 0;
-        if (ci.x >= 0) {
-          // pushed by its predecessor in the run, or entered from outside at one of the run's ends
-          dir = it.y == ci.x ? (it.z == ci.y - 1 ? 1 : -1) : (ci.y == 0 ? 1 : -1);
-          if (dir > 0) __stcg(&B.lohi[ci.x].x, ci.y + 1);
-          else __stcg(&B.lohi[ci.x].y, ci.y);
+        if (tx >= 0) {
+          if (tz > 0) __stcg(B.runs + tx, ty + 1);
+          else __stcg(B.runs + tx + 1, ty);
+          s_items[cur ^ 1][slot] = make_int4(tx, ty, tz, 0);
         } else {
-          B.vis[j] = 1;
+          B.irr[-1 - tx].vis = 1;
+          s_items[cur ^ 1][slot] = make_int4(-1, -1 - tx, 0, 0);
         }
-        s_items[cur ^ 1][slot] = make_int4(j, ci.x, ci.y, (ci.z << 2) | (dir + 1));
-        q[out + slot] = cellpos[j];
+        q[out + slot] = tcp;
       }
       ncnt += __popc(m);
       __syncwarp();
@@ -1324,10 +1433,10 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     }
   if (!need.empty() && !getenv("AOS_LITERAL_BFS")) {
     const size_t nn = (size_t)n, total_jobs = need.size();
-    // nbr int[8n] | state uint2[2n] | cinfo int4[n] | link int2[n] | lohi int2[n] | run_cells int[n] | headbase int[n] |
-    // flagged int[jobs] | fallback int[jobs] | ctr int[64] | vis u8[n]
+    // link int2[n] | state uint2[2n] (later cinfo int4[n]) | runs int[3n] | irr IrrRec[n/4] | flagged, fallback int[jobs] | ctr
     const size_t jobs4 = (total_jobs + 3) & ~(size_t)3;
-    AOS_CUDA_OK(c, c->bfs_buf.reserve(nn * (32 + 16 + 16 + 8 + 8 + 4 + 4 + 1) + (2 * jobs4 + 64) * 4 + 16 * 12));
+    const size_t run_cap = 3 * nn + 64, irr_cap = nn / 4 + 1024;
+    AOS_CUDA_OK(c, c->bfs_buf.reserve(nn * (8 + 16) + run_cap * 4 + irr_cap * sizeof(IrrRec) + (2 * jobs4 + 64) * 4 + 16 * 8));
     BfsBufs B;
     char *p = c->bfs_buf.as<char>();
     auto carve = [&p](size_t bytes) {
@@ -1335,17 +1444,16 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
       p += (bytes + 15) & ~(size_t)15;
       return r;
     };
-    B.nbr = reinterpret_cast<int *>(carve(nn * 32));
-    B.state = reinterpret_cast<uint2 *>(carve(nn * 16));
-    B.cinfo = reinterpret_cast<int4 *>(carve(nn * 16));
     B.link = reinterpret_cast<int2 *>(carve(nn * 8));
-    B.lohi = reinterpret_cast<int2 *>(carve(nn * 8));
-    B.run_cells = reinterpret_cast<int *>(carve(nn * 4));
-    B.headbase = reinterpret_cast<int *>(carve(nn * 4));
+    B.state = reinterpret_cast<uint2 *>(carve(nn * 16));
+    B.cinfo = reinterpret_cast<int4 *>(B.state);
+    B.runs = reinterpret_cast<int *>(carve(run_cap * 4));
+    B.irr = reinterpret_cast<IrrRec *>(carve(irr_cap * sizeof(IrrRec)));
     int *d_flagged = reinterpret_cast<int *>(carve(jobs4 * 4));
     int *d_fallback = reinterpret_cast<int *>(carve(jobs4 * 4));
     B.ctr = reinterpret_cast<int *>(carve(64 * 4));
-    B.vis = reinterpret_cast<unsigned char *>(carve(nn));
+    B.run_cap = (int)std::min<size_t>(run_cap, 0x7fffffff);
+    B.irr_cap = (int)std::min<size_t>(irr_cap, 0x7fffffff);
     if (!c->pin_a.resize(sizeof(int) * jobs4)) {  // pin_a is free again: h_clusters holds its copy
       set_error(c, "cudaHostAlloc failed (replay jobs)");
       return AOS_ERR_CUDA;
@@ -1357,22 +1465,24 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     memcpy(c->pin_a.data(), need.data(), sizeof(int) * total_jobs);
     s = h2d_small(c, d_flagged, c->pin_a.data(), sizeof(int) * jobs4, true);
     if (s != AOS_OK) return s;
-    AOS_CUDA_OK(c, cudaMemsetAsync(B.ctr, 0, 64 * 4 + nn, st));  // counters and the visited bytes behind them
+    AOS_CUDA_OK(c, cudaMemsetAsync(B.ctr, 0, 64 * 4, st));
     const int gb = grid_for(nn, 256);
     bfs_prepare_kernel<<<gb, 256, 0, st>>>(mask, prefix, P.pitch, P.h, P.w, cellpos, cell_cluster, root_cellpos, d_rows, n, B);
     bfs_link_init_kernel<<<gb, 256, 0, st>>>(n, B);
     c->launches += 2;
+    // a run is shorter than its cluster; a round of four hops covers at least five times the distance of the one before
+    // (bfs_runs_kernel checks that every entry arrived and hands the map to the literal replay otherwise)
     int rounds = 1;
-    while ((1u << rounds) < max_need && rounds < 31) ++rounds;  // a run is shorter than its cluster
-    ++rounds;  // the last round finds nothing to change
-    if (rounds > 56) rounds = 56;
+    for (unsigned long long reach = 5; reach < max_need; reach *= 5) ++rounds;
+    rounds += 2;
     for (int r = 0; r < rounds; ++r) bfs_jump_kernel<<<grid_for(2 * nn, 256), 256, 0, st>>>(n, B, r);
     bfs_runs_kernel<<<gb, 256, 0, st>>>(n, B);
-    bfs_scatter_kernel<<<gb, 256, 0, st>>>(n, B);
-    c->launches += rounds + 2;
+    bfs_scatter_kernel<<<gb, 256, 0, st>>>(n, cellpos, B);
+    bfs_irr_kernel<<<gb, 256, 0, st>>>(n, B);
+    c->launches += rounds + 3;
     AOS_CUDA_OK(c, cudaGetLastError());
     c->mark("replay_prep");
-    bfs_chain_kernel<<<(unsigned)total_jobs, 32, 0, st>>>(d_flagged, acc, offsets, root_cellpos, mask, prefix, P.pitch, P.w, cellpos, B,
+    bfs_chain_kernel<<<(unsigned)total_jobs, 32, 0, st>>>(d_flagged, acc, offsets, root_cellpos, mask, prefix, P.pitch, P.w, B,
                                                          d_fallback, queue, centre);
     ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
@@ -1386,8 +1496,8 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     if (s != AOS_OK) return s;
     c->bfs_fallbacks = c->h_flag[1];
     if (getenv("AOS_DEBUG"))
-      fprintf(stderr, "[aos] BFS order: %zu clusters (longest %u cells), %d jump rounds, %d run slots, %d left to the literal replay%s\n",
-              total_jobs, max_need, rounds, c->h_flag[0], c->h_flag[1], c->h_flag[2] ? " (ranking broken)" : "");
+      fprintf(stderr, "[aos] BFS order: %zu clusters (longest %u cells), %d jump rounds, %d run ints, %d irregular cells, %d left to the literal replay%s\n",
+              total_jobs, max_need, rounds, c->h_flag[0], c->h_flag[3], c->h_flag[1], c->h_flag[2] ? " (ranking broken / out of space)" : "");
     // clusters the warp gave up on (a level wider than its list) kept their flags: the literal replay below takes them
     need.clear();
     if (c->h_flag[1] > 0)
