@@ -203,11 +203,16 @@ __global__ void cc_init_kernel(const uint32_t *__restrict__ mask, const uint32_t
     uint32_t v = mask[i];
     if (!v) continue;
     int y = (int)(i / (size_t)pitch), cw = (int)(i - (size_t)y * pitch);
-    int idx = (int)prefix[i];
+    const int idx0 = (int)prefix[i];
+    int idx = idx0;
+    // consecutive cells of a word start out under the first cell of their run (its index is the smaller one, as the
+    // hooking rule wants): the west links inside a word, most of all links on a thinned row, are then already made
+    const uint32_t v0 = v, starts = v & ~(v << 1);
     while (v) {
       int b = __ffs(v) - 1;
       v &= v - 1;
-      parent[idx] = idx;
+      const int sb = 31 - __clz(starts & (0xffffffffu >> (31 - b)));  // first bit of the run that holds bit b
+      parent[idx] = idx0 + __popc(v0 & ((1u << sb) - 1u));
       cellpos[idx] = y * w + (cw << 5) + b;
       ++idx;
     }
@@ -264,10 +269,9 @@ __global__ void cc_link_kernel(const uint32_t *__restrict__ mask, const uint32_t
     const int pos = cellpos[idx];
     const int y = pos / w, x = pos - y * w;
     // W, NW, N, NE  (N = row y-1)
-    if (x > 0) {
-      // the west neighbour is the previous compact index when its bit is set
-      const uint32_t m = mask[(size_t)y * pitch + ((x - 1) >> 5)];
-      if ((m >> ((x - 1) & 31)) & 1u) uf_union(parent, idx, idx - 1);
+    if (x > 0 && (x & 31) == 0) {
+      // west: made by cc_init_kernel inside a word; across a word boundary the neighbour is the previous compact index
+      if (mask[(size_t)y * pitch + ((x - 1) >> 5)] >> 31) uf_union(parent, idx, idx - 1);
     }
     if (y > 0) {
       if (x > 0) {
