@@ -332,7 +332,7 @@ def bench_ours(args):
                          "achieved": round(whole_gbs, 1) if whole_gbs else None, "peak": peak, "unit": "GB/s",
                          "frac": round(whole_gbs / peak, 4) if whole_gbs else None,
                          "algorithmic_bytes": int(b_alg), "device_ms_per_map": round(gpu_ms, 4),
-                         "traffic": None, "traffic_note": "per-kernel dram__bytes from ncu --set full are under profiles/ (r02_*)",
+                         **map_traffic(args.workload),
                          "peak_source": peak_src,
                          "time_dominant_stage": kernels[0] if kernels else None,
                          "largest_traffic_kernel": next((k for k in kernels if k["stage"] == "bin"), None),
@@ -758,6 +758,20 @@ def bench_reference(args):
             "cpu_baseline": cb, "points_per_map": int(npts),
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def map_traffic(workload):
+    """roofline.traffic = dram__bytes_read + dram__bytes_write of ALL kernels of one map, from the committed ncu launch
+    list of the same pipeline (scripts/profile_r02.sh -> scripts/ncu_traffic.py); not re-measured per run (ncu cannot run
+    inside a timed bench), so the source file and its date travel with the number."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f"r02_traffic_{workload.lower()}.json")
+    try:
+        t = json.load(open(path))
+        return {"traffic": int(t["dram_bytes"]),
+                "traffic_note": f"sum over the {t['launches']} launches of one map, ncu dram__bytes_read+write, captured "
+                                f"{t['captured']} (profiles/{os.path.basename(path)}; cold-cache upper bound)"}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None, "traffic_note": "no committed ncu traffic capture for this workload under profiles/"}
 
 
 def main():

@@ -95,6 +95,35 @@ def test_long_rows_bfs_order_replay(gpu_ctx, oracle):
     assert_seed_parity(gpu_ctx, r, check_labels=False)
 
 
+@pytest.mark.parametrize("case", ["long_rows", "tie_breaks", "rotated"])
+def test_literal_bfs_replay_equals_chain_walk(gpu_ctx, oracle, case, monkeypatch):
+    """The BFS order comes from the chain-compressed walk (bfs_chain_kernel); the literal warp-per-cluster replay
+    (bfs_replay_kernel) is its fallback for levels wider than the walk's list.  AOS_LITERAL_BFS forces the fallback for
+    every flagged cluster: both must reproduce the oracle (seed_gen:1008-1059), on rows, fragments and rotated rows."""
+    if case == "long_rows":
+        spec = synth.OrchardSpec(extent_x=1000.0, extent_y=16.0, row_pitch=4.0, n_points=500_000, gap_prob=0.0,
+                                 jitter=0.0, outlier_count=4, seed=11)
+        over = {}
+    elif case == "tie_breaks":
+        spec = synth.config("TINY", seed=1)
+        spec.outlier_count = 12
+        over = dict(cluster_min_length=0.0)
+    else:
+        spec = synth.OrchardSpec(extent_x=400.0, extent_y=100.0, row_pitch=5.0, n_points=800_000, gap_prob=0.01,
+                                 jitter=0.05, outlier_count=8, seed=5, rotation_deg=17.0)
+        over = {}
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle, **over)
+    r = oracle.seed_stage(po, pts)
+    if case != "tie_breaks":
+        assert max(r["cl_sumx"].max(), r["cl_sumy"].max()) >= (1 << 24)  # some centre depends on the order
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r, check_labels=False)
+    monkeypatch.setenv("AOS_LITERAL_BFS", "1")
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r, check_labels=False)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_min_length_zero_tie_breaks(gpu_ctx, oracle, seed):
     """cluster_min_length = 0 turns every fragment into a row, including tiny symmetric ones whose
