@@ -59,10 +59,27 @@ __device__ __forceinline__ void world_to_grid_dev(const SeedGrid &g, float wx, f
 }
 
 // raycastToOccupiedCell, seed_gen:1730-1771
+// The same cell without the two double divisions per ray step: rel = float(q) with q = (w - o) / res, cell = floorf(rel).
+// With q placed by a reciprocal multiplication (relative error of a few 2^-53) the cell can differ from the literal one
+// only when q is within that error of an integer from above, or within half a float32 ulp (<= |q| 2^-24) of one from below
+// (where the float rounding reaches the integer): those steps take the literal expression.
+__device__ __forceinline__ void world_to_grid_fast(const SeedGrid &g, double inv_res, float wx, float wy, int *gx, int *gy) {
+  const double qx = ((double)wx - g.ox) * inv_res, qy = ((double)wy - g.oy) * inv_res;
+  const double fx = qx - floor(qx), fy = qy - floor(qy);
+  const double hx = fabs(qx) * 6.0e-8 + 1e-6, hy = fabs(qy) * 6.0e-8 + 1e-6;
+  if (!(fx > 1e-6 && fx < 1.0 - hx && fy > 1e-6 && fy < 1.0 - hy)) {
+    world_to_grid_dev(g, wx, wy, gx, gy);
+    return;
+  }
+  *gx = max(0, min(g.w - 1, (int)floorf((float)qx)));
+  *gy = max(0, min(g.h - 1, (int)floorf((float)qy)));
+}
+
 __device__ bool raycast_to_occupied_dev(const SeedGrid &g, double sx, double sy, double dx, double dy, double max_distance,
                                         double *hx, double *hy) {
   const double step = (double)g.res * 0.5;
   const int max_steps = (int)(max_distance / step);
+  const double inv_res = 1.0 / (double)g.res;
   double cx = sx, cy = sy;
   for (int i = 0; i < max_steps; ++i) {
     cx += dx * step;
@@ -72,7 +89,7 @@ __device__ bool raycast_to_occupied_dev(const SeedGrid &g, double sx, double sy,
     // double below 1 has a root below the midpoint to 1), so the root itself is not needed
     if (ex * ex + ey * ey < 1.0) continue;
     int gx, gy;
-    world_to_grid_dev(g, (float)cx, (float)cy, &gx, &gy);
+    world_to_grid_fast(g, inv_res, (float)cx, (float)cy, &gx, &gy);
     if (sg_occ(g, gx, gy)) {
       *hx = cx;
       *hy = cy;
