@@ -1142,8 +1142,9 @@ __device__ __forceinline__ void ordered_centre(const int *q, int n, int w, int l
 __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ flagged, const ClusterAcc *__restrict__ acc,
                                                        const uint32_t *__restrict__ offsets, const int *__restrict__ root_cellpos,
                                                        const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix,
-                                                       int pitch, int w, BfsBufs B, int *__restrict__ fallback,
-                                                       int *__restrict__ queue, float *__restrict__ centre_out) {
+                                                       int pitch, int w, BfsBufs B, int item_cap,
+                                                       int *__restrict__ fallback, int *__restrict__ queue,
+                                                       float *__restrict__ centre_out) {
   __shared__ int4 s_items[2][kItemCap];
   const int lane = threadIdx.x;
   const int c = flagged[blockIdx.x];
@@ -1264,7 +1265,7 @@ __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ f
       const unsigned same = __match_any_sync(0xffffffffu, take ? key : INT_MIN + 1 + lane);
       take = take && (__ffs(same) - 1 == lane);
       const unsigned m = __ballot_sync(0xffffffffu, take);
-      if (ncnt + __popc(m) > kItemCap || out + ncnt + __popc(m) > n) {
+      if (ncnt + __popc(m) > item_cap || out + ncnt + __popc(m) > n) {
         overflow = true;
         break;
       }
@@ -1486,8 +1487,10 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     c->launches += rounds + 3;
     AOS_CUDA_OK(c, cudaGetLastError());
     c->mark("replay_prep");
+    int item_cap = kItemCap;  // AOS_BFS_ITEM_CAP (tests): a narrower level list, so that some clusters take the fallback
+    if (const char *e = getenv("AOS_BFS_ITEM_CAP")) item_cap = std::max(1, std::min(kItemCap, atoi(e)));
     bfs_chain_kernel<<<(unsigned)total_jobs, 32, 0, st>>>(d_flagged, acc, offsets, root_cellpos, mask, prefix, P.pitch, P.w, B,
-                                                         d_fallback, queue, centre);
+                                                         item_cap, d_fallback, queue, centre);
     ++c->launches;
     AOS_CUDA_OK(c, cudaGetLastError());
     c->mark("replay_bfs");

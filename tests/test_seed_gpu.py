@@ -122,6 +122,11 @@ def test_literal_bfs_replay_equals_chain_walk(gpu_ctx, oracle, case, monkeypatch
     monkeypatch.setenv("AOS_LITERAL_BFS", "1")
     gpu_ctx.seed_stage(pl, pts)
     assert_seed_parity(gpu_ctx, r, check_labels=False)
+    # a level list of two cells: clusters with a junction hand over to the fallback, plain rows stay with the walk
+    monkeypatch.delenv("AOS_LITERAL_BFS")
+    monkeypatch.setenv("AOS_BFS_ITEM_CAP", "2")
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r, check_labels=False)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
