@@ -385,11 +385,13 @@ __global__ void acc_sizes_kernel(const ClusterAcc *acc, int n, uint32_t *sizes) 
 }
 
 __global__ void cc_group_kernel(const int *__restrict__ cell_cluster, const int *__restrict__ cellpos, int n,
-                                const uint32_t *__restrict__ offsets, ClusterAcc *acc, int *__restrict__ grouped) {
+                                const uint32_t *__restrict__ offsets, ClusterAcc *acc, int *__restrict__ grouped,
+                                int *__restrict__ grouped_id) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int c = cell_cluster[i];
     unsigned int k = atomicAdd(&acc[c].cursor, 1u);
     grouped[offsets[c] + k] = cellpos[i];
+    grouped_id[offsets[c] + k] = i;  // the same list as compact indices (bfs_chain_kernel stages a cluster from it)
   }
 }
 
@@ -1138,43 +1140,57 @@ __device__ __forceinline__ void ordered_centre(const int *q, int n, int w, int l
   *cy = __fdiv_rn(sum_y, (float)(unsigned long long)n);
 }
 
-// One warp per flagged cluster.  items: x = run base (walker) or -1 (irregular), y = position / irregular slot, z = direction
-__global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ flagged, const ClusterAcc *__restrict__ acc,
-                                                       const uint32_t *__restrict__ offsets, const int *__restrict__ root_cellpos,
-                                                       const uint32_t *__restrict__ mask, const uint32_t *__restrict__ prefix,
-                                                       int pitch, int w, BfsBufs B, int item_cap,
-                                                       int *__restrict__ fallback, int *__restrict__ queue,
-                                                       float *__restrict__ centre_out) {
-  __shared__ int4 s_items[2][kItemCap];
-  const int lane = threadIdx.x;
-  const int c = flagged[blockIdx.x];
-  const int n = (int)acc[c].size;
-  int *q = queue + offsets[c];
+// ---- where the walk keeps what it reads and writes at every level ------------------------------------------------
+// GlobalStore: the tables as the ranking kernels left them (a run is named by its base in B.runs, an irregular cell by its
+// slot in B.irr).  SharedStore: a copy of THIS cluster's irregular records and run headers in shared memory, indexed locally;
+// a level then costs shared-memory latency instead of two L2 round trips (0.3-0.4 us each on B200), which is what the walk
+// of a long row consists of.  The cells of the runs stay in B.runs either way (they are only read to be written out).
+struct GlobalStore {
+  BfsBufs B;
+  __device__ __forceinline__ int2 nb(int irr, int k) const { return __ldg(&B.irr[irr].nb[k]); }
+  __device__ __forceinline__ int2 cellpos_vis(int irr) const { return __ldcg(reinterpret_cast<const int2 *>(&B.irr[irr].cellpos)); }
+  __device__ __forceinline__ void set_vis(int irr) const { B.irr[irr].vis = 1; }
+  __device__ __forceinline__ int4 hdr(int run) const { return __ldcg(reinterpret_cast<const int4 *>(B.runs + run)); }  // lo, hi, L, out0
+  __device__ __forceinline__ int out1(int run) const { return __ldg(B.runs + run + 4); }
+  __device__ __forceinline__ int base(int run) const { return run; }
+  __device__ __forceinline__ void set_lo(int run, int v) const { __stcg(B.runs + run, v); }
+  __device__ __forceinline__ void set_hi(int run, int v) const { __stcg(B.runs + run + 1, v); }
+};
+
+struct SIrr {  // 72 bytes
+  int2 nb[8];
+  int cellpos, vis;
+};
+struct SHdr {  // 24 bytes
+  int lo, hi, L, out0, out1, rb;
+};
+struct SharedStore {
+  SIrr *irr;
+  SHdr *hd;
+  __device__ __forceinline__ int2 nb(int i, int k) const { return irr[i].nb[k]; }
+  __device__ __forceinline__ int2 cellpos_vis(int i) const { return make_int2(irr[i].cellpos, irr[i].vis); }
+  __device__ __forceinline__ void set_vis(int i) const { irr[i].vis = 1; }
+  __device__ __forceinline__ int4 hdr(int r) const { return make_int4(hd[r].lo, hd[r].hi, hd[r].L, hd[r].out0); }
+  __device__ __forceinline__ int out1(int r) const { return hd[r].out1; }
+  __device__ __forceinline__ int base(int r) const { return hd[r].rb; }
+  __device__ __forceinline__ void set_lo(int r, int v) const { hd[r].lo = v; }
+  __device__ __forceinline__ void set_hi(int r, int v) const { hd[r].hi = v; }
+};
+
+// The walk itself, by ONE warp.  items: x = run (walker) or -1 (irregular), y = position / irregular index, z = direction.
+// It writes REFERENCES into q -- the index of a chain cell in B.runs, or -1 - (irregular index) -- so that no global load
+// sits on its path; the caller turns them into cell positions afterwards, all threads at once.
+// Returns the number of cells written to q, or -1 when a level did not fit the list.
+template <typename Store>
+__device__ int bfs_chain_walk(const Store S, int4 (*s_items)[kItemCap], int item_cap, int root_irr, int n, int *q, int lane) {
   const unsigned lt = (1u << lane) - 1u;
-  auto give_up = [&]() {
-    if (lane == 0) {
-      fallback[blockIdx.x] = 1;
-      atomicAdd(&B.ctr[1], 1);
-    }
-  };
-  if (lane == 0) fallback[blockIdx.x] = 0;
-  if (__ldcg(&B.ctr[2])) {  // the ranking found something it does not understand: every cluster takes the literal replay
-    give_up();
-    return;
-  }
   int cur = 0, cnt = 1, out = 1;
-  {
-    const int rpos = root_cellpos[c];
-    const int ry = rpos / w, rx = rpos - ry * w;
-    const int root = compact_index(mask, prefix, pitch, rx, ry);
-    const int slot = B.link[root].y;
-    if (lane == 0) {
-      q[0] = rpos;
-      B.irr[slot].vis = 1;
-      s_items[0][0] = make_int4(-1, slot, 0, 0);
-    }
-    __syncwarp();
+  if (lane == 0) {
+    q[0] = -1 - root_irr;
+    S.set_vis(root_irr);
+    s_items[0][0] = make_int4(-1, root_irr, 0, 0);
   }
+  __syncwarp();
   const int sub = lane >> 3, k8 = lane & 7;
   while (cnt > 0) {
     // ---- how many levels can the whole list be fast-forwarded? (only a list of walkers can) ----
@@ -1187,7 +1203,7 @@ __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ f
       for (int base = 0; base < cnt; base += 32) {
         if (base + lane < cnt) {
           const int4 it = s_items[cur][base + lane];
-          const int4 hd = __ldcg(reinterpret_cast<const int4 *>(B.runs + it.x));  // lo, hi, L, out0
+          const int4 hd = S.hdr(it.x);
           const int gap = hd.y - hd.x;
           f = min(f, (hd.x > 0 && hd.y < hd.z) ? gap >> 1 : gap);  // entered from both ends: the walkers share what is left
         }
@@ -1195,19 +1211,19 @@ __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ f
       f = __reduce_min_sync(0xffffffffu, f);
     }
     if (f >= 1) {
-      if (out + (long long)f * cnt > n) break;  // cannot happen; the check after the loop reports it
+      if (out + (long long)f * cnt > n) return out;  // cannot happen; the caller's check reports it
       const int total = f * cnt;
       for (int idx = lane; idx < total; idx += 32) {
         const int t = idx / cnt, i = idx - t * cnt;
         const int4 it = s_items[cur][i];
-        q[out + idx] = B.runs[it.x + kRunHdr + it.y + it.z * (t + 1)];
+        q[out + idx] = S.base(it.x) + kRunHdr + it.y + it.z * (t + 1);
       }
       __syncwarp();
       for (int i = lane; i < cnt; i += 32) {
         int4 it = s_items[cur][i];
         it.y += it.z * f;
-        if (it.z > 0) __stcg(B.runs + it.x, it.y + 1);
-        else __stcg(B.runs + it.x + 1, it.y);
+        if (it.z > 0) S.set_lo(it.x, it.y + 1);
+        else S.set_hi(it.x, it.y);
         s_items[cur][i] = it;
       }
       out += total;
@@ -1217,87 +1233,175 @@ __global__ void __launch_bounds__(32) bfs_chain_kernel(const int *__restrict__ f
     // ---- one literal level: four cells per step.  Lanes 8 s .. 8 s + 7 test the neighbours of the s-th one if it is
     // irregular; a walker has one way to go (lane 8 s): the next cell of its run, or the irregular cell beyond its end ----
     int ncnt = 0;
-    bool overflow = false;
     for (int base = 0; base < cnt; base += 4) {
       const bool valid = base + sub < cnt;
       const int4 it = valid ? s_items[cur][base + sub] : make_int4(-1, -1, 0, 0);
-      // target: tx >= 0: chain cell (run tx, position ty), direction tz; tx < 0: irregular slot -1 - tx; tcp = its cellpos.
-      // What decides (run header / visited flag) and what is stored (cellpos) are loaded side by side: a step costs two
-      // memory latencies (neighbour record, then these), not three.
-      int tx = INT_MIN, ty = 0, tz = 0, tcp = 0;
+      // target: tx >= 0: chain cell (run tx, position ty), direction tz; tx < 0: irregular cell -1 - tx; tkey = its reference
+      int tx = INT_MIN, ty = 0, tz = 0, tkey = 0;
       bool take = false;
       if (valid && it.x < 0) {
-        const int2 nb = __ldg(&B.irr[it.y].nb[k8]);
+        const int2 nb = S.nb(it.y, k8);
         tx = nb.x;
         ty = nb.y;
         if (tx >= 0) {
-          const int4 hd = __ldcg(reinterpret_cast<const int4 *>(B.runs + tx));
-          tcp = __ldg(B.runs + tx + kRunHdr + ty);
+          const int4 hd = S.hdr(tx);
+          tkey = S.base(tx) + kRunHdr + ty;
           take = hd.x <= ty && ty < hd.y;
           // entered from outside at one of the run's ends; a run of one cell is entered "forwards" from its out0 side
           tz = hd.z == 1 ? (hd.w == it.y ? 1 : -1) : (ty == 0 ? 1 : -1);
         } else if (tx != INT_MIN) {
-          const int2 cv = __ldcg(reinterpret_cast<const int2 *>(&B.irr[-1 - tx].cellpos));  // cellpos, vis
-          tcp = cv.x;
-          take = cv.y == 0;
+          take = S.cellpos_vis(-1 - tx).y == 0;
+          tkey = tx;
         }
       } else if (valid && k8 == 0) {
-        const int4 hd = __ldcg(reinterpret_cast<const int4 *>(B.runs + it.x));
-        const int o1 = __ldg(B.runs + it.x + 4);
-        const int ncp = __ldg(B.runs + it.x + kRunHdr + it.y + it.z);  // next cell of the run (a pad / header int beyond its ends)
+        const int4 hd = S.hdr(it.x);
+        const int o1 = S.out1(it.x);
         const int gap = hd.y - hd.x;
-        if (gap >= 1) {
+        if (gap >= 1) {  // the next cell of the run
           tx = it.x;
           ty = it.y + it.z;
           tz = it.z;
-          tcp = ncp;
+          tkey = S.base(it.x) + kRunHdr + ty;
           take = true;
         } else if (!(hd.x > 0 && hd.y < hd.z)) {  // walked to the end: the irregular cell beyond it
           const int o = it.z > 0 ? o1 : hd.w;
-          const int2 cv = __ldcg(reinterpret_cast<const int2 *>(&B.irr[o].cellpos));
           tx = -1 - o;
-          tcp = cv.x;
-          take = cv.y == 0;
+          take = S.cellpos_vis(o).y == 0;
+          tkey = tx;
         }
       }
       // a cell claimed by two lanes of this step goes to the lower lane: the cell popped earlier, as in the FIFO
-      const int key = tx >= 0 ? tx + kRunHdr + ty : tx;
-      const unsigned same = __match_any_sync(0xffffffffu, take ? key : INT_MIN + 1 + lane);
+      const unsigned same = __match_any_sync(0xffffffffu, take ? tkey : INT_MIN + 1 + lane);
       take = take && (__ffs(same) - 1 == lane);
       const unsigned m = __ballot_sync(0xffffffffu, take);
-      if (ncnt + __popc(m) > item_cap || out + ncnt + __popc(m) > n) {
-        overflow = true;
-        break;
-      }
+      if (ncnt + __popc(m) > item_cap) return -1;
+      if (out + ncnt + __popc(m) > n) return out + ncnt + __popc(m);
       if (take) {
         const int slot = ncnt + __popc(m & lt);
         if (tx >= 0) {
-          if (tz > 0) __stcg(B.runs + tx, ty + 1);
-          else __stcg(B.runs + tx + 1, ty);
+          if (tz > 0) S.set_lo(tx, ty + 1);
+          else S.set_hi(tx, ty);
           s_items[cur ^ 1][slot] = make_int4(tx, ty, tz, 0);
         } else {
-          B.irr[-1 - tx].vis = 1;
+          S.set_vis(-1 - tx);
           s_items[cur ^ 1][slot] = make_int4(-1, -1 - tx, 0, 0);
         }
-        q[out + slot] = tcp;
+        q[out + slot] = tkey;
       }
       ncnt += __popc(m);
       __syncwarp();
-    }
-    if (overflow) {
-      give_up();
-      return;
     }
     out += ncnt;
     cnt = ncnt;
     cur ^= 1;
     __syncwarp();
   }
-  if (out != n) {  // defensive: the literal replay recomputes the cluster
-    give_up();
+  return out;
+}
+
+constexpr int kChainThreads = 256;   // threads per cluster (1024 for the longest rows: staging is a latency-bound gather)
+// One CTA per flagged cluster.  All of its threads stage the cluster's irregular records and run headers in shared memory
+// (if they fit `budget` bytes; otherwise the walk reads the global tables), warp 0 walks, all threads turn the references
+// it wrote into cell positions, warp 0 adds up the float32 centre in that order.
+__global__ void __launch_bounds__(1024) bfs_chain_kernel(const int *__restrict__ flagged, const ClusterAcc *__restrict__ acc,
+                                                                  const uint32_t *__restrict__ offsets,
+                                                                  const int *__restrict__ grouped_id,
+                                                                  const int *__restrict__ root_cellpos,
+                                                                  const uint32_t *__restrict__ mask,
+                                                                  const uint32_t *__restrict__ prefix, int pitch, int w, BfsBufs B,
+                                                                  int item_cap, int budget, int *__restrict__ fallback,
+                                                                  int *__restrict__ queue, float *__restrict__ centre_out) {
+  __shared__ int4 s_items[2][kItemCap];
+  __shared__ int s_nirr, s_nrun, s_out;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int c = flagged[blockIdx.x];
+  const int n = (int)acc[c].size;
+  int *q = queue + offsets[c];
+  if (tid == 0) {
+    fallback[blockIdx.x] = 0;
+    s_nirr = 0;
+    s_nrun = 0;
+  }
+  const bool broken = __ldcg(&B.ctr[2]) != 0;  // the ranking found something it does not understand
+  __syncthreads();
+  const int rpos = root_cellpos[c];
+  const int root = compact_index(mask, prefix, pitch, rpos - (rpos / w) * w, rpos / w);
+  // ---- stage this cluster's tables: count its irregular cells and runs, give them local numbers ----
+  bool shared_ok = !broken && budget > 0;
+  const int *cells = grouped_id + offsets[c];
+  if (shared_ok) {
+    for (int k = tid; k < n; k += (int)blockDim.x) {
+      const int id = cells[k];
+      const int2 l = B.link[id];
+      if (l.x == -1) {
+        B.irr[l.y].pad[0] = atomicAdd(&s_nirr, 1);
+      } else if (l.x >= 0) {
+        const int4 ci = B.cinfo[id];
+        if (ci.y == 0) B.runs[ci.x + 5] = atomicAdd(&s_nrun, 1);  // the head cell numbers its run
+      }
+    }
+    __syncthreads();
+    shared_ok = (size_t)s_nirr * sizeof(SIrr) + (size_t)s_nrun * sizeof(SHdr) <= (size_t)budget;
+  }
+  SharedStore SS;
+  SS.irr = reinterpret_cast<SIrr *>(s_dyn);
+  SS.hd = reinterpret_cast<SHdr *>(s_dyn + (size_t)s_nirr * sizeof(SIrr));
+  if (shared_ok) {
+    for (int k = tid; k < n; k += (int)blockDim.x) {
+      const int id = cells[k];
+      const int2 l = B.link[id];
+      if (l.x == -1) {
+        const IrrRec *r = B.irr + l.y;
+        SIrr o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int2 v = r->nb[j];
+          if (v.x >= 0) v.x = __ldcg(B.runs + v.x + 5);                         // run base -> local run number
+          else if (v.x != INT_MIN) v.x = -1 - __ldcg(&B.irr[-1 - v.x].pad[0]);  // slot -> local irregular number
+          o.nb[j] = v;
+        }
+        o.cellpos = r->cellpos;
+        o.vis = 0;
+        SS.irr[__ldcg(&r->pad[0])] = o;
+      } else if (l.x >= 0) {
+        const int4 ci = B.cinfo[id];
+        if (ci.y == 0) {
+          const int *h = B.runs + ci.x;
+          SHdr o;
+          o.lo = 0;
+          o.hi = o.L = h[2];
+          o.out0 = __ldcg(&B.irr[h[3]].pad[0]);
+          o.out1 = __ldcg(&B.irr[h[4]].pad[0]);
+          o.rb = ci.x;
+          SS.hd[__ldcg(h + 5)] = o;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int out;
+    if (broken) out = -1;
+    else if (shared_ok) out = bfs_chain_walk(SS, s_items, item_cap, __ldcg(&B.irr[B.link[root].y].pad[0]), n, q, lane);
+    else out = bfs_chain_walk(GlobalStore{B}, s_items, item_cap, B.link[root].y, n, q, lane);
+    if (lane == 0) s_out = out;
+  }
+  __syncthreads();
+  if (s_out != n) {  // a level wider than the list (or, defensively, a count that does not add up): the literal replay takes it
+    if (tid == 0) {
+      fallback[blockIdx.x] = 1;
+      atomicAdd(&B.ctr[1], 1);
+    }
     return;
   }
-  __syncwarp();
+  // references -> cell positions
+  for (int i = tid; i < n; i += (int)blockDim.x) {
+    const int ref = q[i];
+    q[i] = ref >= 0 ? B.runs[ref] : shared_ok ? SS.irr[-1 - ref].cellpos : B.irr[-1 - ref].cellpos;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
   float cx, cy;
   ordered_centre(q, n, w, lane, &cx, &cy);
   if (lane == 0) {
@@ -1378,11 +1482,12 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   int *root_cellpos = reinterpret_cast<int *>(aux + off_rootpos);
   float *centre = reinterpret_cast<float *>(aux + off_centre);
 
-  // cell_cluster int[n] | grouped int[n] | BFS-order queue int[n]
-  AOS_CUDA_OK(c, c->cand_buf.reserve(sizeof(int) * 3 * (size_t)n));
+  // cell_cluster int[n] | grouped int[n] | BFS-order queue int[n] | grouped_id int[n]
+  AOS_CUDA_OK(c, c->cand_buf.reserve(sizeof(int) * 4 * (size_t)n));
   int *cell_cluster = c->cand_buf.as<int>();
   int *grouped = cell_cluster + n;
   int *queue = grouped + n;
+  int *grouped_id = queue + n;
   c->d_cell_cluster = cell_cluster;
   c->d_root_cellpos = root_cellpos;
 
@@ -1397,7 +1502,7 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
   AOS_CUDA_OK(c, cudaGetLastError());
   s = exclusive_scan_u32(c, offsets, (size_t)nc, c->cc_blocksum, d_tot + 2);
   if (s != AOS_OK) return s;
-  cc_group_kernel<<<grid_for(n, 256), 256, 0, st>>>(cell_cluster, cellpos, n, offsets, acc, grouped);
+  cc_group_kernel<<<grid_for(n, 256), 256, 0, st>>>(cell_cluster, cellpos, n, offsets, acc, grouped, grouped_id);
   ++c->launches;
 
   c->mark("cc_stats_group");
@@ -1489,9 +1594,40 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     c->mark("replay_prep");
     int item_cap = kItemCap;  // AOS_BFS_ITEM_CAP (tests): a narrower level list, so that some clusters take the fallback
     if (const char *e = getenv("AOS_BFS_ITEM_CAP")) item_cap = std::max(1, std::min(kItemCap, atoi(e)));
-    bfs_chain_kernel<<<(unsigned)total_jobs, 32, 0, st>>>(d_flagged, acc, offsets, root_cellpos, mask, prefix, P.pitch, P.w, B,
-                                                         item_cap, d_fallback, queue, centre);
-    ++c->launches;
+    // the walk stages a cluster's tables in shared memory (about 6 bytes per cell of a thinned row: 6 % irregular cells of 72
+    // bytes, as many run headers of 24): launches by size class, longest rows (sorted to the front) first; a cluster that needs
+    // more than its class provides walks on the global tables.  AOS_BFS_GLOBAL=1 (tests) switches the staging off.
+    const bool staged = getenv("AOS_BFS_GLOBAL") == nullptr;
+    const unsigned class_cells[3] = {16000u, 6000u, 1500u};  // clusters larger than this many cells ...
+    const int class_budget[3] = {160 << 10, 96 << 10, 48 << 10};  // ... get this much; the rest 16 KB
+    AOS_CUDA_OK(c, cudaFuncSetAttribute(bfs_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, class_budget[0]));
+    // the classes are independent launches: the few longest rows would otherwise serialise in front of the many short ones
+    AOS_CUDA_OK(c, cudaEventRecord(c->ev_fork, st));
+    bool forked[3] = {false, false, false};
+    size_t first = 0;
+    for (int k = 0; k < 4; ++k) {
+      size_t last = first;
+      while (last < total_jobs && (k == 3 || c->h_clusters[need[last]].size > (long long)class_cells[k])) ++last;
+      if (last > first) {
+        const int budget = staged ? (k == 3 ? 16 << 10 : class_budget[k]) : 0;
+        cudaStream_t ls = st;
+        if (k < 3) {
+          ls = c->aux[k];
+          AOS_CUDA_OK(c, cudaStreamWaitEvent(ls, c->ev_fork, 0));
+          forked[k] = true;
+        }
+        bfs_chain_kernel<<<(unsigned)(last - first), k < 2 ? 1024 : kChainThreads, budget, ls>>>(
+            d_flagged + first, acc, offsets, grouped_id, root_cellpos, mask, prefix, P.pitch, P.w, B, item_cap, budget,
+            d_fallback + first, queue, centre);
+        ++c->launches;
+      }
+      first = last;
+    }
+    for (int k = 0; k < 3; ++k)
+      if (forked[k]) {
+        AOS_CUDA_OK(c, cudaEventRecord(c->ev_join[k], c->aux[k]));
+        AOS_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join[k], 0));
+      }
     AOS_CUDA_OK(c, cudaGetLastError());
     c->mark("replay_bfs");
     cluster_finalize_kernel<<<(unsigned)total_jobs, kClThreads, 0, st>>>(P, acc, offsets, grouped, root_cellpos, min_length, d_flagged,

@@ -127,6 +127,11 @@ def test_literal_bfs_replay_equals_chain_walk(gpu_ctx, oracle, case, monkeypatch
     monkeypatch.setenv("AOS_BFS_ITEM_CAP", "2")
     gpu_ctx.seed_stage(pl, pts)
     assert_seed_parity(gpu_ctx, r, check_labels=False)
+    # the walk on the global tables (what a cluster too large for the shared-memory staging does)
+    monkeypatch.delenv("AOS_BFS_ITEM_CAP")
+    monkeypatch.setenv("AOS_BFS_GLOBAL", "1")
+    gpu_ctx.seed_stage(pl, pts)
+    assert_seed_parity(gpu_ctx, r, check_labels=False)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
