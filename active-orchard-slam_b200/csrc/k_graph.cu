@@ -65,7 +65,8 @@ enum : unsigned char { kUndecided = 0, kAccept = 1, kReject = 2 };
 // One round of the first-come merge over the facet-vertex slots (slot order == the order in which the
 // reference meets the points: edge e = (slot e, next slot) contributes its start, then its end).
 __global__ void boundary_round_kernel(const double2 *__restrict__ pts, int n, PointGrid g, volatile unsigned char *state,
-                                      const int *__restrict__ ovf_list, int n_ovf, int *pending_flag) {
+                                      const int *__restrict__ ovf_list, int n_ovf, const int *prev_flag, int *pending_flag) {
+  if (prev_flag && *prev_flag == 0) return;  // the previous round of this batch left nothing pending
   const double thr = 0.05;
   const double thr2 = thr * thr;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
@@ -860,14 +861,20 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
     set_error(c, "more than 4096 Voronoi vertices beyond +-2.1e7 m (integer-key overflow list full)");
     return AOS_ERR_CAPACITY;
   }
-  for (int round = 0; round < 100000; ++round) {
-    AOS_CUDA_OK(c, cudaMemsetAsync(d_cnt + 1, 0, 4, st));
-    boundary_round_kernel<<<blocks_for(K), 256, 0, st>>>(d_pts, K, g5, d_state, d_ovf, n_ovf, d_cnt + 1);
-  ++c->launches;
+  constexpr int kBoundaryBatch = 6;  // rounds per host synchronisation (a round exits at once when its predecessor was the last)
+  int *d_rflags = d_cnt + 32;
+  for (int batch = 0; batch < 100000; ++batch) {
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_rflags, 0, sizeof(int) * kBoundaryBatch, st));
+    for (int j = 0; j < kBoundaryBatch; ++j)
+      boundary_round_kernel<<<blocks_for(K), 256, 0, st>>>(d_pts, K, g5, d_state, d_ovf, n_ovf, j ? d_rflags + j - 1 : nullptr,
+                                                           d_rflags + j);
+    c->launches += kBoundaryBatch;
     AOS_CUDA_OK(c, cudaGetLastError());
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_cnt + 1, 4, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_rflags, sizeof(int) * kBoundaryBatch, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-    if (!c->h_flag[0]) break;
+    bool done = false;
+    for (int j = 0; j < kBoundaryBatch; ++j) done |= c->h_flag[j] == 0;
+    if (done) break;
   }
   flags_from_state_kernel<<<blocks_for(K), 256, 0, st>>>(d_state, K, d_scanA);
   ++c->launches;

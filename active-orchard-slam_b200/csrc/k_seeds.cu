@@ -274,10 +274,16 @@ __global__ void seed_grid_build_kernel(const double2 *__restrict__ pts, const un
   }
 }
 
-__global__ void seed_dedup_round_kernel(const double2 *__restrict__ pts, int n, PointGrid g, volatile unsigned char *state,
-                                        double radius, int *pending_flag) {
+// The three candidate lists (virtual seeds, ray points, end points) are filtered independently by the reference, each
+// against its own earlier points; they lie one behind the other in pts (boundaries b1, b2), so one set of rounds serves
+// all three: a point only looks at earlier points of its own list.  prev_flag (may be null): the previous round of the
+// same batch; a round whose predecessor left nothing pending exits at once, so the host synchronises once per batch.
+__global__ void seed_dedup_round_kernel(const double2 *__restrict__ pts, int n, int b1, int b2, PointGrid g,
+                                        volatile unsigned char *state, double radius, const int *prev_flag, int *pending_flag) {
+  if (prev_flag && *prev_flag == 0) return;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     if (state[v] != kSeedUndecided) continue;
+    const int first = v >= b2 ? b2 : v >= b1 ? b1 : 0;  // start of v's own list
     const double2 p = pts[v];
     const long long cx = cell_coord(p.x, g.inv), cy = cell_coord(p.y, g.inv);
     bool reject = false, pending = false;
@@ -286,7 +292,7 @@ __global__ void seed_dedup_round_kernel(const double2 *__restrict__ pts, int n, 
         int slot = hash_find(g.h, cell_key(cx + ox, cy + oy));
         if (slot < 0) continue;
         for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
-          if (u >= v) continue;
+          if (u >= v || u < first) continue;
           unsigned char su = state[u];
           if (su == kSeedReject) continue;
           double ex = pts[u].x - p.x, ey = pts[u].y - p.y;
@@ -325,35 +331,48 @@ inline unsigned pow2_at_least(size_t n) {
   return c;
 }
 
-// De-duplicates pts[0..n) in place of the reference's FirstComeSet; appends survivors (in order) to `out`.
-aos_status dedup_and_fetch(Ctx *c, double2 *d_pts, unsigned char *d_state, int n, PointGrid g, unsigned cap, uint32_t *d_scan,
-                           double2 *d_out, int *d_flag, uint32_t *d_tot, int *n_out) {
+// De-duplicates the three candidate lists pts[0..b1), [b1..b2), [b2..n) in place of the reference's FirstComeSets; the
+// survivors go to `out` in order, n_out[k] of list k.  d_flags: kRoundBatch ints; d_tot: 3 uint32.
+constexpr int kRoundBatch = 4;
+aos_status dedup_and_fetch(Ctx *c, double2 *d_pts, unsigned char *d_state, int n, int b1, int b2, PointGrid g, unsigned cap,
+                           uint32_t *d_scan, double2 *d_out, int *d_flags, uint32_t *d_tot, int n_out[3]) {
   cudaStream_t st = c->stream;
-  *n_out = 0;
+  n_out[0] = n_out[1] = n_out[2] = 0;
   if (n == 0) return AOS_OK;
   AOS_CUDA_OK(c, cudaMemsetAsync(g.h.keys, 0xff, sizeof(unsigned long long) * cap, st));
   AOS_CUDA_OK(c, cudaMemsetAsync(g.h.val, 0xff, sizeof(int) * cap, st));
   seed_grid_build_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, d_state, n, g);
   ++c->launches;
-  for (int round = 0; round < 100000; ++round) {
-    AOS_CUDA_OK(c, cudaMemsetAsync(d_flag, 0, 4, st));
-    seed_dedup_round_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, d_flag);
-    ++c->launches;
+  for (int batch = 0; batch < 100000; ++batch) {
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_flags, 0, sizeof(int) * kRoundBatch, st));
+    for (int j = 0; j < kRoundBatch; ++j)
+      seed_dedup_round_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, n, b1, b2, g, d_state, 0.5, j ? d_flags + j - 1 : nullptr,
+                                                             d_flags + j);
+    c->launches += kRoundBatch;
     AOS_CUDA_OK(c, cudaGetLastError());
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_flags, sizeof(int) * kRoundBatch, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-    if (!c->h_flag[0]) break;
+    bool done = false;
+    for (int j = 0; j < kRoundBatch; ++j) done |= c->h_flag[j] == 0;  // a round that left nothing pending
+    if (done) break;
   }
   seed_flags_kernel<<<blocks_for(n), 256, 0, st>>>(d_state, n, d_scan);
   ++c->launches;
-  aos_status s = exclusive_scan_u32(c, d_scan, (size_t)n, c->cc_blocksum, d_tot);
+  aos_status s = exclusive_scan_u32(c, d_scan, (size_t)n, c->cc_blocksum, d_tot + 2);  // total of all three
   if (s != AOS_OK) return s;
   seed_emit_kernel<<<blocks_for(n), 256, 0, st>>>(d_pts, d_state, d_scan, n, d_out);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
-  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
+  // survivors before b1, before b2, in all: the exclusive scan at the list boundaries
+  if (b1 < n) AOS_CUDA_OK(c, cudaMemcpyAsync(d_tot, d_scan + b1, 4, cudaMemcpyDeviceToDevice, st));
+  if (b2 < n) AOS_CUDA_OK(c, cudaMemcpyAsync(d_tot + 1, d_scan + b2, 4, cudaMemcpyDeviceToDevice, st));
+  AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 12, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-  *n_out = c->h_flag[0];
+  const int total = c->h_flag[2];
+  const int upto1 = b1 < n ? c->h_flag[0] : total, upto2 = b2 < n ? c->h_flag[1] : total;
+  n_out[0] = upto1;
+  n_out[1] = upto2 - upto1;
+  n_out[2] = total - upto2;
   return AOS_OK;
 }
 }  // namespace
@@ -373,7 +392,8 @@ __global__ void merge_init_kernel(const double2 *__restrict__ pts, int n, unsign
 }
 
 __global__ void merge_round_kernel(const double2 *__restrict__ pts, int n, PointGrid g, volatile unsigned char *state,
-                                   double radius, int *pending_flag) {
+                                   double radius, const int *prev_flag, int *pending_flag) {
+  if (prev_flag && *prev_flag == 0) return;  // the previous round of this batch left nothing pending
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     if (state[v] != kSeedUndecided) continue;
     const double2 p = pts[v];
@@ -472,7 +492,7 @@ aos_status device_select_seeds(Ctx *c) {
     hr[i] = RowDev{r.center_x, r.center_y, r.start_x, r.start_y, r.end_x, r.end_y};
   }
   // device memory, part 1: rows + counts
-  AOS_CUDA_OK(c, c->seed_buf.reserve(sizeof(RowDev) * (size_t)n_rows + sizeof(uint32_t) * ((size_t)n_rows + 8) + 4096));
+  AOS_CUDA_OK(c, c->seed_buf.reserve(sizeof(RowDev) * (size_t)n_rows + sizeof(uint32_t) * ((size_t)n_rows + 16) + 4096));
   RowDev *d_rows = c->seed_buf.as<RowDev>();
   uint32_t *d_offs = reinterpret_cast<uint32_t *>(d_rows + n_rows);
   uint32_t *d_tot = d_offs + n_rows + 2;  // [0..3] totals, [4] pending flag
@@ -487,7 +507,7 @@ aos_status device_select_seeds(Ctx *c) {
   AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_tot, 4, cudaMemcpyDeviceToHost, st));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
   const int n_virt = c->h_flag[0], n_ray = 6 * n_rows, n_end = 2 * n_rows;
-  const int n_max = std::max(n_virt, n_ray);
+  const int n_max = n_virt + n_ray + n_end;  // the three lists are filtered in one pass
 
   // part 2: candidates
   const unsigned cap = pow2_at_least((size_t)n_max * 2);
@@ -556,12 +576,8 @@ aos_status device_select_seeds(Ctx *c) {
   AOS_CUDA_OK(c, cudaGetLastError());
 
   int counts[3] = {0, 0, 0};
-  int *d_flag = reinterpret_cast<int *>(d_tot + 4);
-  s = dedup_and_fetch(c, d_vpts, d_vst, n_virt, g, cap, d_scan, d_out, d_flag, d_tot + 1, &counts[0]);
-  if (s != AOS_OK) return s;
-  s = dedup_and_fetch(c, d_rpts, d_rst, n_ray, g, cap, d_scan, d_out + counts[0], d_flag, d_tot + 2, &counts[1]);
-  if (s != AOS_OK) return s;
-  s = dedup_and_fetch(c, d_epts, d_est, n_end, g, cap, d_scan, d_out + counts[0] + counts[1], d_flag, d_tot + 3, &counts[2]);
+  int *d_flags = reinterpret_cast<int *>(d_tot + 4);  // kRoundBatch ints
+  s = dedup_and_fetch(c, d_pts, d_state, (int)n_all, n_virt, n_virt + n_ray, g, cap, d_scan, d_out, d_flags, d_tot + 1, counts);
   if (s != AOS_OK) return s;
   const int total = counts[0] + counts[1] + counts[2];
   if (!c->h_seeds.resize(2 * (size_t)total)) {
@@ -625,14 +641,17 @@ aos_status device_merge_seeds(Ctx *c, const double *seeds, int n) {
   ++c->launches;
   seed_grid_build_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, d_state, n, g);
   ++c->launches;
-  for (int round = 0; round < 100000; ++round) {
-    AOS_CUDA_OK(c, cudaMemsetAsync(d_flag, 0, 4, st));
-    merge_round_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, d_flag);
-    ++c->launches;
+  for (int batch = 0; batch < 100000; ++batch) {  // kRoundBatch rounds per host synchronisation
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_flag, 0, sizeof(int) * kRoundBatch, st));
+    for (int j = 0; j < kRoundBatch; ++j)
+      merge_round_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, j ? d_flag + j - 1 : nullptr, d_flag + j);
+    c->launches += kRoundBatch;
     AOS_CUDA_OK(c, cudaGetLastError());
-    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(c->h_flag, d_flag, sizeof(int) * kRoundBatch, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaStreamSynchronize(st));
-    if (!c->h_flag[0]) break;
+    bool done = false;
+    for (int j = 0; j < kRoundBatch; ++j) done |= c->h_flag[j] == 0;
+    if (done) break;
   }
   merge_owner_kernel<<<blocks_for(N), 256, 0, st>>>(d_pts, n, g, d_state, 0.5, d_owner);
   ++c->launches;
