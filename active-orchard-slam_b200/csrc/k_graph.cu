@@ -589,24 +589,43 @@ __global__ void corner_kernel(const double *__restrict__ rows, CornerParams P, c
     const CornerJob J = corner_job(rows, job);
     double best = DBL_MAX;
     int best_i = -1;
-    // block of cells covering radius 9 m around the endpoint
+    // block of cells covering radius 9 m around the endpoint (rungs 5, 7, 9 apply even on grids whose diagonal is shorter),
+    // searched in growing square shells of the 0.5 m grid: a node in a cell k or more cells away (in either axis) from
+    // the endpoint's cell is farther than (k - 1) cells, so once the best admissible node is nearer than that the shells
+    // still to come cannot beat it (nor tie with it) -- usually after 3-4 m instead of the whole 18 m x 18 m block
     {
-      const double R = 9.0;  // rungs 5, 7, 9 apply even on grids whose diagonal is shorter
+      const double R = 9.0;
+      const double cs = 1.0 / g.inv;  // cell size
       const long long cx0 = cell_coord(J.endpoint.x - R, g.inv), cx1 = cell_coord(J.endpoint.x + R, g.inv);
       const long long cy0 = cell_coord(J.endpoint.y - R, g.inv), cy1 = cell_coord(J.endpoint.y + R, g.inv);
-      const long long nx = cx1 - cx0 + 1, total = nx * (cy1 - cy0 + 1);
-      for (long long c = lane; c < total; c += 32) {
-        int slot = hash_find(g.h, cell_key(cx0 + c % nx, cy0 + c / nx));
-        if (slot < 0) continue;
-        for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
-          double d = corner_candidate(nodes[u], J.endpoint, J.outx, J.outy, J.perpx, J.perpy, J.neg, J.pos, min_distance, R);
-          if (d >= 0.0 && (d < best || (d == best && u < best_i))) {
-            best = d;
-            best_i = u;
+      const long long ex = cell_coord(J.endpoint.x, g.inv), ey = cell_coord(J.endpoint.y, g.inv);
+      const int kmax = (int)max(max(ex - cx0, cx1 - ex), max(ey - cy0, cy1 - ey));
+      int k_done = -1;  // shells 0 .. k_done are searched
+      while (k_done < kmax) {
+        const int k_lo = k_done + 1, k_hi = min(kmax, k_done + 4);  // four shells per pass
+        // cells of the square of half-width k_hi that are not in the square of half-width k_done
+        const int side = 2 * k_hi + 1;
+        for (int c = lane; c < side * side; c += 32) {
+          const int ox = c % side - k_hi, oy = c / side - k_hi;
+          if (max(abs(ox), abs(oy)) < k_lo) continue;
+          const long long gx = ex + ox, gy = ey + oy;
+          if (gx < cx0 || gx > cx1 || gy < cy0 || gy > cy1) continue;
+          int slot = hash_find(g.h, cell_key(gx, gy));
+          if (slot < 0) continue;
+          for (int u = g.h.val[slot]; u >= 0; u = g.next[u]) {
+            double d = corner_candidate(nodes[u], J.endpoint, J.outx, J.outy, J.perpx, J.perpy, J.neg, J.pos, min_distance, R);
+            if (d >= 0.0 && (d < best || (d == best && u < best_i))) {
+              best = d;
+              best_i = u;
+            }
           }
         }
+        warp_argmin(best, best_i);
+        best = __shfl_sync(0xffffffffu, best, 0);
+        best_i = __shfl_sync(0xffffffffu, best_i, 0);
+        k_done = k_hi;
+        if (best_i >= 0 && best < (double)(k_done) * cs * 0.999) break;
       }
-      warp_argmin(best, best_i);
     }
     if (lane != 0) continue;
     if (best_i < 0 && last_radius > 9.0) {  // last rung of the ladder (2 x diagonal): all nodes, by a whole CTA
