@@ -294,26 +294,47 @@ __global__ void edge_key_kernel(const int *__restrict__ nn, const int *__restric
   }
 }
 
-// first occurrence of each key is tested against the skeleton; keep[e] = 1 for the edges the reference adds
-__global__ void edge_test_kernel(const int *__restrict__ nn, const int *__restrict__ enext, int n_edges, DevHash H,
-                                 int *__restrict__ accepted, const double2 *__restrict__ nodes, GridView g,
-                                 uint32_t *__restrict__ keep) {
+// first occurrence of each key is tested against the skeleton; keep[e] = 1 for the edges the reference adds.
+// Two steps: one THREAD per facet-vertex slot finds the slots that are the first occurrence of their node pair (a third of
+// them) and lists them; one WARP per listed slot samples its segment.  (A warp per slot spent most of its warps on the two
+// loads and the hash probe that say "not first".)
+__global__ void edge_first_kernel(const int *__restrict__ nn, const int *__restrict__ enext, int n_edges, DevHash H,
+                                  uint32_t *__restrict__ keep, int4 *__restrict__ list, int *__restrict__ n_list) {
+  const int lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_edges; base += gridDim.x * blockDim.x) {
+    const int e = base + lane;
+    bool first = false;
+    int a = -1, b = -1, slot = -1;
+    if (e < n_edges) {
+      keep[e] = 0u;
+      a = nn[e];
+      b = nn[enext[e]];
+      if (a >= 0 && b >= 0 && a != b) {
+        unsigned long long key = ((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned)max(a, b);
+        slot = hash_find(H, key);
+        first = slot >= 0 && H.val[slot] == e;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (!m) continue;
+    int at = 0;
+    if (lane == 0) at = atomicAdd(n_list, __popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (first) list[at + __popc(m & ((1u << lane) - 1u))] = make_int4(e, a, b, slot);
+  }
+}
+
+__global__ void edge_test_kernel(const int4 *__restrict__ list, const int *__restrict__ n_list, int *__restrict__ accepted,
+                                 const double2 *__restrict__ nodes, GridView g, uint32_t *__restrict__ keep) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_edges; e += warps) {
-    int a = nn[e], b = nn[enext[e]];
-    int slot = -1;
-    bool first = false;
-    if (a >= 0 && b >= 0 && a != b) {
-      unsigned long long key = ((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned)max(a, b);
-      slot = hash_find(H, key);
-      first = slot >= 0 && H.val[slot] == e;
-    }
-    bool k = false;
-    if (first) k = !warp_segment_hits(g, nodes[a], nodes[b], lane);  // warp-uniform branch
-    if (lane == 0) {
-      keep[e] = k ? 1u : 0u;
-      if (k) accepted[slot] = 1;
+  const int n = *n_list;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const int4 it = list[i];
+    const bool k = !warp_segment_hits(g, nodes[it.y], nodes[it.z], lane);
+    if (lane == 0 && k) {
+      keep[it.x] = 1u;
+      accepted[it.w] = 1;
     }
   }
 }
@@ -917,8 +938,16 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   edge_key_kernel<<<blocks_for(K), 256, 0, st>>>(d_nn, d_enext, K, H);
   ++c->launches;
   uint32_t *d_keep = d_scanB;  // K entries
-  edge_test_kernel<<<blocks_for((size_t)K * 32), 256, 0, st>>>(d_nn, d_enext, K, H, d_acc, d_nodes, gv, d_keep);
-  ++c->launches;
+  {
+    // list of first-occurrence slots: int4 per entry, at most K; lives in gvd_buf3 until the labels need that buffer
+    AOS_CUDA_OK(c, c->gvd_buf3.reserve(sizeof(int4) * ((size_t)K + 1) + 64));
+    int4 *d_list = c->gvd_buf3.as<int4>();
+    int *d_nlist = d_cnt + 40;
+    AOS_CUDA_OK(c, cudaMemsetAsync(d_nlist, 0, sizeof(int), st));
+    edge_first_kernel<<<blocks_for(K), 256, 0, st>>>(d_nn, d_enext, K, H, d_keep, d_list, d_nlist);
+    edge_test_kernel<<<blocks_for((size_t)K * 32 / 3), 256, 0, st>>>(d_list, d_nlist, d_acc, d_nodes, gv, d_keep);
+    c->launches += 2;
+  }
   AOS_CUDA_OK(c, cudaGetLastError());
   // positions of the kept edges: scan a copy (keep flags are still needed by the emit kernel)
   uint32_t *d_pos = reinterpret_cast<uint32_t *>(d_pts);  // pts are no longer needed after nearest_node: reuse (K * 16 B)
