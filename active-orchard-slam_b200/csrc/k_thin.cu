@@ -95,50 +95,63 @@ __global__ void __launch_bounds__(kThinThreads) thin_kernel(const __grid_constan
   if (cw == ((P.w - 1) >> 5)) xmask &= ~(1u << ((P.w - 1) & 31));
   const bool lane_owned = lane >= kTileLane0 && lane < kTileLane0 + kTileOwnW && cw >= 0;
   constexpr int kRowsPerWarp = kThinBox / (kThinThreads / 32);  // 16
-  const int r_begin = warp * kRowsPerWarp, r_end = r_begin + kRowsPerWarp;
-  int deleted_owned = 0;
+  const int r_begin = warp * kRowsPerWarp;
+  // Per warp, once: which of its 16 tile rows may lose pixels at all (the tile's first and last row lack a neighbour row,
+  // the image's first and last row are never thinned) and which count towards convergence.  The row loop below is fully
+  // unrolled, so these become one bit test per row instead of six compares.
+  uint32_t del_rows = 0, cnt_rows = 0;
+#pragma unroll
+  for (int j = 0; j < kRowsPerWarp; ++j) {
+    const int r = r_begin + j, y = y0 + r;
+    if (r > 0 && r < kThinBox - 1 && y + P.y_off > 0 && y + P.y_off < P.gh - 1) del_rows |= 1u << j;
+    if (r >= kSub && r < kSub + kThinOwn && y >= P.cnt_r0 && y < P.cnt_r1) cnt_rows |= 1u << j;
+  }
+  uint32_t dacc = 0;  // pixels deleted in counted rows during the last (0,1) pair of this launch
 
   int cur = 0;
 #pragma unroll 1
   for (int s = 0; s < kSub; ++s) {
-    const uint32_t *src = buf[cur];
-    uint32_t *out = buf[cur ^ 1];
+    const uint32_t *src = buf[cur] + sl;
+    uint32_t *out = buf[cur ^ 1] + sl;
     const int iter = s & 1;
+    // convergence = the LAST full (0,1) pair of this launch deleted nothing in the owned rows: that is the reference's
+    // stopping rule, and it spares the extra launch that would only confirm the fixed point
+    if (s == kSub - 2) dacc = 0;
     // sliding window over rows: (centre, west-neighbour plane, east-neighbour plane) of rows r-1, r, r+1
-    auto planes = [&](int r, uint32_t &c, uint32_t &wv, uint32_t &ev) {
-      c = (r >= 0 && r < kThinBox) ? src[r * kTileBoxW + sl] : 0u;
+    auto planes = [&](uint32_t c, uint32_t &wv, uint32_t &ev) {
       uint32_t l = __shfl_up_sync(0xffffffffu, c, 1), rr = __shfl_down_sync(0xffffffffu, c, 1);
       wv = __funnelshift_l(l, c, 1);   // bit i = pixel x-1
       ev = __funnelshift_r(c, rr, 1);  // bit i = pixel x+1
     };
     uint32_t nC, nW, nE, cC, cW, cE, sC, sW, sE;
-    planes(r_begin - 1, nC, nW, nE);
-    planes(r_begin, cC, cW, cE);
-    for (int r = r_begin; r < r_end; ++r) {
-      planes(r + 1, sC, sW, sE);
+    nC = r_begin > 0 ? src[(r_begin - 1) * kTileBoxW] : 0u;
+    planes(nC, nW, nE);
+    cC = src[r_begin * kTileBoxW];
+    planes(cC, cW, cE);
+#pragma unroll
+    for (int j = 0; j < kRowsPerWarp; ++j) {
+      const int r = r_begin + j;
+      if (j + 1 < kRowsPerWarp) sC = src[(r + 1) * kTileBoxW];
+      else sC = r + 1 < kThinBox ? src[(r + 1) * kTileBoxW] : 0u;
+      planes(sC, sW, sE);
       uint32_t res = cC;
-      if (r > 0 && r < kThinBox - 1) {
+      if ((del_rows >> j) & 1u) {
         // a pixel with all 8 neighbours set (or a zero pixel) cannot go: skip solid / empty stretches
         uint32_t boundary = cC & ~(nC & nW & nE & cW & cE & sC & sW & sE);
         if (__any_sync(0xffffffffu, boundary != 0)) {
-          const int y = y0 + r;
-          uint32_t del = zs_delete_mask(cC, nC, nE, cE, sE, sC, sW, cW, nW, iter);
-          del &= xmask;
-          if (y + P.y_off <= 0 || y + P.y_off >= P.gh - 1) del = 0;
+          uint32_t del = zs_delete_mask(cC, nC, nE, cE, sE, sC, sW, cW, nW, iter) & xmask;
           res = cC & ~del;
-          // convergence = the LAST full (0,1) pair of this launch deleted nothing in the owned rows: that is the
-          // reference's stopping rule, and it spares the extra launch that would only confirm the fixed point
-          if (s >= kSub - 2 && lane_owned && r >= kSub && r < kSub + kThinOwn && y >= P.cnt_r0 && y < P.cnt_r1)
-            deleted_owned |= (del != 0);
+          if ((cnt_rows >> j) & 1u) dacc |= del;
         }
       }
-      out[r * kTileBoxW + sl] = res;
+      out[r * kTileBoxW] = res;
       nC = cC; nW = cW; nE = cE;
       cC = sC; cW = sW; cE = sE;
     }
     cur ^= 1;
     __syncthreads();
   }
+  const int deleted_owned = lane_owned && dacc != 0;
   // write back the owned interior (rows kSub .. kSub+kThinOwn-1, lanes 1..30)
   const uint32_t *fin = buf[cur];
   for (int r = kSub + warp; r < kSub + kThinOwn; r += kThinThreads / 32) {
