@@ -547,9 +547,13 @@ aos_status device_select_seeds(Ctx *c) {
 
   double2 *d_vpts = d_pts, *d_rpts = d_pts + n_virt, *d_epts = d_rpts + n_ray;
   unsigned char *d_vst = d_state, *d_rst = d_state + n_virt, *d_est = d_rst + n_ray;
+  // the perpendicular rays of the virtual seeds and the endpoint rays are independent and both latency-bound: side by side
+  AOS_CUDA_OK(c, cudaEventRecord(c->ev_fork, st));
   if (n_virt > 0) {
-    vs_generate_kernel<<<blocks_for(n_virt, 128), 128, 0, st>>>(P, sg, d_rows, n_rows, d_offs, n_virt, d_vpts, d_vst);
+    AOS_CUDA_OK(c, cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
+    vs_generate_kernel<<<blocks_for(n_virt, 128), 128, 0, c->aux[0]>>>(P, sg, d_rows, n_rows, d_offs, n_virt, d_vpts, d_vst);
     ++c->launches;
+    AOS_CUDA_OK(c, cudaEventRecord(c->ev_join[0], c->aux[0]));
   }
   // the accumulated ray parameter 1.0 + 0.1 + 0.1 + ... of castRayFromEndpoint (seed_gen:1840-1880), one addition at a time
   // as the reference performs them; the same for every ray, so it is built once and only ever extended
@@ -574,6 +578,7 @@ aos_status device_select_seeds(Ctx *c) {
                                                                          (int)c->ray_steps_dev, d_rpts, d_rst, d_epts, d_est);
   ++c->launches;
   AOS_CUDA_OK(c, cudaGetLastError());
+  if (n_virt > 0) AOS_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
 
   int counts[3] = {0, 0, 0};
   int *d_flags = reinterpret_cast<int *>(d_tot + 4);  // kRoundBatch ints
