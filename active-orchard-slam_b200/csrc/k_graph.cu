@@ -1046,6 +1046,27 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
     AOS_CUDA_OK(c, cudaGetLastError());
   }
   c->mark("gvd_crop");
+  // node coordinates and edges are final here: their way back to the host (18 of the 23 MB of a config-3 graph) starts now,
+  // on a side stream, beside the corner search and the labels
+  bool early_d2h = false;
+  if (!G.nodes_xyz.resize(3 * (size_t)N) || !G.edges.resize(2 * (size_t)NE) || !G.edge_lengths.resize(NE) ||
+      !G.edge_clearances.resize(NE)) {
+    set_error(c, "cudaHostAlloc failed for the graph result buffers");
+    return AOS_ERR_CUDA;
+  }
+  if (N > 0) {
+    cudaStream_t cs = c->aux[1];
+    AOS_CUDA_OK(c, cudaEventRecord(c->ev_fork, st));
+    AOS_CUDA_OK(c, cudaStreamWaitEvent(cs, c->ev_fork, 0));
+    AOS_CUDA_OK(c, cudaMemcpyAsync(G.nodes_xyz.data(), d_xyz, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, cs));
+    if (NE > 0) {
+      AOS_CUDA_OK(c, cudaMemcpyAsync(G.edges.data(), d_edges, sizeof(int32_t) * 2 * NE, cudaMemcpyDeviceToHost, cs));
+      AOS_CUDA_OK(c, cudaMemcpyAsync(G.edge_lengths.data(), d_len, sizeof(float) * NE, cudaMemcpyDeviceToHost, cs));
+      AOS_CUDA_OK(c, cudaMemcpyAsync(G.edge_clearances.data(), d_clr, sizeof(float) * NE, cudaMemcpyDeviceToHost, cs));
+    }
+    AOS_CUDA_OK(c, cudaEventRecord(c->ev_join[1], cs));
+    early_d2h = true;
+  }
 
   // ---- TL/TR/BL/BR corner nodes + labels ---------------------------------------------------------------
   if (!G.corner_points.resize((size_t)8 * n_rows)) return AOS_ERR_CUDA;
@@ -1108,15 +1129,12 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
   c->mark("gvd_corners_labels");
 
   // ---- results to the host (GvdGraph.msg arrays) -------------------------------------------------------
-  if (!G.nodes_xyz.resize(3 * (size_t)N) || !G.node_labels.resize(N) || !G.node_cluster_indices.resize(N) ||
-      !G.node_label_counts.resize(N) || !G.node_label_clusters.resize(n_label_entries) ||
-      !G.node_label_types.resize(n_label_entries) || !G.edges.resize(2 * (size_t)NE) || !G.edge_lengths.resize(NE) ||
-      !G.edge_clearances.resize(NE)) {
+  if (!G.node_labels.resize(N) || !G.node_cluster_indices.resize(N) || !G.node_label_counts.resize(N) ||
+      !G.node_label_clusters.resize(n_label_entries) || !G.node_label_types.resize(n_label_entries)) {
     set_error(c, "cudaHostAlloc failed for the graph result buffers");
     return AOS_ERR_CUDA;
   }
   if (N > 0) {
-    AOS_CUDA_OK(c, cudaMemcpyAsync(G.nodes_xyz.data(), d_xyz, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.node_labels.data(), d_labels, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.node_cluster_indices.data(), d_cidx, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.node_label_counts.data(), d_lcnt, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
@@ -1125,11 +1143,7 @@ aos_status run_graph(Ctx *c, const GraphInputs &in) {
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.node_label_clusters.data(), d_lcl, sizeof(int32_t) * n_label_entries, cudaMemcpyDeviceToHost, st));
     AOS_CUDA_OK(c, cudaMemcpyAsync(G.node_label_types.data(), d_lty, sizeof(int32_t) * n_label_entries, cudaMemcpyDeviceToHost, st));
   }
-  if (NE > 0) {
-    AOS_CUDA_OK(c, cudaMemcpyAsync(G.edges.data(), d_edges, sizeof(int32_t) * 2 * NE, cudaMemcpyDeviceToHost, st));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(G.edge_lengths.data(), d_len, sizeof(float) * NE, cudaMemcpyDeviceToHost, st));
-    AOS_CUDA_OK(c, cudaMemcpyAsync(G.edge_clearances.data(), d_clr, sizeof(float) * NE, cudaMemcpyDeviceToHost, st));
-  }
+  if (early_d2h) AOS_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
   AOS_CUDA_OK(c, cudaStreamSynchronize(st));
   c->mark("gvd_d2h");
   return AOS_OK;
