@@ -1002,23 +1002,46 @@ __global__ void bfs_link_init_kernel(int n, BfsBufs B) {
   }
 }
 
-// One round of pointer jumping, in place: an entry that reads its target before or after the target's own update composes
-// two true statements either way (8-byte entries are loaded and stored whole).  Finished entries cost one 8-byte read.
-__global__ void bfs_jump_kernel(int n, BfsBufs B, int round) {
-  if (round > 0 && B.ctr[4 + round - 1] == 0) return;  // the previous round changed nothing
-  bool unfinished = false;
-  const unsigned total = 2u * (unsigned)n;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    uint2 st = __ldcg(B.state + idx);
-    if (st.y & kDone) continue;
+// Pointer jumping, in place: an entry that reads its target before or after the target's own update composes two true
+// statements either way (8-byte entries are loaded and stored whole).  Round 0 visits every entry and hops up to eight
+// times; runs are short on average (one irregular cell per ~16 chain cells), so most entries arrive at once.  The ones
+// that do not (entries of long runs) are listed -- in B.runs, which the ranking does not need yet -- and the following
+// rounds only walk that list, four hops each.
+__device__ __forceinline__ bool bfs_hop(BfsBufs &B, unsigned idx, int hops) {
+  uint2 st = __ldcg(B.state + idx);
+  if (st.y & kDone) return true;
 #pragma unroll 1
-    for (int hop = 0; hop < 4 && !(st.y & kDone); ++hop) {  // a few hops per round: the chains shorten under way
-      const uint2 st2 = __ldcg(B.state + st.x);
-      st = make_uint2(st2.x, st.y + st2.y);  // the target's kDone bit carries over: its x is the run's end
-    }
-    __stcg(B.state + idx, st);
-    unfinished |= !(st.y & kDone);
+  for (int hop = 0; hop < hops && !(st.y & kDone); ++hop) {
+    const uint2 st2 = __ldcg(B.state + st.x);
+    st = make_uint2(st2.x, st.y + st2.y);  // the target's kDone bit carries over: its x is the run's end
   }
+  __stcg(B.state + idx, st);
+  return (st.y & kDone) != 0;
+}
+
+__global__ void bfs_jump_first_kernel(int n, BfsBufs B) {
+  const unsigned total = 2u * (unsigned)n;
+  const int lane = threadIdx.x & 31;
+  unsigned *list = reinterpret_cast<unsigned *>(B.runs);
+  for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < total; base += gridDim.x * blockDim.x) {
+    const unsigned idx = base + lane;
+    const bool open = idx < total && !bfs_hop(B, idx, 8);
+    const unsigned m = __ballot_sync(0xffffffffu, open);
+    if (!m) continue;
+    int at = 0;
+    if (lane == 0) at = atomicAdd(&B.ctr[40], __popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (open) list[at + __popc(m & ((1u << lane) - 1u))] = idx;  // at most 2 n entries: B.runs holds 3 n ints
+  }
+}
+
+__global__ void bfs_jump_kernel(BfsBufs B, int round) {
+  if (round > 0 && B.ctr[4 + round - 1] == 0) return;  // the previous round left nothing open
+  const unsigned *list = reinterpret_cast<const unsigned *>(B.runs);
+  const unsigned total = (unsigned)B.ctr[40];
+  bool unfinished = false;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    unfinished |= !bfs_hop(B, list[t], 4);
   if (__syncthreads_or(unfinished) && threadIdx.x == 0) B.ctr[4 + round] = 1;  // one store per CTA, not per entry
 }
 
@@ -1585,11 +1608,12 @@ aos_status run_clusters(Ctx *c, const SeedDeviceParams &P, const uint32_t *skel,
     int rounds = 1;
     for (unsigned long long reach = 5; reach < max_need; reach *= 5) ++rounds;
     rounds += 2;
-    for (int r = 0; r < rounds; ++r) bfs_jump_kernel<<<grid_for(2 * nn, 256), 256, 0, st>>>(n, B, r);
+    bfs_jump_first_kernel<<<grid_for(2 * nn, 256), 256, 0, st>>>(n, B);
+    for (int r = 0; r < rounds; ++r) bfs_jump_kernel<<<4 * kNumSMs, 256, 0, st>>>(B, r);
     bfs_runs_kernel<<<gb, 256, 0, st>>>(n, B);
     bfs_scatter_kernel<<<gb, 256, 0, st>>>(n, cellpos, B);
     bfs_irr_kernel<<<gb, 256, 0, st>>>(n, B);
-    c->launches += rounds + 3;
+    c->launches += rounds + 4;
     AOS_CUDA_OK(c, cudaGetLastError());
     c->mark("replay_prep");
     int item_cap = kItemCap;  // AOS_BFS_ITEM_CAP (tests): a narrower level list, so that some clusters take the fallback
