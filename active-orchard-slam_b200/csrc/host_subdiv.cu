@@ -178,59 +178,61 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
     edx = d.x - pxd;
     edy = d.y - pyd;
   }
-  auto sgn = [](double cw) { return (cw > 0) - (cw < 0); };
-  int right_of_curr = sgn(edx * eoy - edy * eox);
-  if (right_of_curr > 0) {
-    edge ^= 2u;
-    std::swap(eox, edx);
-    std::swap(eoy, edy);
-    right_of_curr = -right_of_curr;
+  // isRightOf(p, edge) enters the walk's decisions only through "is it zero"; its sign is fixed by the walk (p is never
+  // to the right of the current edge)
+  bool on_curr;  // right_of_curr == 0
+  {
+    const double cw = edx * eoy - edy * eox;
+    on_curr = cw == 0;
+    if (cw > 0) {
+      edge ^= 2u;
+      std::swap(eox, edx);
+      std::swap(eoy, edy);
+    }
   }
+  // One step of cv::Subdiv2D::locate with the tests in the order that needs the fewest loads: with p not to the right
+  // of Onext(edge) and off the current edge the walk moves on to Onext whatever Dprev says (more than half of the
+  // steps), so Dprev(edge) = InvRot(next[InvRot edge]) and its origin are only fetched when p is to the right of Onext
+  // (or lies on the current edge).  Same moves, same stop, same number of steps as the literal if-chain.
   for (int i = 0; i < max_edges; ++i) {
     const U32 onext = nx[edge];
-    U32 dprev = nx[(edge & ~3u) | ((edge + 3u) & 3u)];  // Dprev(e) = InvRot(next[InvRot e])
-    dprev = (dprev & ~3u) | ((dprev + 3u) & 3u);
-    const Vertex &c1 = vd[pt[onext ^ 2]], &c2 = vd[pt[dprev]];
-    const double e1x = c1.x - pxd, e1y = c1.y - pyd, e2x = c2.x - pxd, e2y = c2.y - pyd;
-    const int right_of_onext = sgn(e1x * eoy - e1y * eox);
-    const int right_of_dprev = sgn(edx * e2y - edy * e2x);
-    if (right_of_dprev > 0) {
-      if (right_of_onext > 0 || (right_of_onext == 0 && right_of_curr == 0)) {
-        location = LOC_INSIDE;
-        break;
-      }
-      right_of_curr = right_of_onext;
-      edge = onext;
-      edx = e1x;
-      edy = e1y;
-    } else {
-      if (right_of_onext > 0) {
-        if (right_of_dprev == 0 && right_of_curr == 0) {
+    const Vertex &c1 = vd[pt[onext ^ 2]];
+    const double e1x = c1.x - pxd, e1y = c1.y - pyd;
+    const double cw_onext = e1x * eoy - e1y * eox;  // sign = isRightOf(p, onext)
+    if (cw_onext > 0 || on_curr) {
+      U32 dprev = nx[(edge & ~3u) | ((edge + 3u) & 3u)];
+      dprev = (dprev & ~3u) | ((dprev + 3u) & 3u);
+      const Vertex &c2 = vd[pt[dprev]];
+      const double e2x = c2.x - pxd, e2y = c2.y - pyd;
+      const double cw_dprev = edx * e2y - edy * e2x;  // sign = isRightOf(p, dprev)
+      if (cw_onext > 0) {
+        if (cw_dprev > 0 || (cw_dprev == 0 && on_curr)) {
           location = LOC_INSIDE;
           break;
         }
-        right_of_curr = right_of_dprev;
+        on_curr = cw_dprev == 0;
         edge = dprev;
         eox = e2x;
         eoy = e2y;
-      } else if (right_of_curr == 0) {
-        if (right_of(c1.x, c1.y, edge) >= 0) {
-          edge ^= 2u;
-          std::swap(eox, edx);
-          std::swap(eoy, edy);
-        } else {
-          right_of_curr = right_of_onext;
-          edge = onext;
-          edx = e1x;
-          edy = e1y;
+        continue;
+      }
+      // p lies on the current edge and is not to the right of Onext
+      if (cw_dprev > 0) {
+        if (cw_onext == 0) {
+          location = LOC_INSIDE;
+          break;
         }
-      } else {
-        right_of_curr = right_of_onext;
-        edge = onext;
-        edx = e1x;
-        edy = e1y;
+      } else if (right_of(c1.x, c1.y, edge) >= 0) {
+        edge ^= 2u;
+        std::swap(eox, edx);
+        std::swap(eoy, edy);
+        continue;
       }
     }
+    on_curr = cw_onext == 0;
+    edge = onext;
+    edx = e1x;
+    edy = e1y;
   }
   recent_ = (int)edge;
   int edge_out = (int)edge;
@@ -286,15 +288,61 @@ int Subdiv::insert(float px, float py) {
     curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
   } while (dst(curr_edge) != first_point);
   curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
-  flip_around(curr_edge, first_point, px, py);
+  flip_around(curr_edge, first_point, curr_point, px, py);
   return curr_point;
 }
 
-// The Lawson flips around the new point (the second loop of cv::Subdiv2D::insert): same tests, same order, same
-// splices.  Hot loop of the whole gvd half (about 55 flips per seed for seeds sorted along rows), so it works on raw
-// pointers (no re-loading of the vectors' data pointers after every store) and re-uses the orientation determinant
-// that isRightOf and isPtInCircle3 share.
-void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
+// The Lawson flips around the new point (the second loop of cv::Subdiv2D::insert), literally: the reference form of the
+// loop below, taken when aos_set_subdiv_literal_splices is on (tests compare the two).
+void Subdiv::flip_around_literal(int curr_edge, int first_point, int curr_point, float px, float py) {
+  const int max_edges = (int)next_.size();
+  const double eps = FLT_EPSILON * 0.125;
+  const Vertex &p = vtx_[curr_point];
+  (void)px, (void)py;
+  for (int i = 0; i < max_edges; ++i) {
+    const int temp_edge = get_edge(curr_edge, PREV_AROUND_ORG);
+    const int temp_dst = dst(temp_edge), curr_org = org(curr_edge), curr_dst = dst(curr_edge);
+    const Vertex &t = vtx_[temp_dst], &o = vtx_[curr_org], &d = vtx_[curr_dst];
+    // isPtInCircle3(pt = org, a = t, b = dst, c = p)
+    double val = t.n2 * tri_aread(d.x, d.y, p.x, p.y, o.x, o.y);
+    val -= d.n2 * tri_aread(t.x, t.y, p.x, p.y, o.x, o.y);
+    val += p.n2 * tri_aread(t.x, t.y, d.x, d.y, o.x, o.y);
+    val -= o.n2 * tri_aread(t.x, t.y, d.x, d.y, p.x, p.y);
+    if (tri_aread(t.x, t.y, d.x, d.y, o.x, o.y) > 0 && val < -eps) {  // isRightOf(t, curr_edge) > 0 && inside
+      // swapEdges(curr_edge)
+      const int sedge = curr_edge ^ 2;
+      const int a = get_edge(curr_edge, PREV_AROUND_ORG), b = get_edge(sedge, PREV_AROUND_ORG);
+      splice(curr_edge, a);
+      splice(sedge, b);
+      set_edge_points(curr_edge, dst(a), dst(b));
+      splice(curr_edge, get_edge(a, NEXT_AROUND_LEFT));
+      splice(sedge, get_edge(b, NEXT_AROUND_LEFT));
+      curr_edge = get_edge(curr_edge, PREV_AROUND_ORG);
+    } else if (curr_org == first_point) {
+      break;
+    } else {
+      curr_edge = get_edge(next_[curr_edge], PREV_AROUND_LEFT);
+    }
+  }
+}
+
+// The same loop as the replay runs it: same tests, same order, same final stores.  Hot loop of the whole gvd half
+// (seeds sorted along rows: about 46 flips and 95 iterations per seed, 70 % of the replay's time), and bound by the
+// number of instructions it retires, so everything an iteration can know without a load is carried in registers:
+//   * e = (o -> d) always has the new point p to its left (loop invariant of cv::Subdiv2D::insert), so
+//     Oprev(Sym e) = (d -> p): the flipped edge's new destination is p itself, no load;
+//   * after a flip the loop continues with Oprev(e) = (t -> d): the origin becomes the apex t, the destination
+//     and its coordinates stay; after a step without flip with Lprev(Onext(e)), which ends at the old origin;
+//   * rot e is carried (Rot Rot = Sym spares the mask arithmetic after a flip).
+// swapEdges' four splices touch twelve `next` slots whose final values follow from the initial ones (DESIGN.md
+// section 4, "Host hot loop"); every face of the subdivision is a triangle whenever this loop runs (insert() has
+// connected p to every corner of the face it fell into, and a flip maps two triangles to two triangles), which gives
+// the ring identities Onext(e) = Sym Lnext(b), Onext(Sym e) = Sym Lnext(a) used below: five loads and sixteen stores
+// per flip.  With Q = next[rot e], Q2 = next[rot Sym e], U = next[Q], U2 = next[Q2]:
+//   a = Oprev(e) = rot Q, b = Oprev(Sym e) = rot Q2, InvRot a = Q, InvRot b = Q2, la = Lnext(a) = rot U,
+//   lb = Lnext(b) = rot U2, rot Onext(Sym e) = U, rot Onext(e) = U2.
+void Subdiv::flip_around(int curr_edge_i, int first_point, int curr_point, float px, float py) {
+  if (g_literal_splices) return flip_around_literal(curr_edge_i, first_point, curr_point, px, py);
   // edge ids and vertex ids are non-negative: unsigned arithmetic keeps the index computations free of sign extensions
   typedef unsigned U32;
   U32 *const nx = reinterpret_cast<U32 *>(next_.data());
@@ -302,21 +350,11 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
   Vertex *const vd = vtx_.data();
   const int max_edges = (int)next_.size();
   auto rot = [](U32 e) -> U32 { return (e & ~3u) | ((e + 1u) & 3u); };
-  auto splice_raw = [nx, rot](U32 a, U32 b) {
-    U32 &a_next = nx[a];
-    U32 &b_next = nx[b];
-    U32 &a_rot_next = nx[rot(a_next)];
-    U32 &b_rot_next = nx[rot(b_next)];
-    std::swap(a_next, b_next);
-    std::swap(a_rot_next, b_rot_next);
-  };
   const double pxx = (double)px * px + (double)py * py;
   const double pxd = px, pyd = py;
   const double eps = FLT_EPSILON * 0.125;
-  const bool fused = !g_literal_splices;
-  U32 e = (U32)curr_edge_i;
-  // The end points of e are carried from iteration to iteration (ring invariants: Oprev(e) shares e's origin, and the
-  // next link edge Lprev(Onext(e)) ends where e starts), so an iteration loads one or two vertices, not three.
+  const U32 np = (U32)curr_point;
+  U32 e = (U32)curr_edge_i, re = rot(e);
   U32 curr_org = pt[e];
   double ox, oy, on2, dx, dy, dn2;
   {
@@ -325,12 +363,9 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
     dx = d.x, dy = d.y, dn2 = d.n2;
   }
   for (int i = 0; i < max_edges; ++i) {
-    // a = Oprev(e) = rot(next[rot e])
-    const U32 re = rot(e), Q = nx[re], a = rot(Q);
+    const U32 Q = nx[re], a = rot(Q);  // a = Oprev(e) = rot(next[rot e])
     const U32 temp_dst = pt[a ^ 2u];
     const Vertex &t = vd[temp_dst];
-    const U32 rs_h = re ^ 2u;
-    const U32 Q2_h = nx[rs_h], Uu_h = nx[Q], c_h = nx[e], dd_h = nx[e ^ 2u];  // the flip path's first loads, issued early
     const double tx = t.x, ty = t.y, tn2 = t.n2;
     // isRightOf(t, e) = sign of triangleArea(t, dst, org); the same determinant is the third term of
     // isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated unconditionally: one branch for both tests
@@ -340,64 +375,38 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, float px, float py) {
     val += pxx * area_tdo;
     val -= on2 * tri_aread(tx, ty, dx, dy, pxd, pyd);
     if ((area_tdo > 0) & (val < -eps)) {
-      // swapEdges(e): splice(e, a); splice(s, b); setEdgePoints(e, dst(a), dst(b)); splice(e, Lnext(a));
-      // splice(s, Lnext(b)) with s = Sym e, a = Oprev(e), b = Oprev(s).  In a triangulation the four splices touch
-      // twelve `next` slots whose final values follow from the initial ones ("Host hot loop");
-      // they are read once and written once.  Ring identities spare most of the rotations: with Q = next[rot e],
-      // Q2 = next[rot s], U = next[Q], U2 = next[Q2]:  a = rot Q, b = rot Q2, InvRot a = Q, InvRot b = Q2,
-      // Lnext-side edges la = rot U, lb = rot U2, and -- once the guards hold (la = Sym d, lb = Sym c) -- rot d = U,
-      // rot c = U2.  The guards check the local structure the derivation assumes (that both faces are triangles;
-      // next[a] == e and next[b] == s are identities of the edge algebra and are not re-checked); anything else takes
-      // the literal splice sequence.
-      const U32 s = e ^ 2u, rs = rs_h;
-      const U32 Q2 = Q2_h, b = rot(Q2);
-      const U32 c = c_h, dd = dd_h;
-      const U32 Uu = Uu_h, U2 = nx[Q2];
-      const U32 la = rot(Uu), lb = rot(U2);
-      const U32 no = pt[a ^ 2u], nd = pt[b ^ 2u];
-      if (fused & (la == (dd ^ 2u)) & (lb == (c ^ 2u)) & (nx[la] == (a ^ 2u)) & (nx[lb] == (b ^ 2u))) {
-        const U32 P = nx[U2], P2 = nx[Uu];  // slots rot c, rot d
-        nx[e] = a ^ 2u;
-        nx[a] = c;
-        nx[la] = e;
-        nx[s] = b ^ 2u;
-        nx[b] = dd;
-        nx[lb] = s;
-        nx[U2] = Q;   // rot c
-        nx[re] = Uu;
-        nx[Q] = P;    // InvRot a
-        nx[Uu] = Q2;  // rot d
-        nx[rs] = U2;
-        nx[Q2] = P2;  // InvRot b
-        pt[e] = no;
-        pt[s] = nd;
-        vd[no].first_edge = (int)e;
-        vd[nd].first_edge = (int)s;
-        e = la;  // == Oprev(e) after the flip: rot(next[rot e]) with next[rot e] = U
-        curr_org = no;  // Oprev shares the origin of the flipped edge, which now starts at dst(a) = t
-        ox = tx, oy = ty, on2 = tn2;
-        const Vertex &d = vd[pt[e ^ 2u]];
-        dx = d.x, dy = d.y, dn2 = d.n2;
-      } else {
-        splice_raw(e, a);
-        splice_raw(s, b);
-        pt[e] = no;
-        pt[s] = nd;
-        vd[no].first_edge = (int)e;
-        vd[nd].first_edge = (int)s;
-        // Lnext(x) = rot(next[InvRot x]) with InvRot a = Q, InvRot b = Q2 read AFTER the first two splices
-        splice_raw(e, rot(nx[Q]));
-        splice_raw(s, rot(nx[Q2]));
-        e = rot(nx[rot(e)]);
-        curr_org = pt[e];
-        const Vertex &o = vd[curr_org], &d = vd[pt[e ^ 2u]];
-        ox = o.x, oy = o.y, on2 = o.n2;
-        dx = d.x, dy = d.y, dn2 = d.n2;
-      }
+      // loads and stores in an order that lets every value die early (the twelve slots are distinct: six edges of
+      // the two triangles and six of their duals)
+      const U32 rs = re ^ 2u;
+      const U32 Q2 = nx[rs], Uu = nx[Q], U2 = nx[Q2];
+      const U32 P = nx[U2];  // the slot rot Onext(e)
+      nx[U2] = Q;
+      nx[re] = Uu;
+      nx[Q] = P;
+      const U32 P2 = nx[Uu];  // the slot rot Onext(Sym e)
+      nx[Uu] = Q2;
+      nx[rs] = U2;
+      nx[Q2] = P2;
+      const U32 s = e ^ 2u, b = rot(Q2), la = rot(Uu), lb = rot(U2);
+      nx[e] = a ^ 2u;
+      nx[a] = lb ^ 2u;  // Onext(e)
+      nx[lb] = s;
+      nx[s] = b ^ 2u;
+      nx[b] = la ^ 2u;  // Onext(Sym e)
+      nx[la] = e;
+      pt[e] = temp_dst;
+      pt[s] = np;
+      vd[temp_dst].first_edge = (int)e;
+      vd[np].first_edge = (int)s;
+      e = la;  // == Oprev(e) after the flip
+      re = Uu ^ 2u;
+      curr_org = temp_dst;
+      ox = tx, oy = ty, on2 = tn2;
     } else if (curr_org == (U32)first_point) {
       break;
     } else {
       e = nx[nx[e]] ^ 2u;  // Lprev(Onext(e)) = Sym(next[next[e]]): ends at the old origin
+      re = rot(e);
       dx = ox, dy = oy, dn2 = on2;
       curr_org = pt[e];
       const Vertex &o = vd[curr_org];

@@ -51,7 +51,8 @@ class Subdiv {
   void splice(int a, int b);
   void set_edge_points(int edge, int org, int dst);
   int connect_edges(int a, int b);
-  void flip_around(int curr_edge, int first_point, float px, float py);
+  void flip_around(int curr_edge, int first_point, int curr_point, float px, float py);
+  void flip_around_literal(int curr_edge, int first_point, int curr_point, float px, float py);
   int locate(float px, float py, int *edge, int *vertex);
   static bool voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y);
   void calc_voronoi();
