@@ -272,6 +272,10 @@ int Subdiv::insert(float px, float py) {
   int location = locate(px, py, &curr_edge, &curr_point);
   if (location == LOC_ERROR) return -1;  // cv::Exception; the reference skips the seed (voronoi_diagram.cpp:83-88)
   if (location == LOC_VERTEX) return curr_point;
+  if (location == LOC_INSIDE && free_q_ <= 0 && !g_literal_splices) {
+    const int p = connect_inside_triangle(curr_edge, px, py);
+    if (p > 0) return p;
+  }
   if (location == LOC_ON_EDGE) {
     int deleted = curr_edge;
     recent_ = curr_edge = get_edge(curr_edge, PREV_AROUND_ORG);
@@ -290,6 +294,52 @@ int Subdiv::insert(float px, float py) {
   curr_edge = get_edge(base_edge, PREV_AROUND_ORG);
   flip_around(curr_edge, first_point, curr_point, px, py);
   return curr_point;
+}
+
+// insert() between locate() and the flip loop for a point strictly inside a triangle, with the three new quads taken from
+// the end of the arrays (nothing on the free list): the new vertex p and its edges B0 = (o -> p), B1 = (d -> p),
+// B2 = (c -> p) in the triangle e0 = (o -> d), e1 = Lnext(e0) = (d -> c), e2 = Lnext(e1) = (c -> o).  new_edge,
+// splice(B0, e0) and the two connect_edges of the literal sequence leave 18 `next` slots with values that follow from
+// e0, e1, e2 alone, written here once:
+//   rings of o, d, c:   next[ei] = Bi,  next[Bi] = what next[ei] was = Sym(e(i-1))   (the face is a triangle)
+//   ring of p:          Sym B0 -> Sym B1 -> Sym B2 -> Sym B0
+//   faces (dual rings): next[InvRot x] = InvRot(Lnext x) around (e0, B1, Sym B0), (e1, B2, Sym B1), (e2, B0, Sym B2)
+// and first_edge of o, d, c, p as the three set_edge_points calls leave them.  Returns p, or 0 with nothing changed when
+// the face is not a triangle (never the case for a subdivision this class built; the literal sequence takes over).
+int Subdiv::connect_inside_triangle(int e0_i, float px, float py) {
+  typedef unsigned U32;
+  auto rot = [](U32 e) -> U32 { return (e & ~3u) | ((e + 1u) & 3u); };
+  auto invrot = [](U32 e) -> U32 { return (e & ~3u) | ((e + 3u) & 3u); };
+  const U32 e0 = (U32)e0_i, ir0 = invrot(e0);
+  {
+    const U32 *const nx = reinterpret_cast<const U32 *>(next_.data());
+    const U32 e1 = rot(nx[ir0]), e2 = rot(nx[invrot(e1)]);
+    if (rot(nx[invrot(e2)]) != e0) return 0;
+  }
+  valid_geometry_ = false;
+  const U32 p = (U32)new_point(px, py, false);
+  const U32 B0 = (U32)next_.size(), B1 = B0 + 4, B2 = B0 + 8;
+  next_.resize(B0 + 12, 0);
+  pt_.resize(B0 + 12, 0);  // pt of the dual edges stays 0, as new_edge leaves it
+  U32 *const nx = reinterpret_cast<U32 *>(next_.data());
+  U32 *const pt = reinterpret_cast<U32 *>(pt_.data());
+  Vertex *const vd = vtx_.data();
+  const U32 e1 = rot(nx[ir0]), ir1 = invrot(e1), e2 = rot(nx[ir1]), ir2 = invrot(e2);
+  const U32 o = pt[e0], d = pt[e1], c = pt[e2];
+  nx[e0] = B0, nx[e1] = B1, nx[e2] = B2;
+  nx[B0] = e2 ^ 2u, nx[B1] = e0 ^ 2u, nx[B2] = e1 ^ 2u;
+  nx[B0 + 2] = B1 + 2, nx[B1 + 2] = B2 + 2, nx[B2 + 2] = B0 + 2;
+  nx[ir0] = B1 + 3, nx[B1 + 3] = B0 + 1, nx[B0 + 1] = ir0;
+  nx[ir1] = B2 + 3, nx[B2 + 3] = B1 + 1, nx[B1 + 1] = ir1;
+  nx[ir2] = B0 + 3, nx[B0 + 3] = B2 + 1, nx[B2 + 1] = ir2;
+  pt[B0] = o, pt[B1] = d, pt[B2] = c;
+  pt[B0 + 2] = pt[B1 + 2] = pt[B2 + 2] = p;
+  vd[o].first_edge = (int)B0;
+  vd[d].first_edge = (int)B1;
+  vd[c].first_edge = (int)B2;
+  vd[p].first_edge = (int)(B2 + 2);
+  flip_around((int)e2, (int)o, (int)p, px, py);
+  return (int)p;
 }
 
 // The Lawson flips around the new point (the second loop of cv::Subdiv2D::insert), literally: the reference form of the
@@ -362,57 +412,92 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, int curr_point, float
     ox = o.x, oy = o.y, on2 = o.n2;
     dx = d.x, dy = d.y, dn2 = d.n2;
   }
-  for (int i = 0; i < max_edges; ++i) {
-    const U32 Q = nx[re], a = rot(Q);  // a = Oprev(e) = rot(next[rot e])
-    const U32 temp_dst = pt[a ^ 2u];
-    const Vertex &t = vd[temp_dst];
-    const double tx = t.x, ty = t.y, tn2 = t.n2;
-    // isRightOf(t, e) = sign of triangleArea(t, dst, org); the same determinant is the third term of
-    // isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated unconditionally: one branch for both tests
-    const double area_tdo = tri_aread(tx, ty, dx, dy, ox, oy);
-    double val = tn2 * tri_aread(dx, dy, pxd, pyd, ox, oy);
-    val -= dn2 * tri_aread(tx, ty, pxd, pyd, ox, oy);
-    val += pxx * area_tdo;
-    val -= on2 * tri_aread(tx, ty, dx, dy, pxd, pyd);
-    if ((area_tdo > 0) & (val < -eps)) {
-      // loads and stores in an order that lets every value die early (the twelve slots are distinct: six edges of
-      // the two triangles and six of their duals)
-      const U32 rs = re ^ 2u;
-      const U32 Q2 = nx[rs], Uu = nx[Q], U2 = nx[Q2];
-      const U32 P = nx[U2];  // the slot rot Onext(e)
-      nx[U2] = Q;
-      nx[re] = Uu;
-      nx[Q] = P;
-      const U32 P2 = nx[Uu];  // the slot rot Onext(Sym e)
-      nx[Uu] = Q2;
-      nx[rs] = U2;
-      nx[Q2] = P2;
-      const U32 s = e ^ 2u, b = rot(Q2), la = rot(Uu), lb = rot(U2);
-      nx[e] = a ^ 2u;
-      nx[a] = lb ^ 2u;  // Onext(e)
-      nx[lb] = s;
-      nx[s] = b ^ 2u;
-      nx[b] = la ^ 2u;  // Onext(Sym e)
-      nx[la] = e;
-      pt[e] = temp_dst;
-      pt[s] = np;
-      vd[temp_dst].first_edge = (int)e;
-      vd[np].first_edge = (int)s;
-      e = la;  // == Oprev(e) after the flip
-      re = Uu ^ 2u;
-      curr_org = temp_dst;
-      ox = tx, oy = ty, on2 = tn2;
-    } else if (curr_org == (U32)first_point) {
-      break;
-    } else {
-      e = nx[nx[e]] ^ 2u;  // Lprev(Onext(e)) = Sym(next[next[e]]): ends at the old origin
-      re = rot(e);
+  // One iteration's test: the apex t across e -- a = Oprev(e) = rot(next[rot e]), t = dst(a) -- and
+  // isRightOf(t, e) > 0 && isPtInCircle3(org, t, dst, p) < 0.  isRightOf is the sign of triangleArea(t, dst, org); the
+  // same determinant is the third term of isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated once.
+#define AOS_APEX_TEST                                                  \
+  const U32 Q = nx[re], a = rot(Q);                                    \
+  const U32 temp_dst = pt[a ^ 2u];                                     \
+  const Vertex &t = vd[temp_dst];                                      \
+  const double tx = t.x, ty = t.y, tn2 = t.n2;                         \
+  const double area_tdo = tri_aread(tx, ty, dx, dy, ox, oy);           \
+  double val = tn2 * tri_aread(dx, dy, pxd, pyd, ox, oy);              \
+  val -= dn2 * tri_aread(tx, ty, pxd, pyd, ox, oy);                    \
+  val += pxx * area_tdo;                                               \
+  val -= on2 * tri_aread(tx, ty, dx, dy, pxd, pyd);                    \
+  const bool do_flip = (area_tdo > 0) & (val < -eps)
+  // swapEdges(e) and curr_edge = Oprev(e).  Loads and stores in an order that lets every value die early (the twelve
+  // slots are distinct: six edges of the two triangles and six of their duals).  Leaves behind what the step after
+  // the next test needs if that test does not flip: fa = a, fQ = Q, f_org = the origin e had.
+#define AOS_FLIP                                                       \
+  {                                                                    \
+    const U32 rs = re ^ 2u;                                            \
+    const U32 Q2 = nx[rs], Uu = nx[Q], U2 = nx[Q2];                    \
+    const U32 P = nx[U2]; /* the slot rot Onext(e) */                  \
+    nx[U2] = Q;                                                        \
+    nx[re] = Uu;                                                       \
+    nx[Q] = P;                                                         \
+    const U32 P2 = nx[Uu]; /* the slot rot Onext(Sym e) */             \
+    nx[Uu] = Q2;                                                       \
+    nx[rs] = U2;                                                       \
+    nx[Q2] = P2;                                                       \
+    const U32 s = e ^ 2u, b = rot(Q2), la = rot(Uu), lb = rot(U2);     \
+    nx[e] = a ^ 2u;                                                    \
+    nx[a] = lb ^ 2u; /* Onext(e) */                                    \
+    nx[lb] = s;                                                        \
+    nx[s] = b ^ 2u;                                                    \
+    nx[b] = la ^ 2u; /* Onext(Sym e) */                                \
+    nx[la] = e;                                                        \
+    pt[e] = temp_dst;                                                  \
+    pt[s] = np;                                                        \
+    vd[temp_dst].first_edge = (int)e;                                  \
+    vd[np].first_edge = (int)s;                                        \
+    fa = a, fQ = Q, f_org = curr_org;                                  \
+    e = la; /* == Oprev(e) after the flip */                           \
+    re = Uu ^ 2u;                                                      \
+    curr_org = temp_dst;                                               \
+    ox = tx, oy = ty, on2 = tn2;                                       \
+  }
+  U32 fa = 0, fQ = 0, f_org = 0;
+  int left = max_edges;  // cv's loop runs at most max_edges iterations
+  for (;;) {
+    {
+      if (left-- <= 0) return;
+      AOS_APEX_TEST;
+      if (!do_flip) {
+        if (curr_org == (U32)first_point) return;
+        e = nx[nx[e]] ^ 2u;  // Lprev(Onext(e)) = Sym(next[next[e]]): ends at the old origin
+        re = rot(e);
+        dx = ox, dy = oy, dn2 = on2;
+        curr_org = pt[e];
+        const Vertex &o = vd[curr_org];
+        ox = o.x, oy = o.y, on2 = o.n2;
+        continue;
+      }
+      AOS_FLIP;
+    }
+    // e = (t -> d) is what the flip of (o -> d) left as current edge.  If its own test does not flip, the walk moves on
+    // to Sym(next[next[e]]), and the flip has just stored both links: next[e] = the flipped edge, next[that] = Sym a.
+    // So the next edge is a = (o -> t) with rot a = Sym Q: no loads but the old origin's coordinates.
+    for (;;) {
+      if (left-- <= 0) return;
+      AOS_APEX_TEST;
+      if (do_flip) {
+        AOS_FLIP;
+        continue;
+      }
+      if (curr_org == (U32)first_point) return;
+      e = fa;
+      re = fQ ^ 2u;
       dx = ox, dy = oy, dn2 = on2;
-      curr_org = pt[e];
+      curr_org = f_org;
       const Vertex &o = vd[curr_org];
       ox = o.x, oy = o.y, on2 = o.n2;
+      break;
     }
   }
+#undef AOS_APEX_TEST
+#undef AOS_FLIP
 }
 
 // intersection of the bisectors of (org0,dst0) and (org1,dst1): float differences and sums, double solve

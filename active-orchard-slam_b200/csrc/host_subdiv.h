@@ -51,6 +51,7 @@ class Subdiv {
   void splice(int a, int b);
   void set_edge_points(int edge, int org, int dst);
   int connect_edges(int a, int b);
+  int connect_inside_triangle(int e0, float px, float py);
   void flip_around(int curr_edge, int first_point, int curr_point, float px, float py);
   void flip_around_literal(int curr_edge, int first_point, int curr_point, float px, float py);
   int locate(float px, float py, int *edge, int *vertex);

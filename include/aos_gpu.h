@@ -255,8 +255,9 @@ AOS_API aos_status aos_set_subdiv_outer_factor(float factor);
 AOS_API aos_status aos_set_voronoi_mode(aos_ctx *ctx, int32_t mode);
 /* Current kernel-phase gate (aos_set_device_gate); aos_map_to_graph_batch restores it when it returns. */
 AOS_API int32_t aos_get_device_gate(void);
-/* Test switch (process-wide): make every Lawson flip of the replay run swapEdges' four literal splices instead of
- * the fused read-once / write-once update of the twelve `next` slots.  Same result; off by default. */
+/* Test switch (process-wide): run the replay's insert() in its literal form -- new_edge / splice / connect_edges for
+ * the new vertex, swapEdges' four splices for every Lawson flip, every operand re-read from the structure -- instead of
+ * the closed-form read-once / write-once slot updates.  Same result; off by default. */
 AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
 
 /* Kernel-phase gate, process-wide, off (0) by default: at most `max_concurrent` maps per device are admitted to the

@@ -87,7 +87,8 @@ def test_host_voronoi_reproduces_golden_facets():
 
 
 def test_literal_splice_path_gives_the_same_facets(oracle):
-    """swapEdges as four literal splices (the replay's guarded fallback) == the fused slot update == cv2."""
+    """The literal form of insert() (new_edge / splice / connect_edges, swapEdges as four splices: the switch
+    aos_set_subdiv_literal_splices) == the replay's closed-form slot updates == cv2."""
     from oracle import subdiv
     L = lib.load()
     rng = np.random.default_rng(321)
