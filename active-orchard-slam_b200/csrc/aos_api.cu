@@ -231,6 +231,27 @@ aos_status aos_set_stream(aos_ctx *c, void *cuda_stream) {
   return AOS_OK;
 }
 
+aos_status aos_set_host_wait(int device, int32_t blocking) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return AOS_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return AOS_ERR_INVALID;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (cudaSetDevice(device) != cudaSuccess) return AOS_ERR_CUDA;
+  unsigned flags = 0;
+  cudaError_t e = cudaGetDeviceFlags(&flags);
+  if (e == cudaSuccess) {
+    flags = (flags & ~(unsigned)cudaDeviceScheduleMask) | (blocking ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto);
+    e = cudaSetDeviceFlags(flags);
+  }
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return AOS_ERR_CUDA;
+  }
+  return AOS_OK;
+}
+
 aos_status aos_set_device_gate(int32_t max_concurrent) {
   g_device_gate_cap.store(max_concurrent > 0 ? max_concurrent : 0);
   for (auto &g : g_device_gates) g.cv.notify_all();

@@ -166,6 +166,9 @@ def bench_ours(args):
         from oracle import subdiv as _sd
         lib.load().aos_set_subdiv_outer_factor(ctypes.c_float(_sd.outer_factor()))
     lib.load().aos_set_device_gate(gate)   # maps admitted to the seed stage's kernel phase at a time (0 = no limit)
+    host_wait = "spin"
+    if T >= cores and lib.load().aos_set_host_wait(local, 1) == 0:
+        host_wait = "blocking during value/e2e (threads waiting for the GPU sleep), spinning for single_map"
     spec0 = synth.config(args.workload, seed=rank * 64, n_points=args.points)
     params = make_params(lib, spec0)
     gi = lib.grid_geometry(params)
@@ -236,6 +239,8 @@ def bench_ours(args):
     run_batch(min(args.warmup, 2), host=True)
     e2e_ms, info_h = timed(args.steps, host=True)
 
+    if host_wait != "spin":   # latency mode for what follows: a waiting thread spins (a wake-up costs ~50 us per wait)
+        lib.load().aos_set_host_wait(local, 0)
     # ---- one map at a time on one stream: latency per map, per-stage device times ------------------------
     c0 = ctxs[0]
     stream = torch.cuda.Stream(device=dev)
@@ -324,7 +329,7 @@ def bench_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 bit-planes / f32,f64 geometry", "data": "synthetic",
-            "config": workload_config(args, gi, spec0, n_pts, T=T, gate=gate, ncpu=ncpu, pinned=pinned,
+            "config": workload_config(args, gi, spec0, n_pts, T=T, gate=gate, ncpu=ncpu, pinned=pinned, host_wait=host_wait,
                                       pipeline=info.get("pipeline"), graph=info.get("graph")),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms / args.steps, 3),
                     "h2d_bytes_per_step": int(n_pts * 16) * T, "d2h_bytes_per_step": int(info_h.get("d2h_bytes", 0)) * T},
@@ -366,7 +371,7 @@ def workload_config(args, gi, spec, n_pts, **kw):
                        "(nominal; seeded synthetic orchard, SURVEY.md 8(d))"}
     if "T" in kw:
         T = kw["T"]
-        cfg.update({"maps_in_flight": T, "device_gate": kw["gate"],
+        cfg.update({"maps_in_flight": T, "device_gate": kw["gate"], "host_wait": kw.get("host_wait", "spin"),
                     "step": f"{T} independent maps per GPU, one per stream/host thread (the Subdiv2D replay of a map occupies a "
                             "host core; maps queueing for the GPU leave theirs to the others)",
                     "host_cores": kw["ncpu"],

@@ -260,6 +260,12 @@ AOS_API int32_t aos_get_device_gate(void);
  * the closed-form read-once / write-once slot updates.  Same result; off by default. */
 AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
 
+/* How host threads of this process wait for `device` (process-wide, per device): 0 = the CUDA default (a waiting thread
+ * spins on its core: lowest latency, right for a node that processes one map at a time), 1 = blocking waits
+ * (cudaDeviceScheduleBlockingSync: a thread waiting for the GPU sleeps and leaves its core to the Subdiv2D replays of the
+ * other maps in flight: right for batches with as many or more maps in flight than host cores).  Results do not change. */
+AOS_API aos_status aos_set_host_wait(int device, int32_t blocking);
+
 /* Kernel-phase gate, process-wide, off (0) by default: at most `max_concurrent` maps per device are admitted to the
  * seed stage's kernel phase (after the upload of their cloud) at a time; the others wait.  Identical maps in flight
  * on one GPU otherwise run in lockstep -- all in their kernel phase, time-slicing the GPU, then all in their host
