@@ -149,12 +149,12 @@ def bench_ours(args):
         torch.cuda.synchronize()
 
     ncpu = os.cpu_count() or 1
-    # One host thread per map in flight.  A map keeps a core busy during its Subdiv2D replay (0.2 s at C3) and leaves it
-    # idle while it waits for its turn on the GPU (its 9 ms of device stages, queued behind the other maps'), so the
-    # default is an eighth more maps in flight than this rank has cores (measured on 16 cores: 16 maps 23.2 k, 18 maps
-    # 27.3 k, 20 maps 27.4 k Mcells/s).
+    # One host thread per map in flight, as many maps as this rank has cores: a map keeps a core busy during its Subdiv2D
+    # replay (0.2 s at C3).  More maps than cores (--maps-in-flight) with sleeping instead of spinning waits
+    # (--host-wait blocking) fill the core a map leaves idle while it queues for the GPU, but measured on one box back to
+    # back it is a wash: 16 maps spinning 28.9 / 29.7 k, 18 spinning 25.7 k, 18 blocking 29.2 / 28.9 k Mcells/s.
     cores = max(1, min(16, ncpu // max(world, 1)))
-    T = args.maps_in_flight if args.maps_in_flight > 0 else cores + max(1, cores // 8)
+    T = args.maps_in_flight if args.maps_in_flight > 0 else cores
     if args.maps_in_flight <= 0:   # every map in flight holds its cloud twice (resident copy + e2e staging) plus grids
         spec_probe = synth.config(args.workload, n_points=args.points)
         per_map = 2 * 16 * spec_probe.n_points + 1.5e9
@@ -167,7 +167,8 @@ def bench_ours(args):
         lib.load().aos_set_subdiv_outer_factor(ctypes.c_float(_sd.outer_factor()))
     lib.load().aos_set_device_gate(gate)   # maps admitted to the seed stage's kernel phase at a time (0 = no limit)
     host_wait = "spin"
-    if T >= cores and lib.load().aos_set_host_wait(local, 1) == 0:
+    want_blocking = args.host_wait == "blocking" or (args.host_wait == "auto" and T > cores)
+    if want_blocking and lib.load().aos_set_host_wait(local, 1) == 0:
         host_wait = "blocking during value/e2e (threads waiting for the GPU sleep), spinning for single_map"
     spec0 = synth.config(args.workload, seed=rank * 64, n_points=args.points)
     params = make_params(lib, spec0)
@@ -807,6 +808,9 @@ def main():
     ap.add_argument("--device-gate", type=int, default=-1,
                     help="maps admitted to the seed stage's kernel phase at a time per GPU (aos_set_device_gate); 0 = no limit; "
                          "default 2 when at least 4 maps are in flight")
+    ap.add_argument("--host-wait", default="auto", choices=["auto", "spin", "blocking"],
+                    help="how threads wait for the GPU in the throughput legs (aos_set_host_wait); auto = blocking when more "
+                         "maps are in flight than this rank has cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-device-voronoi", action="store_true", help="skip the opt-in device-Voronoi sub-record")
     args = ap.parse_args()

@@ -122,6 +122,30 @@ def test_sweep_of_maps_in_flight(oracle):
         ctx.close()
 
 
+def test_blocking_host_waits_give_the_same_graph(oracle):
+    """aos_set_host_wait(device, 1): threads waiting for the GPU sleep instead of spinning (what bench.py runs its
+    throughput legs with); the switch is about scheduling only -- same graph, and it can be switched back."""
+    L = lib.load()
+    spec = synth.config("SMALL", seed=5)
+    pts = synth.make_orchard(spec)
+    po, pl = params_pair(spec, oracle)
+    r = oracle.seed_stage(po, pts)
+    ref = _oracle_graph(oracle, r)
+    assert L.aos_set_host_wait(99, 1) != 0            # no such device
+    try:
+        assert L.aos_set_host_wait(0, 1) == 0
+        ctx = lib.Context(0)
+        ctx.map_to_graph(pl, pts)
+        assert_graph_parity(ctx.graph(), ref)
+        d_blocking = ctx.result_digest()
+        assert L.aos_set_host_wait(0, 0) == 0
+        ctx.map_to_graph(pl, pts)
+        assert ctx.result_digest() == d_blocking
+        ctx.close()
+    finally:
+        L.aos_set_host_wait(0, 0)
+
+
 def test_inflation_radius_beyond_the_stencil(gpu_ctx, oracle):
     """R = 80 cells (> 64): the seed stage switches to the EDT threshold for applyInflation; still bit-exact."""
     spec = synth.OrchardSpec(extent_x=30.0, extent_y=20.0, row_pitch=7.0, tree_spacing=4.0, n_points=60_000, outlier_count=2,
