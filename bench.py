@@ -801,6 +801,7 @@ def main():
                     help="maps: independent maps per GPU (default, weak scaling) followed by the config-4 band run as the "
                          "`bands` sub-record; bands: only the band run, as the bench line")
     ap.add_argument("--no-bands", action="store_true", help="skip the config-4 band sub-record of the default run")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 sweep sub-record of the default run")
     ap.add_argument("--bands-workload", default="C4")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="(kept for compatibility; the CPU leg runs one full map)")
     ap.add_argument("--reference-budget", type=float, default=420.0,
@@ -838,6 +839,18 @@ def main():
             rec = run_bands(args, args.bands_workload, max(1, min(args.steps, 5)), 2, args.halo)
             if line is not None:
                 line["bands"] = rec
+        if not args.no_sweep and args.workload.upper() == "C3" and args.points is None:
+            # BASELINE config 5 (256 independent small maps, map i on rank i mod N) in the same driver-visible run
+            import copy
+            a5 = copy.copy(args)
+            a5.steps, a5.warmup, a5.maps_in_flight = max(1, min(args.steps, 3)), 2, 0   # contexts reach their buffer sizes in two sweeps
+            rec5 = bench_sweep(a5)
+            if line is not None and rec5 is not None:
+                line["sweep"] = {"workload": rec5["config"]["workload"], "maps_in_flight": rec5["config"]["maps_in_flight"],
+                                 "steps": rec5["steps"], "warmup": rec5["warmup"], "scaling": rec5["scaling"],
+                                 "ms_per_sweep": rec5["ms_per_step"], "maps_per_s": rec5["config"]["maps_per_s"],
+                                 "value": rec5["value"], "unit": rec5["unit"], "e2e": rec5["e2e"],
+                                 "gpu_launches_per_sweep": rec5["gpu_launches"], "clocks": rec5["clocks"]}
     if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:
