@@ -200,8 +200,8 @@ int Subdiv::locate(float px, float py, int *out_edge, int *out_vertex) {
     const double e1x = c1.x - pxd, e1y = c1.y - pyd;
     const double cw_onext = e1x * eoy - e1y * eox;  // sign = isRightOf(p, onext)
     if (cw_onext > 0 || on_curr) {
-      U32 dprev = nx[(edge & ~3u) | ((edge + 3u) & 3u)];
-      dprev = (dprev & ~3u) | ((dprev + 3u) & 3u);
+      U32 dprev = nx[edge ^ (3u - ((edge & 1u) << 1))];  // InvRot: r -> r + 3 mod 4 = xor with 11 (r even) or 01 (r odd)
+      dprev ^= 3u - ((dprev & 1u) << 1);
       const Vertex &c2 = vd[pt[dprev]];
       const double e2x = c2.x - pxd, e2y = c2.y - pyd;
       const double cw_dprev = edx * e2y - edy * e2x;  // sign = isRightOf(p, dprev)
@@ -399,7 +399,8 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, int curr_point, float
   U32 *const pt = reinterpret_cast<U32 *>(pt_.data());
   Vertex *const vd = vtx_.data();
   const int max_edges = (int)next_.size();
-  auto rot = [](U32 e) -> U32 { return (e & ~3u) | ((e + 1u) & 3u); };
+  // rot: r -> r + 1 mod 4 in the two low bits = xor with 01 (r even) or 11 (r odd)
+  auto rot = [](U32 e) -> U32 { return e ^ (((e & 1u) << 1) | 1u); };
   const double pxx = (double)px * px + (double)py * py;
   const double pxd = px, pyd = py;
   const double eps = FLT_EPSILON * 0.125;
@@ -412,12 +413,14 @@ void Subdiv::flip_around(int curr_edge_i, int first_point, int curr_point, float
     ox = o.x, oy = o.y, on2 = o.n2;
     dx = d.x, dy = d.y, dn2 = d.n2;
   }
-  // One iteration's test: the apex t across e -- a = Oprev(e) = rot(next[rot e]), t = dst(a) -- and
+  // One iteration's test: the apex t across e -- a = Oprev(e) = rot(next[rot e]), t = dst(a) = org(Sym a) with
+  // Sym a = InvRot(next[rot e]) (r -> r + 3 mod 4 = xor with 11 for even r, 01 for odd r) -- and
   // isRightOf(t, e) > 0 && isPtInCircle3(org, t, dst, p) < 0.  isRightOf is the sign of triangleArea(t, dst, org); the
   // same determinant is the third term of isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated once.
 #define AOS_APEX_TEST                                                  \
-  const U32 Q = nx[re], a = rot(Q);                                    \
-  const U32 temp_dst = pt[a ^ 2u];                                     \
+  const U32 Q = nx[re];                                                \
+  const U32 sym_a = Q ^ (3u - ((Q & 1u) << 1)), a = sym_a ^ 2u;        \
+  const U32 temp_dst = pt[sym_a];                                      \
   const Vertex &t = vd[temp_dst];                                      \
   const double tx = t.x, ty = t.y, tn2 = t.n2;                         \
   const double area_tdo = tri_aread(tx, ty, dx, dy, ox, oy);           \
