@@ -48,6 +48,40 @@ def test_voronoi_facets_match_cv2_bit_for_bit(oracle, block):
         assert np.array_equal(fx.view(np.uint32), gx.view(np.uint32)), f"facet vertices differ (block {block} trial {trial})"
 
 
+def _hard_seed_sets(rng, trial):
+    """Sets aimed at the replay's rare paths (scripts/dev/subdiv_stress.py runs the same generators by the 100 k)."""
+    n = int(rng.integers(1, 500))
+    mode = trial % 6
+    if mode == 0:    # exact lattice in random order: points on existing edges, co-circular quadruples, duplicates
+        return np.stack([rng.integers(0, 25, n) * 2.0, rng.integers(0, 20, n) * 2.0], 1) + 1.0
+    if mode == 1:    # one exactly collinear line, 5 cm steps, wrapping around (every point on an edge)
+        return np.stack([np.arange(n) * 0.05 % 45 + 1, np.full(n, 7.0)], 1)
+    if mode == 2:    # tight clusters: near-duplicates 0.1 mm apart
+        c = rng.uniform(5, 45, (8, 2))
+        return c[rng.integers(0, 8, n)] + rng.normal(0, 1e-4, (n, 2))
+    if mode == 3:    # co-circular points
+        t = rng.uniform(0, 2 * np.pi, n)
+        return np.stack([25 + 10 * np.cos(t), 20 + 10 * np.sin(t)], 1)
+    if mode == 4:    # pairs one micrometre apart (LOC_VERTEX / tiny triangles)
+        s = rng.uniform(1, 49, (n, 2))
+        s[1::2] = s[::2][: len(s[1::2])] + 1e-6
+        return s
+    x = np.sort(rng.uniform(1, 49, n))   # a monotone curve: every insertion takes over a long fan
+    return np.stack([x, 5 + 0.3 * np.sin(x)], 1)
+
+
+def test_voronoi_facets_match_cv2_on_degenerate_sets(oracle):
+    from oracle import subdiv
+    rng = np.random.default_rng(4242)
+    for trial in range(240):
+        s = _hard_seed_sets(rng, trial)
+        b = (0.0, 50.0, 0.0, 40.0) if trial % 3 else (-4.5, 72.8, -2.4, 42.4)
+        fx, fo, _ = subdiv.voronoi_facets(s, *b)
+        gx, go = lib.voronoi_facets(s, *b)
+        assert np.array_equal(fo, go), f"facet sizes differ (trial {trial})"
+        assert np.array_equal(fx.view(np.uint32), gx.view(np.uint32)), f"facet vertices differ (trial {trial})"
+
+
 def test_voronoi_facets_empty_and_invalid_bounds():
     xy, off = lib.voronoi_facets(np.zeros((0, 2)), 0, 10, 0, 10)
     assert len(xy) == 0 and list(off) == [0]
