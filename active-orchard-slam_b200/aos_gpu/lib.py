@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "aos_gvd_stage", "aos_gvd_stage_bits", "aos_get_graph", "aos_map_to_graph", "aos_map_to_graph_batch", "aos_merge_seeds", "aos_voronoi_facets", "aos_voronoi_facets_device", "aos_merge_seeds_device", "aos_trim_path", "aos_set_subdiv_outer_factor", "aos_set_subdiv_literal_splices", "aos_set_device_gate",
     "aos_radius_outlier_removal", "aos_edt_bits", "aos_inflate_bits_edt", "aos_set_clearance", "aos_band_halo_rows", "aos_band_raster", "aos_band_thin_launch", "aos_band_ipc_export", "aos_band_ipc_import",
     "aos_band_thin_launch_p2p", "aos_band_grid_device", "aos_seed_stage_tail", "aos_band_ipc_release", "aos_get_device_gate", "aos_set_voronoi_mode",
-    "aos_set_host_wait",
+    "aos_set_host_wait", "aos_set_subdiv_simd",
 ]
 
 
@@ -163,6 +163,7 @@ def load() -> C.CDLL:
     L.aos_set_voronoi_mode.argtypes = [vp, i32]
     L.aos_get_device_gate.restype = i32
     L.aos_set_host_wait.argtypes = [C.c_int, i32]
+    L.aos_set_subdiv_simd.argtypes = [i32]
     L.aos_band_grid_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.aos_seed_stage_tail.argtypes = [vp, C.POINTER(CSeedParams), vp, vp]
     L.aos_map_to_graph_batch.argtypes = [C.POINTER(CBatchItem), i32, i32]

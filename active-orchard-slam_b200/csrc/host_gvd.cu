@@ -129,6 +129,13 @@ aos_status aos_set_subdiv_literal_splices(int32_t on) {
   aos::g_literal_splices = on != 0;
   return AOS_OK;
 }
+aos_status aos_set_subdiv_simd(int32_t mode) {
+  if (mode < -1 || mode > 1) return AOS_ERR_INVALID;
+  if (mode == 1 && !aos::subdiv_simd_available()) return AOS_ERR_INVALID;
+  aos::g_subdiv_simd = mode;
+  return AOS_OK;
+}
+
 
 aos_status aos_merge_seeds(const double *seeds_xy, int32_t n, double *out_xy, int32_t *n_out) {
   if (n < 0 || (n > 0 && (!seeds_xy || !out_xy))) return AOS_ERR_INVALID;

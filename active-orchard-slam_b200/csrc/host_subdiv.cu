@@ -19,6 +19,9 @@
 // flat arrays indexed by the id itself; vertices carry their float32 coordinates widened to double plus |v|^2.
 #include <float.h>
 #include <math.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <utility>
 
@@ -52,6 +55,17 @@ inline double tri_area(float ax, float ay, float bx, float by, float cx, float c
 
 float g_outer_factor = 3.f;  // OpenCV <= 4.5.x (the reference's platform); see aos_set_subdiv_outer_factor
 bool g_literal_splices = false;  // see aos_set_subdiv_literal_splices (tests: take swapEdges' literal splice sequence)
+int g_subdiv_simd = -1;  // see aos_set_subdiv_simd: -1 = AVX2 flip loop where the CPU has it, 0 = scalar, 1 = AVX2
+
+bool subdiv_simd_available() {
+#if defined(__x86_64__)
+  static const bool have = __builtin_cpu_supports("avx2") != 0;
+  return have;
+#else
+  return false;
+#endif
+}
+static inline bool subdiv_simd_on() { return g_subdiv_simd != 0 && subdiv_simd_available(); }
 
 void Subdiv::init(int rx_i, int ry_i, int rw, int rh) {
   vtx_.clear();
@@ -391,117 +405,75 @@ void Subdiv::flip_around_literal(int curr_edge, int first_point, int curr_point,
 // per flip.  With Q = next[rot e], Q2 = next[rot Sym e], U = next[Q], U2 = next[Q2]:
 //   a = Oprev(e) = rot Q, b = Oprev(Sym e) = rot Q2, InvRot a = Q, InvRot b = Q2, la = Lnext(a) = rot U,
 //   lb = Lnext(b) = rot U2, rot Onext(Sym e) = U, rot Onext(e) = U2.
-void Subdiv::flip_around(int curr_edge_i, int first_point, int curr_point, float px, float py) {
-  if (g_literal_splices) return flip_around_literal(curr_edge_i, first_point, curr_point, px, py);
-  // edge ids and vertex ids are non-negative: unsigned arithmetic keeps the index computations free of sign extensions
-  typedef unsigned U32;
-  U32 *const nx = reinterpret_cast<U32 *>(next_.data());
-  U32 *const pt = reinterpret_cast<U32 *>(pt_.data());
-  Vertex *const vd = vtx_.data();
-  const int max_edges = (int)next_.size();
-  // rot: r -> r + 1 mod 4 in the two low bits = xor with 01 (r even) or 11 (r odd)
-  auto rot = [](U32 e) -> U32 { return e ^ (((e & 1u) << 1) | 1u); };
-  const double pxx = (double)px * px + (double)py * py;
-  const double pxd = px, pyd = py;
-  const double eps = FLT_EPSILON * 0.125;
-  const U32 np = (U32)curr_point;
-  U32 e = (U32)curr_edge_i, re = rot(e);
-  U32 curr_org = pt[e];
-  double ox, oy, on2, dx, dy, dn2;
-  {
-    const Vertex &o = vd[curr_org], &d = vd[pt[e ^ 2u]];
-    ox = o.x, oy = o.y, on2 = o.n2;
-    dx = d.x, dy = d.y, dn2 = d.n2;
-  }
-  // One iteration's test: the apex t across e -- a = Oprev(e) = rot(next[rot e]), t = dst(a) = org(Sym a) with
-  // Sym a = InvRot(next[rot e]) (r -> r + 3 mod 4 = xor with 11 for even r, 01 for odd r) -- and
-  // isRightOf(t, e) > 0 && isPtInCircle3(org, t, dst, p) < 0.  isRightOf is the sign of triangleArea(t, dst, org); the
-  // same determinant is the third term of isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated once.
-#define AOS_APEX_TEST                                                  \
-  const U32 Q = nx[re];                                                \
-  const U32 sym_a = Q ^ (3u - ((Q & 1u) << 1)), a = sym_a ^ 2u;        \
-  const U32 temp_dst = pt[sym_a];                                      \
-  const Vertex &t = vd[temp_dst];                                      \
-  const double tx = t.x, ty = t.y, tn2 = t.n2;                         \
+#define AOS_GEOM_DECL double ox, oy, on2, dx, dy, dn2
+#define AOS_GEOM_INIT(o, d) (ox = (o).x, oy = (o).y, on2 = (o).n2, dx = (d).x, dy = (d).y, dn2 = (d).n2)
+// isRightOf is the sign of triangleArea(t, dst, org); the same determinant is the third term of
+// isPtInCircle3(pt = org, a = t, b = dst, c = p), evaluated once
+#define AOS_GEOM_TEST(t)                                               \
+  const double tx = (t).x, ty = (t).y, tn2 = (t).n2;                   \
   const double area_tdo = tri_aread(tx, ty, dx, dy, ox, oy);           \
   double val = tn2 * tri_aread(dx, dy, pxd, pyd, ox, oy);              \
   val -= dn2 * tri_aread(tx, ty, pxd, pyd, ox, oy);                    \
   val += pxx * area_tdo;                                               \
   val -= on2 * tri_aread(tx, ty, dx, dy, pxd, pyd);                    \
   const bool do_flip = (area_tdo > 0) & (val < -eps)
-  // swapEdges(e) and curr_edge = Oprev(e).  Loads and stores in an order that lets every value die early (the twelve
-  // slots are distinct: six edges of the two triangles and six of their duals).  Leaves behind what the step after
-  // the next test needs if that test does not flip: fa = a, fQ = Q, f_org = the origin e had.
-#define AOS_FLIP                                                       \
-  {                                                                    \
-    const U32 rs = re ^ 2u;                                            \
-    const U32 Q2 = nx[rs], Uu = nx[Q], U2 = nx[Q2];                    \
-    const U32 P = nx[U2]; /* the slot rot Onext(e) */                  \
-    nx[U2] = Q;                                                        \
-    nx[re] = Uu;                                                       \
-    nx[Q] = P;                                                         \
-    const U32 P2 = nx[Uu]; /* the slot rot Onext(Sym e) */             \
-    nx[Uu] = Q2;                                                       \
-    nx[rs] = U2;                                                       \
-    nx[Q2] = P2;                                                       \
-    const U32 s = e ^ 2u, b = rot(Q2), la = rot(Uu), lb = rot(U2);     \
-    nx[e] = a ^ 2u;                                                    \
-    nx[a] = lb ^ 2u; /* Onext(e) */                                    \
-    nx[lb] = s;                                                        \
-    nx[s] = b ^ 2u;                                                    \
-    nx[b] = la ^ 2u; /* Onext(Sym e) */                                \
-    nx[la] = e;                                                        \
-    pt[e] = temp_dst;                                                  \
-    pt[s] = np;                                                        \
-    vd[temp_dst].first_edge = (int)e;                                  \
-    vd[np].first_edge = (int)s;                                        \
-    fa = a, fQ = Q, f_org = curr_org;                                  \
-    e = la; /* == Oprev(e) after the flip */                           \
-    re = Uu ^ 2u;                                                      \
-    curr_org = temp_dst;                                               \
-    ox = tx, oy = ty, on2 = tn2;                                       \
-  }
-  U32 fa = 0, fQ = 0, f_org = 0;
-  int left = max_edges;  // cv's loop runs at most max_edges iterations
-  for (;;) {
-    {
-      if (left-- <= 0) return;
-      AOS_APEX_TEST;
-      if (!do_flip) {
-        if (curr_org == (U32)first_point) return;
-        e = nx[nx[e]] ^ 2u;  // Lprev(Onext(e)) = Sym(next[next[e]]): ends at the old origin
-        re = rot(e);
-        dx = ox, dy = oy, dn2 = on2;
-        curr_org = pt[e];
-        const Vertex &o = vd[curr_org];
-        ox = o.x, oy = o.y, on2 = o.n2;
-        continue;
-      }
-      AOS_FLIP;
-    }
-    // e = (t -> d) is what the flip of (o -> d) left as current edge.  If its own test does not flip, the walk moves on
-    // to Sym(next[next[e]]), and the flip has just stored both links: next[e] = the flipped edge, next[that] = Sym a.
-    // So the next edge is a = (o -> t) with rot a = Sym Q: no loads but the old origin's coordinates.
-    for (;;) {
-      if (left-- <= 0) return;
-      AOS_APEX_TEST;
-      if (do_flip) {
-        AOS_FLIP;
-        continue;
-      }
-      if (curr_org == (U32)first_point) return;
-      e = fa;
-      re = fQ ^ 2u;
-      dx = ox, dy = oy, dn2 = on2;
-      curr_org = f_org;
-      const Vertex &o = vd[curr_org];
-      ox = o.x, oy = o.y, on2 = o.n2;
-      break;
-    }
-  }
-#undef AOS_APEX_TEST
-#undef AOS_FLIP
+#define AOS_GEOM_FLIPPED (ox = tx, oy = ty, on2 = tn2)
+#define AOS_GEOM_ADVANCED(o) (dx = ox, dy = oy, dn2 = on2, ox = (o).x, oy = (o).y, on2 = (o).n2)
+void Subdiv::flip_around(int curr_edge_i, int first_point, int curr_point, float px, float py) {
+  if (g_literal_splices) return flip_around_literal(curr_edge_i, first_point, curr_point, px, py);
+#if defined(__x86_64__)
+  if (subdiv_simd_on()) return flip_around_avx2(curr_edge_i, first_point, curr_point, px, py);
+#endif
+#include "host_subdiv_flip.inc"
 }
+#undef AOS_GEOM_DECL
+#undef AOS_GEOM_INIT
+#undef AOS_GEOM_TEST
+#undef AOS_GEOM_FLIPPED
+#undef AOS_GEOM_ADVANCED
+
+#if defined(__x86_64__)
+// The same loop with the four triangle areas of the in-circle test in the four lanes of one AVX2 register.  Lane k
+// evaluates (M - B) x (N - B) with  M = [p, p, d, d],  B = [d, t, t, t],  N = [o, o, o, p]:
+//   A0 = area(d, p, o), A1 = area(t, p, o), A2 = area(t, d, o) (= isRightOf's determinant), A3 = area(t, d, p),
+// every lane with the operations of tri_aread in their order, then W = [|t|^2, |d|^2, |p|^2, |o|^2] times A and the sum
+// ((W0 A0 - W1 A1) + W2 A2) - W3 A3 in the scalar order: bit for bit the value of the scalar loop.  M, N and W are
+// kept across iterations and re-blended where an end point changes (a flip changes o, a step changes both).
+#define AOS_GEOM_DECL __m256d PXv, PYv, Mx, My, Nx, Ny, Dx, Dy, Wb
+#define AOS_GEOM_INIT(o, d)                                                                                   \
+  (PXv = _mm256_set1_pd(pxd), PYv = _mm256_set1_pd(pyd), Dx = _mm256_broadcast_sd(&(d).x),                    \
+   Dy = _mm256_broadcast_sd(&(d).y), Mx = _mm256_blend_pd(PXv, Dx, 12), My = _mm256_blend_pd(PYv, Dy, 12),    \
+   Nx = _mm256_blend_pd(_mm256_broadcast_sd(&(o).x), PXv, 8), Ny = _mm256_blend_pd(_mm256_broadcast_sd(&(o).y), PYv, 8), \
+   Wb = _mm256_blend_pd(_mm256_blend_pd(_mm256_set1_pd(pxx), _mm256_broadcast_sd(&(d).n2), 2), _mm256_broadcast_sd(&(o).n2), 8))
+#define AOS_GEOM_TEST(t)                                                                                      \
+  const __m256d Tx = _mm256_broadcast_sd(&(t).x), Ty = _mm256_broadcast_sd(&(t).y), Tn = _mm256_broadcast_sd(&(t).n2); \
+  const __m256d Bx = _mm256_blend_pd(Tx, Dx, 1), By = _mm256_blend_pd(Ty, Dy, 1);                             \
+  const __m256d Ux = _mm256_sub_pd(Mx, Bx), Vy = _mm256_sub_pd(Ny, By);                                       \
+  const __m256d Uy = _mm256_sub_pd(My, By), Vx = _mm256_sub_pd(Nx, Bx);                                       \
+  const __m256d Ar = _mm256_sub_pd(_mm256_mul_pd(Ux, Vy), _mm256_mul_pd(Uy, Vx));                             \
+  const __m256d Wa = _mm256_mul_pd(_mm256_blend_pd(Wb, Tn, 1), Ar);                                           \
+  const __m128d w_lo = _mm256_castpd256_pd128(Wa), w_hi = _mm256_extractf128_pd(Wa, 1);                       \
+  __m128d val = _mm_sub_sd(w_lo, _mm_unpackhi_pd(w_lo, w_lo));                                                \
+  val = _mm_add_sd(val, w_hi);                                                                                \
+  val = _mm_sub_sd(val, _mm_unpackhi_pd(w_hi, w_hi));                                                         \
+  const bool do_flip = (_mm_cvtsd_f64(_mm256_extractf128_pd(Ar, 1)) > 0) & (_mm_cvtsd_f64(val) < -eps)
+#define AOS_GEOM_FLIPPED (Nx = _mm256_blend_pd(Tx, PXv, 8), Ny = _mm256_blend_pd(Ty, PYv, 8), Wb = _mm256_blend_pd(Wb, Tn, 8))
+// d := o (lane 0 of N), o := the record; W's |d|^2 lane takes the old |o|^2 (lane 3 -> lane 1)
+#define AOS_GEOM_ADVANCED(o)                                                                                  \
+  (Dx = _mm256_broadcastsd_pd(_mm256_castpd256_pd128(Nx)), Dy = _mm256_broadcastsd_pd(_mm256_castpd256_pd128(Ny)), \
+   Mx = _mm256_blend_pd(PXv, Dx, 12), My = _mm256_blend_pd(PYv, Dy, 12),                                      \
+   Nx = _mm256_blend_pd(_mm256_broadcast_sd(&(o).x), PXv, 8), Ny = _mm256_blend_pd(_mm256_broadcast_sd(&(o).y), PYv, 8), \
+   Wb = _mm256_blend_pd(_mm256_permute4x64_pd(Wb, 0xEC), _mm256_broadcast_sd(&(o).n2), 8))
+__attribute__((target("avx2"))) void Subdiv::flip_around_avx2(int curr_edge_i, int first_point, int curr_point, float px,
+                                                              float py) {
+#include "host_subdiv_flip.inc"
+}
+#undef AOS_GEOM_DECL
+#undef AOS_GEOM_INIT
+#undef AOS_GEOM_TEST
+#undef AOS_GEOM_FLIPPED
+#undef AOS_GEOM_ADVANCED
+#endif
 
 // intersection of the bisectors of (org0,dst0) and (org1,dst1): float differences and sums, double solve
 bool Subdiv::voronoi_point(const Vertex &vo0, const Vertex &vd0, const Vertex &vo1, const Vertex &vd1, float *x, float *y) {

@@ -8,6 +8,8 @@ namespace aos {
 
 extern float g_outer_factor;
 extern bool g_literal_splices;
+extern int g_subdiv_simd;
+bool subdiv_simd_available();
 
 class Subdiv {
  public:
@@ -54,6 +56,7 @@ class Subdiv {
   int connect_inside_triangle(int e0, float px, float py);
   void flip_around(int curr_edge, int first_point, int curr_point, float px, float py);
   void flip_around_literal(int curr_edge, int first_point, int curr_point, float px, float py);
+  void flip_around_avx2(int curr_edge, int first_point, int curr_point, float px, float py);
   int locate(float px, float py, int *edge, int *vertex);
   static bool voronoi_point(const Vertex &o0, const Vertex &d0, const Vertex &o1, const Vertex &d1, float *x, float *y);
   void calc_voronoi();

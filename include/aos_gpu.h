@@ -260,6 +260,12 @@ AOS_API int32_t aos_get_device_gate(void);
  * the closed-form read-once / write-once slot updates.  Same result; off by default. */
 AOS_API aos_status aos_set_subdiv_literal_splices(int32_t on);
 
+/* Test switch (process-wide): which copy of the replay's flip loop runs.  -1 (default) = the AVX2 one where the CPU has
+ * AVX2 (the four triangle areas of the in-circle test in the four lanes of one register, every lane with the scalar
+ * operations in their order), 0 = the scalar one, 1 = AVX2 (AOS_ERR_INVALID on a CPU without it).  Same result, bit
+ * for bit (tests/test_subdiv_cpu.py). */
+AOS_API aos_status aos_set_subdiv_simd(int32_t mode);
+
 /* How host threads of this process wait for `device` (process-wide, per device): 0 = the CUDA default (a waiting thread
  * spins on its core: lowest latency, right for a node that processes one map at a time), 1 = blocking waits
  * (cudaDeviceScheduleBlockingSync: a thread waiting for the GPU sleeps and leaves its core to the Subdiv2D replays of the

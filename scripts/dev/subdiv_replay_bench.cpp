@@ -23,6 +23,7 @@ int main(int argc,char**argv){
   minx-=1;maxx+=1;miny-=1;maxy+=1;
   const float rx = (float)(minx - 1.0), ry = (float)(miny - 1.0);
   const float rw = (float)(fabs(maxx - minx) + 2.0), rh = (float)(fabs(maxy - miny) + 2.0);
+  if (argc > 1 && !strcmp(argv[1], "scalar")) aos::g_subdiv_simd = 0;  // the scalar flip loop instead of the AVX2 one
   for(int it=0;it<7;it++){
     g_flip=g_pred=g_loc=g_conn=0;
     auto t0=std::chrono::steady_clock::now();

@@ -141,6 +141,33 @@ def test_literal_splice_path_gives_the_same_facets(oracle):
         L.aos_set_subdiv_literal_splices(0)
 
 
+def test_scalar_and_avx2_flip_loops_give_the_same_facets(oracle):
+    """aos_set_subdiv_simd: the scalar flip loop and the AVX2 one (four triangle areas per register) == cv2."""
+    from oracle import subdiv
+    L = lib.load()
+    rng = np.random.default_rng(99)
+    modes = [0] + ([1] if L.aos_set_subdiv_simd(1) == 0 else [])
+    try:
+        for trial in range(60):
+            s = _hard_seed_sets(rng, trial) if trial % 2 else _seed_sets(rng, trial)
+            b = (0.0, 50.0, 0.0, 40.0)
+            fx, fo, _ = subdiv.voronoi_facets(s, *b)
+            for m in modes:
+                assert L.aos_set_subdiv_simd(m) == 0
+                gx, go = lib.voronoi_facets(s, *b)
+                assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32)), (trial, m)
+        # the map-order pattern (long fans) in the scalar loop; the default mode runs it in the tests below
+        assert L.aos_set_subdiv_simd(0) == 0
+        s = _orchard_seed_order(rng, 12, 300)
+        b = (0.0, 400.0, 0.0, 60.0)
+        fx, fo, _ = subdiv.voronoi_facets(s, *b)
+        gx, go = lib.voronoi_facets(s, *b)
+        assert np.array_equal(fo, go) and np.array_equal(fx.view(np.uint32), gx.view(np.uint32))
+        assert L.aos_set_subdiv_simd(2) != 0
+    finally:
+        L.aos_set_subdiv_simd(-1)
+
+
 def _orchard_seed_order(rng, n_rows, per_row, pitch=4.0, half=1.95):
     """Seeds in the order a real map produces them: row after row, walking along the row, alternating between the two
     sides of the tree line (the insertion pattern with ~55 Lawson flips per seed that the replay's hot loop is tuned for)."""
